@@ -1,0 +1,631 @@
+// artes_gpu.cu -- host side of the C-ABI declared in include/artes_gpu.h.
+//
+// Owns the device contexts, turns the reference's program-scope arrays into HBM-resident tables
+// (SoA, de-duplicated matrices), launches the sm_100a transport kernels and reduces the per-device
+// accumulators with NCCL (loaded lazily with dlopen so that a single-GPU run needs no NCCL at all).
+// There is no CPU fallback: every entry point fails if no CUDA device is usable.
+
+#include "../../include/artes_gpu.h"
+#include "kernel_args.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace artes {
+namespace faithful {
+size_t smem_bytes(int nr, int nt, int np);
+cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
+                             const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
+}  // namespace faithful
+namespace fast {
+size_t smem_bytes(int nr, int nt, int np);
+cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
+                             const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
+}  // namespace fast
+cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
+}  // namespace artes
+
+using namespace artes;
+
+namespace {
+
+const double PI = 4.0 * std::atan(1.0);
+std::string g_create_error;
+
+// ---- lazily bound NCCL -------------------------------------------------------------------------
+struct Nccl {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string err;
+    bool load() {
+        if (ok) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (handle) break; }
+        if (!handle) for (const char* n : names) { handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
+        if (!handle) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define BIND(sym) sym = reinterpret_cast<decltype(sym)>(dlsym(handle, "nccl" #sym)); if (!sym) { err = "missing symbol nccl" #sym; return false; }
+        BIND(GetUniqueId) BIND(CommInitRank) BIND(CommInitAll) BIND(CommDestroy) BIND(AllReduce) BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
+#undef BIND
+        ok = true;
+        return true;
+    }
+};
+Nccl g_nccl;
+
+struct DeviceState {
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // kernel start/stop, reduce stop, spare
+    std::vector<void*> grid_allocs, wl_allocs;
+    DevTables T{};
+    double* out_d = nullptr;               // [det 10*npx | flux 2 | flow4 4*cells | flow3 3*cells]
+    size_t out_d_cap = 0;
+    unsigned long long* out_u = nullptr;   // [err 64 | stats 8 | counter 1]
+    ncclComm_t comm = nullptr;
+    unsigned long long n_photons = 0;
+};
+
+}  // namespace
+
+struct artes_gpu_ctx {
+    std::vector<DeviceState> devs;
+    std::string error;
+    bool have_grid = false, have_wl = false, thermal = false;
+    int nr = 0, nt = 0, np = 0, cells = 0;
+    // host copies needed to rebuild per-wavelength tables
+    std::vector<double> sinbeta, cos2beta, sin2beta;
+    // NCCL across processes
+    int nranks = 1, rank = 0;
+    bool rank_comm = false;
+    // pending async launch
+    bool pending = false;
+    artes_launch_t pending_launch{};
+    size_t n_out_d = 0;
+    double last_h2d_ms = 0.0;
+};
+
+namespace {
+
+int fail(artes_gpu_ctx* c, int code, const std::string& msg) {
+    if (c) c->error = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(ctx, -2, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+#define NC(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return fail(ctx, -4, std::string(#call) + ": " + g_nccl.GetErrorString(r__)); } while (0)
+
+template <typename Tp>
+int upload(artes_gpu_ctx* ctx, DeviceState& d, std::vector<void*>& pool, const Tp* host, size_t n, const Tp** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(Tp);
+    CU(cudaMalloc(&p, bytes));
+    pool.push_back(p);
+    if (n) CU(cudaMemcpyAsync(p, host, n * sizeof(Tp), cudaMemcpyHostToDevice, d.stream));
+    *out = static_cast<const Tp*>(p);
+    return 0;
+}
+
+void free_pool(std::vector<void*>& pool) {
+    for (void* p : pool) cudaFree(p);
+    pool.clear();
+}
+
+int ensure_outputs(artes_gpu_ctx* ctx, DeviceState& d, size_t n_d) {
+    if (!d.out_u) CU(cudaMalloc(&d.out_u, (ARTES_ERR_SLOTS + 8 + 8) * sizeof(unsigned long long)));
+    if (n_d > d.out_d_cap) {
+        if (d.out_d) cudaFree(d.out_d);
+        d.out_d = nullptr;
+        CU(cudaMalloc(&d.out_d, n_d * sizeof(double)));
+        d.out_d_cap = n_d;
+    }
+    return 0;
+}
+
+// LaunchArgs from the ABI struct: host-evaluated detector / star geometry (src/ARTES.f90:495-502, 1080-1109, 4628, 4871)
+void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
+    a.n_photons = L.n_photons; a.id_base = L.photon_id_base; a.seed = L.seed;
+    a.photon_source = L.photon_source; a.photon_scattering = L.photon_scattering; a.photon_emission = L.photon_emission;
+    a.stellar_direction = L.stellar_direction; a.limb_emission = L.limb_emission;
+    a.flow_global = L.flow_global; a.flow_theta = L.flow_theta; a.nx = L.nx; a.ny = L.ny;
+    a.fstop = L.fstop; a.photon_minimum = L.photon_minimum; a.photon_bias = L.photon_bias;
+    a.surface_albedo = L.surface_albedo; a.theta_star = L.theta_star; a.phi_star = L.phi_star;
+    a.x_max = L.x_max; a.y_max = L.y_max;
+    a.det[0] = 1.0 * std::sin(L.det_theta) * std::cos(L.det_phi);
+    a.det[1] = 1.0 * std::sin(L.det_theta) * std::sin(L.det_phi);
+    a.det[2] = 1.0 * std::cos(L.det_theta);
+    a.sin_dt = std::sin(L.det_theta); a.cos_dt = std::cos(L.det_theta);
+    a.sin_dp = std::sin(L.det_phi); a.cos_dp = std::cos(L.det_phi);
+    double pn = std::atan2(a.det[1], a.det[0]);
+    if (pn < 0.0) pn = pn + 2.0 * PI;
+    if (pn > 2.0 * PI) pn = pn - 2.0 * PI;
+    a.det_atan2 = pn;
+    double r = std::sqrt(a.det[0] * a.det[0] + a.det[1] * a.det[1] + a.det[2] * a.det[2]);
+    a.det_sph_theta = std::acos(a.det[2] / r);
+    double ph = std::atan2(a.det[1], a.det[0]);
+    if (ph < 0.0) ph = ph + 2.0 * PI;
+    a.det_sph_phi = ph;
+    const double ay = -(PI / 2.0 - L.theta_star);
+    a.rot_y_cos = std::cos(ay); a.rot_y_sin = std::sin(ay);
+    a.rot_z_cos = std::cos(L.phi_star); a.rot_z_sin = std::sin(L.phi_star);
+    double td = PI - L.theta_star, pd = PI + L.phi_star;
+    if (td < 0.0) td = td + 2.0 * PI;
+    if (td > 2.0 * PI) td = td - 2.0 * PI;
+    if (pd < 0.0) pd = pd + 2.0 * PI;
+    if (pd > 2.0 * PI) pd = pd - 2.0 * PI;
+    a.star_dir[0] = 1.0 * std::sin(td) * std::cos(pd);
+    a.star_dir[1] = 1.0 * std::sin(td) * std::sin(pd);
+    a.star_dir[2] = 1.0 * std::cos(td);
+}
+
+int check_launch(artes_gpu_ctx* ctx, const artes_launch_t* L) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!L || L->struct_size != sizeof(artes_launch_t)) return fail(ctx, -1, "artes_launch_t: struct_size mismatch (ABI)");
+    if (!ctx->have_grid || !ctx->have_wl) return fail(ctx, -1, "set_grid / set_wavelength not called");
+    if (L->mode != ARTES_MODE_FAITHFUL && L->mode != ARTES_MODE_FAST) return fail(ctx, -1, "unknown mode");
+    if (L->photon_source != 1 && L->photon_source != 2) return fail(ctx, -1, "photon_source must be 1 or 2");
+    if (L->photon_source == 2 && !ctx->thermal) return fail(ctx, -1, "photon_source=2 needs cell_weight and emis_cdf");
+    if (L->nx < 1 || L->ny < 1 || !(L->x_max > 0.0) || !(L->y_max > 0.0)) return fail(ctx, -1, "bad detector geometry");
+    return 0;
+}
+
+size_t out_doubles(const artes_gpu_ctx* c, const artes_launch_t& L) {
+    return (size_t)10 * L.nx * L.ny + 2 + (size_t)7 * c->cells;
+}
+
+}  // namespace
+
+extern "C" {
+
+int artes_gpu_abi_version(void) { return ARTES_GPU_ABI_VERSION; }
+
+const char* artes_gpu_last_error(const artes_gpu_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int artes_gpu_create(artes_gpu_ctx** out, int ndev, const int* dev_ids) {
+    artes_gpu_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, -1, "null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1)
+        return fail(nullptr, -2, std::string("no CUDA device (libartes_gpu has no CPU fallback): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+    if (ndev < 1) ndev = 1;
+    if (ndev > count && !dev_ids) return fail(nullptr, -1, "more devices requested than present");
+    ctx = new artes_gpu_ctx();
+    ctx->devs.resize(ndev);
+    for (int i = 0; i < ndev; ++i) {
+        DeviceState& d = ctx->devs[i];
+        d.dev = dev_ids ? dev_ids[i] : i;
+        cudaDeviceProp prop;
+        if ((e = cudaSetDevice(d.dev)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, d.dev)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            std::string msg = std::string("device init: ") + cudaGetErrorString(e);
+            delete ctx;
+            return fail(nullptr, -2, msg);
+        }
+        d.sm_count = prop.multiProcessorCount;
+        for (auto& ev : d.ev) cudaEventCreate(&ev);
+    }
+    if (ndev > 1) {  // single-process multi-GPU: one communicator per device
+        if (!g_nccl.load()) { std::string m = g_nccl.err; delete ctx; return fail(nullptr, -4, m); }
+        std::vector<ncclComm_t> comms(ndev);
+        std::vector<int> ids(ndev);
+        for (int i = 0; i < ndev; ++i) ids[i] = ctx->devs[i].dev;
+        ncclResult_t r = g_nccl.CommInitAll(comms.data(), ndev, ids.data());
+        if (r != ncclSuccess) { std::string m = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r); delete ctx; return fail(nullptr, -4, m); }
+        for (int i = 0; i < ndev; ++i) ctx->devs[i].comm = comms[i];
+    }
+    *out = ctx;
+    return 0;
+}
+
+int artes_gpu_destroy(artes_gpu_ctx* ctx) {
+    if (!ctx) return 0;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.dev);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.comm && g_nccl.ok) g_nccl.CommDestroy(d.comm);
+        free_pool(d.grid_allocs);
+        free_pool(d.wl_allocs);
+        if (d.out_d) cudaFree(d.out_d);
+        if (d.out_u) cudaFree(d.out_u);
+        for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+    return 0;
+}
+
+int artes_gpu_device_info(const artes_gpu_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
+    if (!ctx || ctx->devs.empty()) return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->devs[0].dev) != cudaSuccess) return -2;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_len > 0) { std::strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return 0;
+}
+
+int artes_gpu_set_grid(artes_gpu_ctx* ctx, int nr, int ntheta, int nphi, const double* rfront, const double* thetafront,
+                       const int32_t* thetaplane, const double* phifront, double ox, double oy, double oz) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (nr < 1 || ntheta < 1 || nphi < 1 || !rfront || !thetafront || !thetaplane || !phifront) return fail(ctx, -1, "bad grid");
+    ctx->nr = nr; ctx->nt = ntheta; ctx->np = nphi; ctx->cells = nr * ntheta * nphi;
+    std::vector<double> tcos(ntheta + 1), ttan(ntheta + 1), pcos(nphi), psin(nphi), trig(540);
+    for (int i = 0; i <= ntheta; ++i) { tcos[i] = std::cos(thetafront[i]); ttan[i] = std::tan(thetafront[i]); }  // :2261-2264
+    for (int i = 0; i < nphi; ++i) { pcos[i] = std::cos(phifront[i]); psin[i] = std::sin(phifront[i]); }          // :2267-2270
+    ctx->sinbeta.resize(180); ctx->cos2beta.resize(180); ctx->sin2beta.resize(180);
+    for (int i = 1; i <= 180; ++i) {  // :409-420
+        ctx->sinbeta[i - 1] = (std::sin((double)i * PI / 180.0) + std::sin((double)(i - 1) * PI / 180.0)) / 2.0;
+        ctx->cos2beta[i - 1] = (std::cos(2.0 * (double)i * PI / 180.0) + std::cos(2.0 * (double)(i - 1) * PI / 180.0)) / 2.0;
+        ctx->sin2beta[i - 1] = (std::sin(2.0 * (double)i * PI / 180.0) + std::sin(2.0 * (double)(i - 1) * PI / 180.0)) / 2.0;
+        trig[i - 1] = ctx->sinbeta[i - 1]; trig[180 + i - 1] = ctx->cos2beta[i - 1]; trig[360 + i - 1] = ctx->sin2beta[i - 1];
+    }
+    std::vector<double> cdfA(2 * 181, 0.0);  // fast-mode prefix sums of cos2beta / sin2beta
+    for (int i = 1; i <= 180; ++i) { cdfA[i] = cdfA[i - 1] + ctx->cos2beta[i - 1]; cdfA[181 + i] = cdfA[181 + i - 1] + ctx->sin2beta[i - 1]; }
+    std::vector<int> tp(thetaplane, thetaplane + ntheta + 1);
+    for (auto& d : ctx->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaStreamSynchronize(d.stream));
+        free_pool(d.grid_allocs);
+        DevTables& T = d.T;
+        T.nr = nr; T.nt = ntheta; T.np = nphi; T.cells = ctx->cells; T.ox = ox; T.oy = oy; T.oz = oz;
+        int rc = 0;
+        rc |= upload(ctx, d, d.grid_allocs, rfront, (size_t)nr + 1, &T.rfront);
+        rc |= upload(ctx, d, d.grid_allocs, thetafront, (size_t)ntheta + 1, &T.thetafront);
+        rc |= upload(ctx, d, d.grid_allocs, ttan.data(), ttan.size(), &T.ttan);
+        rc |= upload(ctx, d, d.grid_allocs, tcos.data(), tcos.size(), &T.tcos);
+        rc |= upload(ctx, d, d.grid_allocs, tp.data(), tp.size(), &T.tplane);
+        rc |= upload(ctx, d, d.grid_allocs, phifront, (size_t)nphi, &T.phifront);
+        rc |= upload(ctx, d, d.grid_allocs, psin.data(), psin.size(), &T.psin);
+        rc |= upload(ctx, d, d.grid_allocs, pcos.data(), pcos.size(), &T.pcos);
+        rc |= upload(ctx, d, d.grid_allocs, trig.data(), trig.size(), &T.trig);
+        rc |= upload(ctx, d, d.grid_allocs, cdfA.data(), cdfA.size(), &T.cdfA);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    ctx->have_grid = true;
+    ctx->have_wl = false;
+    return 0;
+}
+
+int artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, int n_uniq,
+                             const double* uniq_matrix, const int32_t* cell_to_uniq, int cell_depth,
+                             const double* cell_weight, const double* emis_cdf) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!ctx->have_grid) return fail(ctx, -1, "set_grid first");
+    if (!k_sca || !k_abs || !uniq_matrix || !cell_to_uniq || n_uniq < 1) return fail(ctx, -1, "bad wavelength tables");
+    if (cell_depth < 0 || cell_depth >= ctx->nr) return fail(ctx, -1, "cell_depth out of range");
+    const int n = ctx->cells;
+    for (int i = 0; i < n; ++i) if (cell_to_uniq[i] < 0 || cell_to_uniq[i] >= n_uniq) return fail(ctx, -1, "cell_to_uniq out of range");
+    std::vector<double> kext(n), albedo(n, 0.0);
+    for (int i = 0; i < n; ++i) {  // :2178-2188
+        kext[i] = k_sca[i] + k_abs[i];
+        if (kext[i] > 0.0) albedo[i] = k_sca[i] / kext[i];
+        if (albedo[i] < 1.e-20) albedo[i] = 1.e-20;
+    }
+    std::vector<double> p1k((size_t)n_uniq * 4, 0.0), mrow((size_t)n_uniq * 720), cdfP((size_t)n_uniq * 181 * 4, 0.0);
+    for (int u = 0; u < n_uniq; ++u) {
+        for (int a = 0; a < 180; ++a)
+            for (int k = 0; k < 4; ++k) {
+                const double m = uniq_matrix[((size_t)u * 180 + a) * 16 + k];
+                mrow[((size_t)u * 180 + a) * 4 + k] = m;
+                p1k[(size_t)u * 4 + k] = p1k[(size_t)u * 4 + k] + m * ctx->sinbeta[a] * PI / 180.0;  // :2221-2224
+                cdfP[((size_t)u * 181 + a + 1) * 4 + k] = cdfP[((size_t)u * 181 + a) * 4 + k] + m * ctx->sinbeta[a] * PI / 180.0;
+            }
+    }
+    std::vector<double> cdf_lin;
+    ctx->thermal = (cell_weight && emis_cdf);
+    if (ctx->thermal) {  // reorder emissivity_cumulative into its (i,j,k) construction order (:2425-2427)
+        const int nr = ctx->nr, nt = ctx->nt, np = ctx->np;
+        cdf_lin.resize((size_t)(nr - cell_depth) * nt * np);
+        size_t p = 0;
+        for (int i = cell_depth; i < nr; ++i)
+            for (int j = 0; j < nt; ++j)
+                for (int k = 0; k < np; ++k) cdf_lin[p++] = emis_cdf[i + nr * (j + nt * k)];
+    }
+    cudaEvent_t e0, e1;
+    for (auto& d : ctx->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaStreamSynchronize(d.stream));
+        free_pool(d.wl_allocs);
+        DevTables& T = d.T;
+        T.cell_depth = cell_depth; T.n_uniq = n_uniq;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, d.stream));
+        int rc = 0;
+        rc |= upload(ctx, d, d.wl_allocs, kext.data(), kext.size(), &T.kext);
+        rc |= upload(ctx, d, d.wl_allocs, albedo.data(), albedo.size(), &T.albedo);
+        rc |= upload(ctx, d, d.wl_allocs, cell_to_uniq, (size_t)n, &T.c2u);
+        rc |= upload(ctx, d, d.wl_allocs, uniq_matrix, (size_t)n_uniq * 2880, &T.M);
+        rc |= upload(ctx, d, d.wl_allocs, mrow.data(), mrow.size(), &T.Mrow);
+        rc |= upload(ctx, d, d.wl_allocs, p1k.data(), p1k.size(), &T.p1k);
+        rc |= upload(ctx, d, d.wl_allocs, cdfP.data(), cdfP.size(), &T.cdfP);
+        T.cell_weight = nullptr; T.emis_cdf = nullptr;
+        if (ctx->thermal) {
+            rc |= upload(ctx, d, d.wl_allocs, cell_weight, (size_t)n, &T.cell_weight);
+            rc |= upload(ctx, d, d.wl_allocs, cdf_lin.data(), cdf_lin.size(), &T.emis_cdf);
+        }
+        if (rc) return rc;
+        CU(cudaEventRecord(e1, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ctx->last_h2d_ms = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    ctx->have_wl = true;
+    return 0;
+}
+
+int artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, const double* dense,
+                                   int cell_depth, const double* cell_weight, const double* emis_cdf) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!ctx->have_grid) return fail(ctx, -1, "set_grid first");
+    if (!dense) return fail(ctx, -1, "null matrix");
+    // De-duplicate the per-cell 180x16 blocks: python/atmosphere.py:351-372 mixes a handful of species,
+    // so the dense HDU (cells x 23 040 B) holds few distinct blocks.
+    const size_t n = (size_t)ctx->cells;
+    std::vector<double> block(2880);
+    std::vector<double> uniq;
+    std::vector<int32_t> c2u(n);
+    std::unordered_multimap<uint64_t, int> seen;
+    for (size_t cidx = 0; cidx < n; ++cidx) {
+        uint64_t h = 1469598103934665603ull;
+        for (int a = 0; a < 180; ++a)
+            for (int e = 0; e < 16; ++e) {
+                double v = dense[cidx + n * ((size_t)e + 16 * (size_t)a)];
+                block[a * 16 + e] = v;
+                uint64_t bits; std::memcpy(&bits, &v, 8);
+                h ^= bits; h *= 1099511628211ull;
+            }
+        int found = -1;
+        auto range = seen.equal_range(h);
+        for (auto it = range.first; it != range.second; ++it)
+            if (std::memcmp(&uniq[(size_t)it->second * 2880], block.data(), 2880 * 8) == 0) { found = it->second; break; }
+        if (found < 0) {
+            found = (int)(uniq.size() / 2880);
+            uniq.insert(uniq.end(), block.begin(), block.end());
+            seen.emplace(h, found);
+        }
+        c2u[cidx] = found;
+    }
+    return artes_gpu_set_wavelength(ctx, k_sca, k_abs, (int)(uniq.size() / 2880), uniq.data(), c2u.data(), cell_depth, cell_weight, emis_cdf);
+}
+
+int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
+    int rc = check_launch(ctx, L);
+    if (rc) return rc;
+    if (ctx->pending) return fail(ctx, -1, "a launch is already pending (call artes_gpu_wait)");
+    const int ndev = (int)ctx->devs.size();
+    const size_t npx = (size_t)L->nx * L->ny;
+    const size_t n_d = out_doubles(ctx, *L);
+    ctx->n_out_d = n_d;
+    // contiguous photon-id ranges: first over ranks (done by the caller through photon_id_base), then over devices
+    unsigned long long per = L->n_photons / ndev, rem = L->n_photons % ndev, off = 0;
+    for (int i = 0; i < ndev; ++i) {
+        DeviceState& d = ctx->devs[i];
+        CU(cudaSetDevice(d.dev));
+        rc = ensure_outputs(ctx, d, n_d);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(d.out_d, 0, n_d * sizeof(double), d.stream));
+        CU(cudaMemsetAsync(d.out_u, 0, (ARTES_ERR_SLOTS + 16) * sizeof(unsigned long long), d.stream));
+        KernelArgs a{};
+        a.T = d.T;
+        fill_launch(*L, a.L);
+        a.L.n_photons = per + ((unsigned long long)i < rem ? 1 : 0);
+        a.L.id_base = L->photon_id_base + off;
+        off += a.L.n_photons;
+        d.n_photons = a.L.n_photons;
+        a.O.det = d.out_d;
+        a.O.flux = d.out_d + 10 * npx;
+        a.O.flow4 = d.out_d + 10 * npx + 2;
+        a.O.flow3 = d.out_d + 10 * npx + 2 + (size_t)4 * ctx->cells;
+        a.O.err = d.out_u;
+        a.O.stats = d.out_u + ARTES_ERR_SLOTS;
+        a.O.counter = d.out_u + ARTES_ERR_SLOTS + 8;
+        CU(cudaEventRecord(d.ev[0], d.stream));
+        if (a.L.n_photons > 0) {
+            cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, false, d.sm_count, d.stream)
+                                                             : fast::launch_transport(a, false, d.sm_count, d.stream);
+            if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
+        }
+        CU(cudaEventRecord(d.ev[1], d.stream));
+    }
+    // NCCL sum of the packed accumulators (the thread sum of :959-975 across devices / ranks)
+    const bool reduce = (ndev > 1) || ctx->rank_comm;
+    if (reduce) {
+        NC(g_nccl.GroupStart());
+        for (auto& d : ctx->devs) {
+            NC(g_nccl.AllReduce(d.out_d, d.out_d, n_d, ncclDouble, ncclSum, d.comm, d.stream));
+            NC(g_nccl.AllReduce(d.out_u, d.out_u, ARTES_ERR_SLOTS + 8, ncclUint64, ncclSum, d.comm, d.stream));
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    for (auto& d : ctx->devs) { CU(cudaSetDevice(d.dev)); CU(cudaEventRecord(d.ev[2], d.stream)); }
+    ctx->pending = true;
+    ctx->pending_launch = *L;
+    return 0;
+}
+
+int artes_gpu_wait(artes_gpu_ctx* ctx, double* det_sum, double* flux, double* flow4, double* flow3,
+                   uint64_t* err_hist, artes_stats_t* stats) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!ctx->pending) return fail(ctx, -1, "no pending launch");
+    ctx->pending = false;
+    const artes_launch_t& L = ctx->pending_launch;
+    const size_t npx = (size_t)L.nx * L.ny;
+    const size_t n_d = ctx->n_out_d;
+    double kernel_ms = 0.0, reduce_ms = 0.0;
+    for (auto& d : ctx->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaStreamSynchronize(d.stream));
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, d.ev[0], d.ev[1]);
+        cudaEventElapsedTime(&b, d.ev[1], d.ev[2]);
+        kernel_ms = std::max(kernel_ms, (double)a);
+        reduce_ms = std::max(reduce_ms, (double)b);
+    }
+    // every device holds the reduced result; read device 0
+    DeviceState& d0 = ctx->devs[0];
+    CU(cudaSetDevice(d0.dev));
+    std::vector<double> h(n_d);
+    std::vector<unsigned long long> hu(ARTES_ERR_SLOTS + 8);
+    cudaEvent_t e0 = d0.ev[3];
+    CU(cudaEventRecord(e0, d0.stream));
+    CU(cudaMemcpyAsync(h.data(), d0.out_d, n_d * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaMemcpyAsync(hu.data(), d0.out_u, hu.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaEventRecord(d0.ev[2], d0.stream));
+    CU(cudaStreamSynchronize(d0.stream));
+    float d2h = 0.f;
+    cudaEventElapsedTime(&d2h, e0, d0.ev[2]);
+    if (det_sum) {  // expand to detector(nx,ny,4,3): the count plane is shared by Q,U,V (:4969-4972)
+        std::memcpy(det_sum, h.data(), 8 * npx * sizeof(double));
+        std::memcpy(det_sum + 8 * npx, h.data() + 8 * npx, npx * sizeof(double));
+        for (int k = 1; k < 4; ++k) std::memcpy(det_sum + (8 + k) * npx, h.data() + 9 * npx, npx * sizeof(double));
+    }
+    if (flux) { flux[0] = h[10 * npx]; flux[1] = h[10 * npx + 1]; }
+    if (flow4) std::memcpy(flow4, h.data() + 10 * npx + 2, (size_t)4 * ctx->cells * sizeof(double));
+    if (flow3) std::memcpy(flow3, h.data() + 10 * npx + 2 + (size_t)4 * ctx->cells, (size_t)3 * ctx->cells * sizeof(double));
+    if (err_hist) for (int k = 0; k < ARTES_ERR_SLOTS; ++k) err_hist[k] = hu[k];
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        const unsigned long long* s = hu.data() + ARTES_ERR_SLOTS;
+        stats->n_emit = s[0]; stats->n_cell_face = s[1]; stats->n_scatter = s[2]; stats->n_peel = s[3];
+        stats->n_surface = s[4]; stats->n_draws = s[5]; stats->n_error = s[6];
+        stats->kernel_ms = kernel_ms; stats->reduce_ms = reduce_ms; stats->h2d_ms = ctx->last_h2d_ms; stats->d2h_ms = d2h;
+    }
+    return 0;
+}
+
+int artes_gpu_run(artes_gpu_ctx* ctx, const artes_launch_t* L, double* det_sum, double* flux, double* flow4,
+                  double* flow3, uint64_t* err_hist, artes_stats_t* stats) {
+    int rc = artes_gpu_run_async(ctx, L);
+    if (rc) return rc;
+    return artes_gpu_wait(ctx, det_sum, flux, flow4, flow3, err_hist, stats);
+}
+
+int artes_gpu_nccl_unique_id(void* id_out) {
+    if (!id_out) return -1;
+    if (!g_nccl.load()) { g_create_error = g_nccl.err; return -4; }
+    static_assert(sizeof(ncclUniqueId) <= ARTES_NCCL_ID_BYTES, "ncclUniqueId larger than ARTES_NCCL_ID_BYTES");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = g_nccl.GetErrorString(r); return -4; }
+    std::memset(id_out, 0, ARTES_NCCL_ID_BYTES);
+    std::memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+int artes_gpu_nccl_init_rank(artes_gpu_ctx* ctx, int nranks, int rank, const void* id_bytes) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (ctx->devs.size() != 1) return fail(ctx, -1, "nccl_init_rank needs a single-device context (one process per GPU)");
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id_bytes) return fail(ctx, -1, "bad rank arguments");
+    if (!g_nccl.load()) return fail(ctx, -4, g_nccl.err);
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof(id));
+    DeviceState& d = ctx->devs[0];
+    CU(cudaSetDevice(d.dev));
+    NC(g_nccl.CommInitRank(&d.comm, nranks, id, rank));
+    ctx->nranks = nranks; ctx->rank = rank; ctx->rank_comm = true;
+    return 0;
+}
+
+int artes_gpu_trace(artes_gpu_ctx* ctx, const artes_launch_t* L, const double* xi, uint64_t n, int max_draws,
+                    int32_t* seq_len, uint64_t* seq_hash, int32_t* seq_head, int max_rec, double* fstate) {
+    int rc = check_launch(ctx, L);
+    if (rc) return rc;
+    if (!xi || !seq_len || !seq_hash || n == 0 || max_draws < 1) return fail(ctx, -1, "bad trace arguments");
+    DeviceState& d = ctx->devs[0];
+    CU(cudaSetDevice(d.dev));
+    const size_t npx = (size_t)L->nx * L->ny;
+    const size_t n_d = out_doubles(ctx, *L);
+    rc = ensure_outputs(ctx, d, n_d);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(d.out_d, 0, n_d * sizeof(double), d.stream));
+    CU(cudaMemsetAsync(d.out_u, 0, (ARTES_ERR_SLOTS + 16) * sizeof(unsigned long long), d.stream));
+    double *d_xi = nullptr, *d_f = nullptr;
+    int *d_len = nullptr, *d_head = nullptr;
+    unsigned long long* d_hash = nullptr;
+    CU(cudaMalloc(&d_xi, (size_t)n * max_draws * sizeof(double)));
+    CU(cudaMalloc(&d_len, n * sizeof(int)));
+    CU(cudaMalloc(&d_hash, n * sizeof(unsigned long long)));
+    if (seq_head && max_rec > 0) { CU(cudaMalloc(&d_head, (size_t)n * max_rec * 5 * sizeof(int))); CU(cudaMemsetAsync(d_head, 0xff, (size_t)n * max_rec * 5 * sizeof(int), d.stream)); }
+    if (fstate) CU(cudaMalloc(&d_f, n * 8 * sizeof(double)));
+    CU(cudaMemcpyAsync(d_xi, xi, (size_t)n * max_draws * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    KernelArgs a{};
+    a.T = d.T;
+    fill_launch(*L, a.L);
+    a.L.n_photons = n;
+    a.O.det = d.out_d; a.O.flux = d.out_d + 10 * npx; a.O.flow4 = d.out_d + 10 * npx + 2;
+    a.O.flow3 = d.out_d + 10 * npx + 2 + (size_t)4 * ctx->cells;
+    a.O.err = d.out_u; a.O.stats = d.out_u + ARTES_ERR_SLOTS; a.O.counter = d.out_u + ARTES_ERR_SLOTS + 8;
+    a.R.xi = d_xi; a.R.max_draws = max_draws; a.R.max_rec = d_head ? max_rec : 0;
+    a.R.seq_len = d_len; a.R.seq_hash = d_hash; a.R.seq_head = d_head; a.R.fstate = d_f;
+    cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, true, d.sm_count, d.stream)
+                                                     : fast::launch_transport(a, true, d.sm_count, d.stream);
+    if (e != cudaSuccess) return fail(ctx, -2, std::string("trace launch: ") + cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(seq_len, d_len, n * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaMemcpyAsync(seq_hash, d_hash, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+    if (d_head) CU(cudaMemcpyAsync(seq_head, d_head, (size_t)n * max_rec * 5 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    if (d_f) CU(cudaMemcpyAsync(fstate, d_f, n * 8 * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    cudaFree(d_xi); cudaFree(d_len); cudaFree(d_hash); cudaFree(d_head); cudaFree(d_f);
+    return 0;
+}
+
+int artes_gpu_cell_face(artes_gpu_ctx* ctx, int mode, uint64_t n, const double* pos, const double* dir,
+                        const int32_t* face, const int32_t* cell, int32_t* out_i, double* out_d) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!ctx->have_grid || !ctx->have_wl) return fail(ctx, -1, "set_grid / set_wavelength not called");
+    if (n == 0) return 0;
+    DeviceState& d = ctx->devs[0];
+    CU(cudaSetDevice(d.dev));
+    double *dp = nullptr, *dd = nullptr, *dod = nullptr;
+    int *df = nullptr, *dc = nullptr, *doi = nullptr;
+    CU(cudaMalloc(&dp, n * 3 * sizeof(double))); CU(cudaMalloc(&dd, n * 3 * sizeof(double))); CU(cudaMalloc(&dod, n * sizeof(double)));
+    CU(cudaMalloc(&df, n * 2 * sizeof(int))); CU(cudaMalloc(&dc, n * 3 * sizeof(int))); CU(cudaMalloc(&doi, n * 7 * sizeof(int)));
+    CU(cudaMemcpyAsync(dp, pos, n * 3 * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(dd, dir, n * 3 * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(df, face, n * 2 * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(dc, cell, n * 3 * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+    cudaError_t e = (mode == ARTES_MODE_FAITHFUL) ? faithful::launch_cell_face(d.T, n, dp, dd, df, dc, doi, dod, d.stream)
+                                                  : fast::launch_cell_face(d.T, n, dp, dd, df, dc, doi, dod, d.stream);
+    if (e != cudaSuccess) return fail(ctx, -2, std::string("cell_face launch: ") + cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(out_i, doi, n * 7 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaMemcpyAsync(out_d, dod, n * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    cudaFree(dp); cudaFree(dd); cudaFree(dod); cudaFree(df); cudaFree(dc); cudaFree(doi);
+    return 0;
+}
+
+int artes_gpu_fma_peak(artes_gpu_ctx* ctx, double* fp64_tflops, double* fp32_tflops) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    DeviceState& d = ctx->devs[0];
+    CU(cudaSetDevice(d.dev));
+    cudaError_t e = fma_peak(fp64_tflops, fp32_tflops, d.sm_count, d.stream);
+    if (e != cudaSuccess) return fail(ctx, -2, std::string("fma_peak: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+/*
+ * artes_gpu.h -- C-ABI of libartes_gpu: the B200 (sm_100a) replacement for the
+ * photon-packet transport loop of ARTES.
+ *
+ * The reference has no FFI; its seam is the argument-less internal subroutine
+ * `radiative_transfer` (src/ARTES.f90:518-1006) which `run` calls once per
+ * wavelength / detector azimuth (src/ARTES.f90:146,185,241,255) and which talks
+ * to the rest of the program through program-scope variables
+ * (src/ARTES.f90:19-115; the OpenMP clause :534-544 lists exactly what crosses).
+ * Every entry point below names the reference state it replaces.
+ *
+ * Conventions
+ *  - plain C, fixed-width integers, IEEE doubles, caller owns all host buffers;
+ *  - all 3-D cell arrays are in the reference's Fortran order, radial index
+ *    fastest: idx = ir + nr*(itheta + ntheta*iphi)   (src/ARTES.f90:64-70);
+ *  - every function returns 0 on success, <0 on error
+ *    (artes_gpu_last_error() gives the text); nothing exits or throws across
+ *    the ABI (the reference calls exit(0), src/ARTES.f90:554,2825);
+ *  - there is NO CPU fallback: without a CUDA device artes_gpu_create fails.
+ */
+#ifndef ARTES_GPU_H
+#define ARTES_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARTES_GPU_ABI_VERSION 1
+
+/* arithmetic modes */
+#define ARTES_MODE_FAITHFUL 0 /* reference operation order, no FMA contraction, sequential 180-bin CDFs */
+#define ARTES_MODE_FAST     1 /* same physics; prefix-table CDF inversion, FMA allowed                   */
+
+#define ARTES_ERR_SLOTS 64 /* err_hist[code]: code = the reference's `error NNN` number (src/ARTES.f90, ~50 sites) */
+
+typedef struct artes_gpu_ctx artes_gpu_ctx;
+
+/* Per-launch parameters = the scalar program-scope inputs of radiative_transfer. */
+typedef struct artes_launch_t {
+    uint32_t struct_size;       /* sizeof(artes_launch_t), ABI check                                   */
+    int32_t  mode;              /* ARTES_MODE_*                                                        */
+    uint64_t n_photons;         /* `packages` handled by THIS call (src/ARTES.f90:26,546)              */
+    uint64_t photon_id_base;    /* global id of the first photon (Philox counter; multi-GPU sharding)  */
+    uint64_t seed;              /* Philox key; replaces the clock-seeded state(:,:) (:433-449)         */
+    int32_t  photon_source;     /* 1 = star, 2 = planet (:20)                                          */
+    int32_t  photon_scattering; /* (:32)                                                               */
+    int32_t  photon_emission;   /* 1 isotropic, 2 biased (:33)                                         */
+    int32_t  stellar_direction; /* (:37)                                                               */
+    int32_t  limb_emission;     /* phase_curve .and. det_phi*180/pi >= 170 (:1041)                     */
+    int32_t  flow_global;       /* (:53)                                                               */
+    int32_t  flow_theta;        /* (:54)                                                               */
+    int32_t  nx, ny;            /* detector pixels (:48-49)                                            */
+    int32_t  reserved0;
+    double   fstop;             /* (:29)                                                               */
+    double   photon_minimum;    /* (:30)                                                               */
+    double   photon_bias;       /* (:34)                                                               */
+    double   surface_albedo;    /* (:40)                                                               */
+    double   theta_star;        /* [rad] (:38)                                                         */
+    double   phi_star;          /* [rad] (:39)                                                         */
+    double   det_theta;         /* [rad] det_dir(4) (:91,496)                                          */
+    double   det_phi;           /* [rad] det_dir(5) (:91,497)                                          */
+    double   x_max, y_max;      /* image half-size [m] (:50-51,475-479)                                */
+} artes_launch_t;
+
+/* Exact event counters of one launch (the flop accounting uses them). */
+typedef struct artes_stats_t {
+    uint64_t n_emit;       /* photons emitted                       */
+    uint64_t n_cell_face;  /* cell_face evaluations (all walks)     */
+    uint64_t n_scatter;    /* scatter_photon calls                  */
+    uint64_t n_peel;       /* peel_photon + peel_surface + peel_thermal walks started */
+    uint64_t n_surface;    /* surface hits                          */
+    uint64_t n_draws;      /* random numbers consumed               */
+    uint64_t n_error;      /* photons dropped through an error path */
+    uint64_t reserved;
+    double   kernel_ms;    /* CUDA-event time of the transport kernel(s), max over this ctx's devices */
+    double   reduce_ms;    /* CUDA-event time of the NCCL reduce (0 if single device)                 */
+    double   h2d_ms;       /* last table upload                                                        */
+    double   d2h_ms;       /* result download                                                          */
+} artes_stats_t;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* One context owns `ndev` devices (dev_ids may be NULL = 0..ndev-1) of this process; the
+ * OpenMP team of the reference (src/ARTES.f90:360-363) becomes these devices. */
+int  artes_gpu_create(artes_gpu_ctx** ctx, int ndev, const int* dev_ids);
+int  artes_gpu_destroy(artes_gpu_ctx* ctx);
+const char* artes_gpu_last_error(const artes_gpu_ctx* ctx); /* ctx may be NULL: last create error */
+int  artes_gpu_abi_version(void);
+
+/* ---- static inputs (per run) ------------------------------------------------------------ */
+
+/* Replaces rfront/thetafront/thetaplane/phifront (src/ARTES.f90:58-61, filled at :2071-2122)
+ * and oblate_x/y/z (:42,469-471). The derived tables theta_grid_cos/tan, phi_grid_sin/cos
+ * (:2261-2270) and sinbeta/cos2beta/sin2beta (:409-420) are rebuilt inside, on the host,
+ * in double, with the same expressions.
+ *   rfront[nr+1] [m], thetafront[ntheta+1] [rad], thetaplane[ntheta+1] (1 cone, 2 plane),
+ *   phifront[nphi] [rad] */
+int  artes_gpu_set_grid(artes_gpu_ctx* ctx, int nr, int ntheta, int nphi,
+                        const double* rfront, const double* thetafront, const int32_t* thetaplane,
+                        const double* phifront, double oblate_x, double oblate_y, double oblate_z);
+
+/* ---- per-wavelength inputs ---------------------------------------------------------------- */
+
+/* Replaces the wl_count slices of cell_scattering_opacity / cell_absorption_opacity
+ * (src/ARTES.f90:64-65) and cell_scatter_matrix (:69) plus the host-derived cell_opacity,
+ * cell_albedo (:2172-2188), cell_p11..p14_int (:2203-2230), cell_depth (:2329-2393),
+ * cell_weight and emissivity_cumulative (:2395-2453).
+ *   k_sca, k_abs       [cells] [m^-1]
+ *   uniq_matrix        [n_uniq][180][16]  (angle bin, then element 4*row+col; = one cell's
+ *                      block of HDU 8 of atmosphere.fits)
+ *   cell_to_uniq       [cells] index into uniq_matrix
+ *   cell_depth         surface face index
+ *   cell_weight, emis_cdf [cells] or NULL (only photon_source = 2) */
+int  artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs,
+                              int n_uniq, const double* uniq_matrix, const int32_t* cell_to_uniq,
+                              int cell_depth, const double* cell_weight, const double* emis_cdf);
+
+/* Same, taking the reference's dense array for ONE wavelength exactly as it sits in memory
+ * after ftgpvd (src/ARTES.f90:2196-2198): element (cell, e, a) at cell + cells*(e + 16*a),
+ * e = 0..15, a = 0..179.  De-duplicated internally (hash of each cell's 2880 doubles). */
+int  artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs,
+                                    const double* matrix_dense, int cell_depth,
+                                    const double* cell_weight, const double* emis_cdf);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+
+/* Replaces `call radiative_transfer` up to and excluding the package_energy scaling
+ * (src/ARTES.f90:546-955 and the thread sum of :959-975).
+ *   det_sum  [nx*ny*4*3], Fortran order detector(ix,iy,stokes,l): l=1 sum W, l=2 sum W^2,
+ *            l=3 counts (:84-85); UNscaled (the driver applies package_energy, :957-975)
+ *   flux     [2] = sum(flux_emitted), sum(flux_exit) (:86-87,607,780,953)
+ *   flow4    [4*cells] cell_flow summed over threads, (dir, cell) dir fastest (:82) or NULL
+ *   flow3    [3*cells] cell_flow_global likewise (:81) or NULL
+ *   err_hist [ARTES_ERR_SLOTS] per-code error counts (replaces error.log appends) or NULL
+ * With several devices (or after artes_gpu_nccl_init_rank) the outputs are the NCCL sum
+ * over all devices/ranks; every rank receives the sum. */
+int  artes_gpu_run(artes_gpu_ctx* ctx, const artes_launch_t* launch,
+                   double* det_sum, double* flux, double* flow4, double* flow3,
+                   uint64_t* err_hist, artes_stats_t* stats);
+
+/* Asynchronous form: enqueue on the context's stream(s) and return; artes_gpu_wait copies
+ * the results out.  Lets the driver overlap launch k's reduce/download with launch k+1's
+ * host work (phase curve: 73 launches, src/ARTES.f90:215-245). */
+int  artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* launch);
+int  artes_gpu_wait(artes_gpu_ctx* ctx, double* det_sum, double* flux, double* flow4, double* flow3,
+                    uint64_t* err_hist, artes_stats_t* stats);
+
+/* ---- multi-process NCCL (one process per GPU, e.g. under torchrun / MPI) ---------------------- */
+
+#define ARTES_NCCL_ID_BYTES 128
+int  artes_gpu_nccl_unique_id(void* id_out /* ARTES_NCCL_ID_BYTES */);
+int  artes_gpu_nccl_init_rank(artes_gpu_ctx* ctx, int nranks, int rank, const void* id);
+
+/* ---- test hooks --------------------------------------------------------------------------------- */
+
+/* Walk `n` photons with an INJECTED random stream xi[n][max_draws] (draw order of SURVEY
+ * App. C) and report every cell_face outcome in program order (tau pre-pass, walks, peel
+ * walks): tuple (next_face(1), next_face(2), cell_out(1..3)); a detector deposit is the
+ * tuple (100, ix, iy, 0, 0).
+ *   seq_len  [n]   number of tuples of photon i
+ *   seq_hash [n]   FNV-1a-64 over all tuple words
+ *   seq_head [n][max_rec][5] first max_rec tuples (may be NULL / max_rec = 0)
+ *   fstate   [n][8] final x,y,z,I,Q,U,V,n_scatter (may be NULL)
+ * Deterministic: single device, no atomics on the outputs. */
+int  artes_gpu_trace(artes_gpu_ctx* ctx, const artes_launch_t* launch,
+                     const double* xi, uint64_t n, int max_draws,
+                     int32_t* seq_len, uint64_t* seq_hash, int32_t* seq_head, int max_rec,
+                     double* fstate);
+
+/* Batch of isolated cell_face evaluations (src/ARTES.f90:2800-3470):
+ *   pos[n][3], dir[n][3], face[n][2], cell[n][3]  ->
+ *   out_i[n][7] = next_face(2), cell_out(3), grid_exit, cell_error ; out_d[n] = face_distance */
+int  artes_gpu_cell_face(artes_gpu_ctx* ctx, int mode, uint64_t n, const double* pos, const double* dir,
+                         const int32_t* face, const int32_t* cell, int32_t* out_i, double* out_d);
+
+/* Device properties of the context's first device (bench/roofline bookkeeping). */
+int  artes_gpu_device_info(const artes_gpu_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                           char* name, int name_len);
+
+/* FP64 / FP32 FMA peak microbenchmark (roofline denominator): returns TFLOP/s. */
+int  artes_gpu_fma_peak(artes_gpu_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARTES_GPU_H */
