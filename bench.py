@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- photon packets / s (peel-off on) of the ARTES transport path on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c4] [--photons P]
+
+One "step" = one pass of the hot path (one `artes_gpu_run`, i.e. one `call radiative_transfer`,
+src/ARTES.f90:518) over P photon packets per GPU on the synthetic atmosphere named by --workload
+(default C4: 3-D r-theta-phi grid, Rayleigh gas + Mie cloud patches, 64x64 Stokes images -- the
+configuration the north-star target is quoted on).  Photons shard over ranks by photon id (weak
+scaling: P per GPU), the images are summed with NCCL inside the library.
+
+Numbers on the JSON line:
+  value      photon packets/s, all ranks, tables resident in HBM, CUDA-event time of kernel+reduce
+  e2e        same through the public call with HOST buffers: table upload + launch + image download
+  roofline   algorithmic FP64 flop (SURVEY 8d event accounting x exact event counters) / kernel time
+             against the FP64 FMA peak measured in this run (this path is FP64-issue bound; the HBM
+             side is reported next to it as roofline_hbm)
+  cpu_baseline  the CPU oracle (C++ restatement of ARTES.f90 -- the image has no Fortran compiler)
+             on the box's host cores, bounded sample of the same workload
+`--impl reference` times that CPU implementation alone on the same workload/metric.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "photon packets/sec (peel-off on)"
+UNIT = "packets/s"
+
+WORKLOADS = {
+    # name: (builder, launch overrides, default photons per GPU per step)
+    "c1": ("c1_template_rayleigh", dict(nx=25, ny=25, det_phi=90.0), 4_000_000),
+    "c2": ("c2_hg_deck", dict(nx=1, ny=1, det_phi=60.0), 8_000_000),
+    "c3": ("c3_molecular", dict(nx=1, ny=1, det_phi=90.0), 8_000_000),
+    "c4": ("c4_mie_patches", dict(nx=64, ny=64, det_phi=60.0), 8_000_000),
+    "c5": ("c5_scale", dict(nx=64, ny=64, det_phi=60.0), 4_000_000),
+}
+
+# algorithmic FP64 flop per event
+F_CF = {3: 104.0, 2: 90.0, 1: 50.0}
+F_SC = {"faithful": 2700.0, "fast": 2700.0 - 900.0 - 1620.0 + 2 * 64.0}
+F_PEEL, F_EMIT = 200.0, 60.0
+B_CF, B_PEEL = 8.0, 256.0 + 12 * 8.0
+B_SC = {"faithful": 4 * 180 * 8.0 + 2 * 16 * 8.0, "fast": 2 * 8 * 32.0 + 2 * 16 * 8.0}
+
+
+def grid_dim(atm):
+    return 3 if atm.nphi > 1 else (2 if atm.ntheta > 1 else 1)
+
+
+def algorithmic(stats, atm, mode):
+    d = grid_dim(atm)
+    fl = stats["n_emit"] * F_EMIT + stats["n_cell_face"] * F_CF[d] + stats["n_scatter"] * F_SC[mode] + stats["n_peel"] * F_PEEL
+    by = stats["n_cell_face"] * B_CF + stats["n_scatter"] * B_SC[mode] + stats["n_peel"] * B_PEEL
+    return fl, by
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(atm, wl_kw, photons, seed, nthreads=0):
+    """The reference's CPU implementation of the path (oracle port; gfortran is not in the image)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, RNG_MZ
+    from artes_b200.abi import make_launch
+    o = Oracle()
+    o.set_atmosphere(atm)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(n_photons=int(photons), x_max=xm, y_max=xm, seed=seed, nx=wl_kw["nx"], ny=wl_kw["ny"],
+                    det_phi=math.radians(wl_kw["det_phi"]))
+    r = o.run(L, rng=RNG_MZ, nthreads=nthreads)
+    return r["stats"]["kernel_ms"] * 1e-3, int(r["stats"]["reserved"]), r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--photons", type=float, default=0, help="photon packets per GPU per step")
+    ap.add_argument("--mode", default="fast", choices=["fast", "faithful"])
+    ap.add_argument("--cpu-sample", type=float, default=300000, help="photons of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from tools import atmospheres as A
+    builder, wl_kw, default_p = WORKLOADS[args.workload]
+    atm = getattr(A, builder)()
+    P = int(args.photons) if args.photons else default_p
+    config = {"workload": f"{args.workload}:{builder} nr={atm.nr} ntheta={atm.ntheta} nphi={atm.nphi} "
+                          f"image={wl_kw['nx']}x{wl_kw['ny']} det_phi={wl_kw['det_phi']}deg star source, peel-off on",
+              "photons_per_gpu_per_step": P, "mode": args.mode, "parallelism": f"photon-id sharding x{world}",
+              "l2": "tables (<= few MB) are L2-resident by design; 256 MiB memset flushes L2 between steps"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = int(min(args.cpu_sample, P))
+        for _ in range(min(args.warmup, 1)):
+            cpu_arm(atm, wl_kw, max(sample // 10, 1000), 1)
+        tot = 0.0
+        cores = 0
+        for s in range(args.steps):
+            dt, cores, _ = cpu_arm(atm, wl_kw, sample, 100 + s)
+            tot += dt
+        v = sample * args.steps / tot
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{sample} packets per step of the same workload; C++ restatement of ARTES.f90 "
+                                           f"(g++ -O3 -fopenmp, gfortran unavailable), all host threads"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from artes_b200 import abi, host, lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    mode = abi.MODE_FAST if args.mode == "fast" else abi.MODE_FAITHFUL
+    params = host.Params(nx=wl_kw["nx"], ny=wl_kw["ny"], det_phi=math.radians(wl_kw["det_phi"]))
+    t = host.Transport(atm, params, devices=(local_rank,), mode=mode)
+    if world > 1:  # NCCL communicator of the library itself: the id travels through torch.distributed
+        obj = [lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        t.gpu.nccl_init_rank(world, rank, obj[0])
+    t.set_wavelength(0)
+    peaks = t.gpu.fma_peak()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        base = (i * world + rank) * P          # disjoint photon ids for every step and rank
+        L = t.launch_struct(P, seed=4, photon_id_base=base)
+        return t.gpu.run(L)
+
+    for i in range(args.warmup):
+        step(i)
+        flush.zero_()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev_ms = 0.0
+    kern_ms = 0.0
+    agg = dict(n_emit=0, n_cell_face=0, n_scatter=0, n_peel=0)
+    last = None
+    for i in range(args.steps):
+        res = step(args.warmup + i)
+        dev_ms += res["stats"]["kernel_ms"] + res["stats"]["reduce_ms"]
+        kern_ms += res["stats"]["kernel_ms"]
+        for k in agg:
+            agg[k] += res["stats"][k]          # already summed over ranks by the NCCL reduce
+        last = res
+        flush.zero_()                          # L2 flush, outside the event-timed region
+        torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    tm = torch.tensor([dev_ms, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms, kern_ms = float(tm[0]), float(tm[1])
+    value = world * args.steps * P / (dev_ms * 1e-3)
+
+    # ---- end to end through the public call with host buffers: upload tables, launch, download image
+    a = atm
+    h2d = (a.k_sca[0].nbytes + a.k_abs[0].nbytes + a.uniq[0].nbytes + a.cell_to_uniq[0].nbytes)
+    d2h = (10 * wl_kw["nx"] * wl_kw["ny"] + 2 + 7 * a.cells) * 8 + (64 + 8) * 8
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        t.set_wavelength(0)
+        step(args.warmup + args.steps + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * args.steps * P / float(te[0])
+
+    if rank == 0:
+        fl, by = algorithmic(agg, atm, args.mode)          # all ranks, all timed steps
+        per_launch_fl = fl / (world * args.steps)
+        per_launch_by = by / (world * args.steps)
+        k_s = kern_ms * 1e-3 / args.steps                  # average kernel duration (max over ranks)
+        achieved = per_launch_fl / k_s / 1e12
+        peaks_file = {}
+        try:
+            peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": args.steps * world,
+                "clocks": clocks,
+                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
+                             "frac": achieved / peaks["fp64_tflops"], "traffic": traffic,
+                             "note": "dominant kernel transport_kernel; algorithmic FP64 flop = exact event counters x "
+                                     "SURVEY 8d per-event figures; peak = FP64 FMA rate measured in this run by "
+                                     "artes_gpu_fma_peak (MEASURED_PEAKS.json holds no FP64 figure)",
+                             "flop_per_packet": fl / (world * args.steps * P), "fp32_peak_tflops": peaks["fp32_tflops"]},
+                "roofline_hbm": {"bound": "hbm", "achieved": per_launch_by / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": per_launch_by / k_s / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback",
+                                 "note": "algorithmic bytes are table reads served by L1/L2; HBM is not the bound of this path"},
+                "events_per_packet": {k: v / (world * args.steps * P) for k, v in agg.items()}}
+        if world == 1 and not args.no_cpu_baseline:
+            sample = int(args.cpu_sample)
+            dt, cores, _ = cpu_arm(atm, wl_kw, sample, 7)
+            line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} packets of the same workload; C++ restatement of ARTES.f90 "
+                                              f"(g++ -O3 -fopenmp; gfortran unavailable), all host threads"}
+        print(json.dumps(line))
+    t.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,307 @@
+"""GPU parity tests: libartes_gpu (through the C-ABI) against the CPU oracle and the committed
+golden fixtures.  Bar (BASELINE.json north_star): cell-crossing sequences bit-exact for an injected
+random stream; images within Monte Carlo tolerance (3 sigma of the combined photon noise)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from artes_b200 import abi, host
+from artes_b200.abi import make_launch
+from tools import atmospheres as A
+from test_oracle import random_interior_points
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODES = [abi.MODE_FAITHFUL, abi.MODE_FAST]
+
+
+def oblate_pair(atm, oblateness):
+    """oracle + gpu contexts with an oblate planet (src/ARTES.f90:469-471)."""
+    from oracle_lib import Oracle
+    from artes_b200.lib import GpuTransport
+    ox = 1.0 / (1.0 - oblateness)
+    o = Oracle(); depth = o.set_atmosphere(atm, oblateness=oblateness)
+    g = GpuTransport((0,))
+    g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront(), (ox, ox, 1.0))
+    g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth)
+    return o, g
+
+
+# ---- cell_face ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_template_rayleigh", "c2_hg_deck", "c4_mie_patches"])
+def test_cell_face_bit_exact(atmospheres, oracle_factory, gpu_factory, name):
+    atm = atmospheres(name)
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    pos, d, face, cell = random_interior_points(atm, 100000, 11)
+    oi, od = o.cell_face(pos, d, face, cell)
+    gi, gd = g.cell_face(pos, d, face, cell, mode=abi.MODE_FAITHFUL)
+    np.testing.assert_array_equal(oi, gi)
+    np.testing.assert_array_equal(od, gd)          # bit-exact distances
+    # second step: start ON the face just reached, in the next cell
+    ok = (oi[:, 6] == 0) & (oi[:, 5] == 0) & (oi[:, 2] >= 0)
+    pos2 = (pos + od[:, None] * d)[ok]
+    oi2, od2 = o.cell_face(pos2, d[ok], oi[ok, 0:2].copy(), oi[ok, 2:5].copy())
+    gi2, gd2 = g.cell_face(pos2, d[ok], oi[ok, 0:2].copy(), oi[ok, 2:5].copy(), mode=abi.MODE_FAITHFUL)
+    np.testing.assert_array_equal(oi2, gi2)
+    np.testing.assert_array_equal(od2, gd2)
+    # fast mode: same topology, distances to rounding
+    fi, fd = g.cell_face(pos, d, face, cell, mode=abi.MODE_FAST)
+    same = np.all(fi == oi, axis=1)
+    assert same.mean() > 0.9999
+    np.testing.assert_allclose(fd[same], od[same], rtol=1e-6)
+
+
+def test_cell_face_oblate_bit_exact(atmospheres):
+    atm = atmospheres("c4_mie_patches")
+    o, g = oblate_pair(atm, 0.06)
+    pos, d, face, cell = random_interior_points(atm, 50000, 12)
+    pos[:, 0:2] *= 1.0 / (1.0 - 0.06)
+    oi, od = o.cell_face(pos, d, face, cell)
+    gi, gd = g.cell_face(pos, d, face, cell, mode=abi.MODE_FAITHFUL)
+    np.testing.assert_array_equal(oi, gi)
+    np.testing.assert_array_equal(od, gd)
+
+
+# ---- injected-stream walk parity -------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "c2", "c4"])
+@pytest.mark.parametrize("mode", MODES)
+def test_trace_matches_committed_golden(atmospheres, gpu_factory, name, mode):
+    from golden.make_golden import build_case
+    gold = np.load(os.path.join(GOLDEN, f"golden_{name}.npz"))
+    atm, lt, lr, xi = build_case(name, atmospheres)
+    g, depth = gpu_factory(atm)
+    assert depth == int(gold["cell_depth"])
+    lt.mode = mode
+    t = g.trace(lt, xi)
+    np.testing.assert_array_equal(t["len"], gold["seq_len"])
+    np.testing.assert_array_equal(t["hash"], gold["seq_hash"])
+    np.testing.assert_allclose(t["fstate"][:, 3:7], gold["fstate"][:, 3:7], rtol=1e-6, atol=1e-12)
+    lr.mode = mode
+    r = g.run(lr)
+    np.testing.assert_array_equal(r["det"][2], gold["det"][2])                       # counts: integers
+    np.testing.assert_allclose(r["det"][0].sum(axis=(1, 2)), gold["det"][0].sum(axis=(1, 2)), rtol=1e-6, atol=1e-9)
+    assert r["stats"]["n_cell_face"] == int(gold["n_cell_face"]) and r["stats"]["n_scatter"] == int(gold["n_scatter"])
+
+
+CASES_LIVE = [
+    ("c1_template_rayleigh", dict(), 40000),
+    ("c2_hg_deck", dict(nx=1, ny=1, det_phi=math.radians(140.0)), 40000),
+    ("c4_mie_patches", dict(nx=64, ny=64, det_phi=math.radians(60.0)), 30000),
+    ("c4_mie_patches", dict(surface_albedo=0.7, det_phi=math.radians(20.0)), 20000),
+    ("c4_mie_patches", dict(stellar_direction=1, theta_star=math.radians(70.0), phi_star=math.radians(33.0)), 20000),
+    ("c2_hg_deck", dict(limb_emission=1, nx=1, ny=1, det_phi=math.radians(175.0)), 20000),
+    ("c3_molecular", dict(nx=1, ny=1), 20000),
+]
+
+
+@pytest.mark.parametrize("name,kw,n", CASES_LIVE)
+@pytest.mark.parametrize("mode", MODES)
+def test_crossing_sequences_bit_exact_vs_oracle(atmospheres, oracle_factory, gpu_factory, name, kw, n, mode):
+    """>= 1e5 injected-stream photons over the grid classes (1-D, 2-D with the equatorial plane face,
+    3-D with phi wrap): every (face, cell) sequence identical."""
+    atm = atmospheres(name)
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    xi = np.random.RandomState(hash(name) % 1000 + n).random_sample((n, 160))
+    L = make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, fstop=0.03, **kw)
+    ro = o.trace(L, xi, max_rec=4)
+    rg = g.trace(L, xi, max_rec=4)
+    same = (ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])
+    assert same.all(), f"{(~same).sum()} of {n} sequences differ"
+    np.testing.assert_array_equal(ro["head"], rg["head"])
+    assert ro["len"].mean() > 5
+    np.testing.assert_allclose(rg["fstate"][:, 3], ro["fstate"][:, 3], rtol=1e-5, atol=1e-14)   # Stokes I
+    assert (rg["fstate"][:, 7] == ro["fstate"][:, 7]).all()                                        # n_scatter
+
+
+def test_trace_thermal_source(atmospheres, oracle_factory):
+    from artes_b200.lib import GpuTransport
+    atm = atmospheres("c3_molecular")
+    o, depth = oracle_factory(atm, 0, 2)
+    vol = host.cell_volume(atm.rfront, atm.thetafront(), atm.phifront())
+    cw, lum, cdf = host.thermal_tables(depth, atm.k_abs[0], atm.temperature, vol, atm.wavelengths[0] * 1e-6,
+                                       atm.nr, atm.ntheta, atm.nphi)
+    o.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth, cw, cdf)
+    g = GpuTransport((0,))
+    g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+    g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth, cw, cdf)
+    xm = 1.3 * atm.rfront[-1]
+    n = 20000
+    xi = np.random.RandomState(5).random_sample((n, 160))
+    for emission in (1, 2):
+        for mode in MODES:
+            L = make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, fstop=0.03, photon_source=2,
+                            photon_emission=emission, nx=1, ny=1)
+            ro, rg = o.trace(L, xi), g.trace(L, xi)
+            assert ((ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])).all()
+        L = make_launch(mode=abi.MODE_FAST, n_photons=n, x_max=xm, y_max=xm, seed=3, photon_source=2,
+                        photon_emission=emission, nx=1, ny=1)
+        a, b = o.run(L), g.run(L)
+        np.testing.assert_allclose(b["flux"], a["flux"], rtol=1e-9)
+        np.testing.assert_allclose(b["det"][0, 0], a["det"][0, 0], rtol=1e-6)
+
+
+def test_trace_oblate_planet(atmospheres):
+    atm = atmospheres("c4_mie_patches")
+    o, g = oblate_pair(atm, 0.06)
+    xm = 1.06 * 1.3 * atm.rfront[-1]
+    n = 15000
+    xi = np.random.RandomState(8).random_sample((n, 160))
+    for mode in MODES:
+        L = make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, fstop=0.03, surface_albedo=0.5)
+        ro, rg = o.trace(L, xi), g.trace(L, xi)
+        assert ((ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])).all()
+
+
+# ---- images -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kw", [("c1_template_rayleigh", dict()),
+                                     ("c4_mie_patches", dict(nx=64, ny=64, det_phi=math.radians(60.0), surface_albedo=0.2))])
+@pytest.mark.parametrize("mode", MODES)
+def test_same_stream_images_agree(atmospheres, oracle_factory, gpu_factory, name, kw, mode):
+    """Same Philox stream on both sides: identical event counts, images equal to rounding."""
+    atm = atmospheres(name)
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(mode=mode, n_photons=60000, x_max=xm, y_max=xm, seed=21, flow_theta=1, flow_global=1, **kw)
+    a = o.run(L, flows=True)
+    b = g.run(L, flows=True)
+    for k in ("n_emit", "n_cell_face", "n_scatter", "n_peel", "n_surface", "n_draws", "n_error"):
+        assert a["stats"][k] == b["stats"][k], k
+    np.testing.assert_array_equal(a["det"][2], b["det"][2])
+    # libm differences (CUDA vs glibc, <= 2 ulp) are amplified along a multiple-scattering path, so single
+    # deposits agree to ~1e-5 relative; the sums agree far better.
+    scale = np.abs(a["det"][0]).max()
+    np.testing.assert_allclose(b["det"][0], a["det"][0], rtol=1e-4, atol=1e-7 * scale)
+    np.testing.assert_allclose(b["det"][1], a["det"][1], rtol=1e-4, atol=1e-9 * scale * scale)
+    np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=1e-7, atol=1e-9 * scale)
+    np.testing.assert_array_equal(a["err"], b["err"])
+    np.testing.assert_allclose(b["flow4"], a["flow4"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(b["flow3"], a["flow3"], rtol=1e-6, atol=1e-3 * np.abs(a["flow3"]).max())
+
+
+def three_sigma_check(da, db, min_count=30):
+    """SURVEY 8d gate 2: |I_a - I_b| <= 3 sqrt(sa^2 + sb^2) per pixel with sigma from the sum-of-squares
+    plane as in src/ARTES.f90:3490-3493; <= 1 % of pixels beyond 3 sigma, none beyond 5."""
+    ea, eb = host.stokes_error(da), host.stokes_error(db)
+    report = {}
+    for k, nm in enumerate("IQU"):
+        m = (da[2, k] >= min_count) & (db[2, k] >= min_count)
+        sig = np.sqrt(ea[k] ** 2 + eb[k] ** 2)[m]
+        z = np.abs(da[0, k] - db[0, k])[m] / sig
+        report[nm] = (int(m.sum()), float((z > 3).mean()), float(z.max()))
+    return report
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_statistical_parity_independent_streams(atmospheres, oracle_factory, gpu_factory, mode):
+    """Independent random streams (oracle: the reference's Marsaglia-Zaman generator; GPU: Philox)."""
+    import oracle_lib
+    atm = atmospheres("c4_mie_patches")
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    kw = dict(x_max=xm, y_max=xm, nx=16, ny=16, det_phi=math.radians(60.0))
+    a = o.run(make_launch(n_photons=400000, seed=101, **kw), rng=oracle_lib.RNG_MZ)
+    b = g.run(make_launch(mode=mode, n_photons=400000, seed=202, **kw))
+    rep = three_sigma_check(a["det"], b["det"])
+    for nm, (npix, frac3, zmax) in rep.items():
+        assert npix > 50, rep
+        assert frac3 <= 0.02 and zmax < 5.0, rep
+    # disk-integrated degree of polarisation with the reference's error propagation (:995-1002)
+    pa, pb = host.photometry(a["det"]), host.photometry(b["det"])
+    assert abs(pa[9] - pb[9]) < 3.0 * math.hypot(pa[10], pb[10]) + 1e-12
+
+
+def test_lambert_sphere_on_gpu(gpu_factory):
+    atm = A.lambert_sphere()
+    g, _ = gpu_factory(atm)
+    n = 400000
+    xm = 1.3 * atm.rfront[-1]
+    for a_deg in (30.0, 110.0):
+        a = math.radians(a_deg)
+        for mode in MODES:
+            r = g.run(make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, seed=3, surface_albedo=1.0, det_phi=a, nx=1, ny=1))
+            hit = (atm.rfront[0] / atm.rfront[-1]) ** 2
+            expect = hit * (2.0 / (3.0 * math.pi)) * (math.sin(a) + (math.pi - a) * math.cos(a)) / math.pi
+            assert abs(r["det"][0, 0].sum() / n / expect - 1.0) < 0.008
+
+
+# ---- API behaviour ---------------------------------------------------------------------------------------------
+def test_dense_matrix_entry_equals_compact(atmospheres, gpu_factory):
+    atm = atmospheres("c2_hg_deck")
+    g, depth = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(mode=abi.MODE_FAITHFUL, n_photons=30000, x_max=xm, y_max=xm, seed=4)
+    a = g.run(L)
+    g.set_wavelength_dense(atm.k_sca[0], atm.k_abs[0], atm.dense_matrix(0), depth)
+    b = g.run(L)
+    np.testing.assert_array_equal(a["det"][2], b["det"][2])
+    np.testing.assert_allclose(a["det"][0], b["det"][0], rtol=1e-9, atol=1e-12)
+
+
+def test_async_equals_sync_and_empty_launch(atmospheres, gpu_factory):
+    atm = atmospheres("c1_template_rayleigh")
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(mode=abi.MODE_FAST, n_photons=20000, x_max=xm, y_max=xm, seed=6)
+    a = g.run(L)
+    g.run_async(L)
+    b = g.wait()
+    np.testing.assert_array_equal(a["det"][2], b["det"][2])
+    np.testing.assert_allclose(a["det"][0], b["det"][0], rtol=1e-9, atol=1e-12)
+    z = g.run(make_launch(mode=abi.MODE_FAST, n_photons=0, x_max=xm, y_max=xm))
+    assert z["det"].sum() == 0 and z["stats"]["n_emit"] == 0
+
+
+def test_photon_id_sharding_is_additive(atmospheres, gpu_factory):
+    """Two shards with disjoint photon-id ranges = one launch over the union (multi-GPU invariant)."""
+    atm = atmospheres("c2_hg_deck")
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=12, nx=8, ny=8)
+    full = g.run(make_launch(n_photons=50000, **kw))
+    s1 = g.run(make_launch(n_photons=20000, photon_id_base=0, **kw))
+    s2 = g.run(make_launch(n_photons=30000, photon_id_base=20000, **kw))
+    np.testing.assert_array_equal(full["det"][2], s1["det"][2] + s2["det"][2])
+    np.testing.assert_allclose(full["det"][0], s1["det"][0] + s2["det"][0], rtol=1e-9, atol=1e-12)
+    assert full["stats"]["n_cell_face"] == s1["stats"]["n_cell_face"] + s2["stats"]["n_cell_face"]
+
+
+def test_errors_are_reported_not_fatal(atmospheres):
+    from artes_b200.lib import ArtesGpuError, GpuTransport
+    atm = atmospheres("c1_template_rayleigh")
+    g = GpuTransport((0,))
+    xm = 1.3 * atm.rfront[-1]
+    with pytest.raises(ArtesGpuError):
+        g.run(make_launch(n_photons=10, x_max=xm, y_max=xm))              # no grid yet
+    g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+    g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)
+    with pytest.raises(ArtesGpuError):
+        g.run(make_launch(n_photons=10, x_max=xm, y_max=xm, photon_source=2))   # thermal tables missing
+    bad = make_launch(n_photons=10, x_max=xm, y_max=xm)
+    bad.struct_size = 8
+    with pytest.raises(ArtesGpuError):
+        g.run(bad)
+
+
+def test_full_size_invariants_c4(atmospheres, gpu_factory):
+    """BASELINE config C4 at its full image size and 2e6 photons: size-independent properties."""
+    atm = atmospheres("c4_mie_patches")
+    t = host.Transport(atm, host.Params(nx=64, ny=64, det_phi=math.radians(60.0)), mode=abi.MODE_FAST)
+    det, phot, res = t.radiative_transfer(2_000_000, seed=4)
+    st = res["stats"]
+    assert st["n_emit"] == 2_000_000 and st["n_error"] == 0
+    assert st["n_peel"] == st["n_scatter"]                      # star source, black surface: one peel per scattering
+    assert abs(det[0, 0].sum() - phot[0]) <= 1e-12 * abs(phot[0])   # image sum = photometry(1)
+    np.testing.assert_array_equal(det[2, 1], det[2, 2]); np.testing.assert_array_equal(det[2, 1], det[2, 3])
+    assert (det[2, 0] >= det[2, 1]).all() and det[2, 0].sum() <= st["n_peel"]
+    assert (det[0, 0] >= 0).all() and (np.abs(det[0, 1]) <= det[0, 0] + 1e-30).all()
+    # the planet is symmetric about the equator and the detector sits in the equatorial plane:
+    top, bot = det[0, 0][32:].sum(), det[0, 0][:32].sum()
+    assert abs(top / bot - 1.0) < 0.02
+    t.close()
