@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -141,12 +142,22 @@ int ensure_outputs(artes_gpu_ctx* ctx, DeviceState& d, size_t n_d) {
     return 0;
 }
 
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    int x = std::atoi(v);
+    return x < 1 ? 1 : (x > 32 ? 32 : x);
+}
+
 // LaunchArgs from the ABI struct: host-evaluated detector / star geometry (src/ARTES.f90:495-502, 1080-1109, 4628, 4871)
 void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
     a.n_photons = L.n_photons; a.id_base = L.photon_id_base; a.seed = L.seed;
     a.photon_source = L.photon_source; a.photon_scattering = L.photon_scattering; a.photon_emission = L.photon_emission;
     a.stellar_direction = L.stellar_direction; a.limb_emission = L.limb_emission;
     a.flow_global = L.flow_global; a.flow_theta = L.flow_theta; a.nx = L.nx; a.ny = L.ny;
+    // warp regrouping thresholds; tunable for experiments through the environment
+    static const int defer_events = env_int("ARTES_DEFER_EVENTS", 12), defer_refill = env_int("ARTES_DEFER_REFILL", 4);
+    a.defer_events = defer_events; a.defer_refill = defer_refill;
     a.fstop = L.fstop; a.photon_minimum = L.photon_minimum; a.photon_bias = L.photon_bias;
     a.surface_albedo = L.surface_albedo; a.theta_star = L.theta_star; a.phi_star = L.phi_star;
     a.x_max = L.x_max; a.y_max = L.y_max;

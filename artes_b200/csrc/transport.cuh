@@ -143,54 +143,63 @@ __device__ __forceinline__ void cell_face(const double* __restrict__ sm, const S
     const double C1 = a * a * x * x + b * b * y * y,     C2 = c * c * z * z;
     const double qa_s = A1 + A2, qb_s = 2.0 * (B1 + B2), qc_s = C1 + C2;
 
-    double d00 = 0.0, d01 = 0.0, d02 = 0.0, d10 = 0.0, d11 = 0.0, d12 = 0.0, d20 = 0.0, d21 = 0.0;
-
-    // ---- radial :2885-3010
-    {
-        bool do_in, do_out, do_same = false;
-        if (cf0 == 1) { do_in = (c0 == cf1 - 1); do_out = (!do_in) && (c0 == cf1); do_same = do_in; }
-        else { do_in = true; do_out = true; }
-        if (do_in)   { double r = sm[f00]; d00 = solve_pick(qa_s, qb_s, qc_s - r * r, 1.e-15, 0, 0.0, 0.0); }
-        if (do_out)  { double r = sm[f01]; d01 = solve_pick(qa_s, qb_s, qc_s - r * r, 1.e-15, 0, 0.0, 0.0); }
-        if (do_same) { double r = sm[f02]; d02 = solve_pick(qa_s, qb_s, qc_s - r * r, 1.e-3, 0, 0.0, 0.0); }
+    // Which of the (up to) six quadric candidates exist for this lane: bit k of `act`,
+    // k = 0..2 spheres (inner, outer, same), k = 3..5 cones / equatorial plane (inner, outer, same).
+    unsigned act = 0u;
+    if (cf0 == 1) {  // radial :2885-2964
+        if (c0 == cf1 - 1) act |= 1u | 4u;
+        else if (c0 == cf1) act |= 2u;
+    } else act |= 1u | 2u;
+    if (cf0 == 2) {  // polar :3020-3171
+        if (c1 == cf1 - 1 && f10 != 0) act |= 8u;
+        else if (c1 == cf1 && f11 != T.nt) act |= 16u;
+        const double tf = sm[lay.o_tf + f12];
+        if (((tf < PI / 2.0 && c1 == cf1 - 1) || (tf > PI / 2.0 && c1 == cf1)) && tplane[f12] == 1) act |= 32u;
+    } else {
+        if (f10 < 0 || f10 > T.nt) f10 = 0;  // error 029 (log only)
+        if (f10 != 0) act |= 8u;
+        if (f11 != T.nt) act |= 16u;
     }
+    const unsigned long long packS = (unsigned long long)(unsigned)(f00 & 0xffff) | ((unsigned long long)(unsigned)(f01 & 0xffff) << 16) |
+                                     ((unsigned long long)(unsigned)(f02 & 0xffff) << 32);
+    const unsigned long long packC = (unsigned long long)(unsigned)(f10 & 0xffff) | ((unsigned long long)(unsigned)(f11 & 0xffff) << 16) |
+                                     ((unsigned long long)(unsigned)(f12 & 0xffff) << 32);
 
-    // ---- polar :3014-3290
-    {
-        bool do_in, do_out, do_same = false;
-        if (cf0 == 2) {
-            do_in = (c1 == cf1 - 1) && (f10 != 0);
-            do_out = (!do_in) && (c1 == cf1) && (f11 != T.nt);
-            double tf = sm[lay.o_tf + f12];
-            do_same = ((tf < PI / 2.0 && c1 == cf1 - 1) || (tf > PI / 2.0 && c1 == cf1)) && (tplane[f12] == 1);
-        } else {
-            if (f10 < 0 || f10 > T.nt) f10 = 0;  // error 029 (log only)
-            do_in = (f10 != 0);
-            do_out = (f11 != T.nt);
+    // Nearest face, src/ARTES.f90:3358-3418: the reference scans distance(i,j) with j (inner, outer, same)
+    // outer and i (r, theta, phi) inner and a strict <, first over candidates > 1e-9 and, if there is none,
+    // over candidates > 1e-12.  Equivalent: minimum by (distance, scan position ord = 3 j + i).
+    double fd = 1.e100, fd12 = 1.e100;
+    int sel = -1, sel12 = -1;       // ord | face << 4
+    auto consider = [&](double d, int ord, int face) {
+        if (d > 1.e-9 && (d < fd || (d == fd && ord < (sel & 15)))) { fd = d; sel = ord | (face << 4); }
+        if (d > 1.e-12 && (d < fd12 || (d == fd12 && ord < (sel12 & 15)))) { fd12 = d; sel12 = ord | (face << 4); }
+    };
+
+    // One solver body for all quadrics: the loop keeps the warp converged (every lane solves its k-th
+    // candidate in the same instruction stream) and keeps the kernel small enough for the instruction cache.
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) {
+        if (!((act >> k) & 1u)) continue;
+        const bool cone = k >= 3;
+        const int j = cone ? k - 3 : k;
+        const int f = (int)(((cone ? packC : packS) >> (16 * j)) & 0xffffull);
+        double qa = qa_s, qb = qb_s, qc;
+        int mir = 0;
+        double d;
+        if (!cone) { const double r = sm[f]; qc = qc_s - r * r; }
+        else {
+            const double t = sm[lay.o_tt + f], tf = sm[lay.o_tf + f];
+            mir = (tf > PI / 2.0) ? 1 : ((tf < PI / 2.0) ? -1 : 0);
+            qa = A1 - A2 * t * t; qb = 2.0 * (B1 - B2 * t * t); qc = C1 - C2 * t * t;
         }
-        if (do_in) {
-            if (tplane[f10] == 1) {
-                double t = sm[lay.o_tt + f10], tf = sm[lay.o_tf + f10];
-                int mir = (tf > PI / 2.0) ? 1 : ((tf < PI / 2.0) ? -1 : 0);
-                d10 = solve_pick(A1 - A2 * t * t, 2.0 * (B1 - B2 * t * t), C1 - C2 * t * t, 1.e-15, mir, z, n2);
-            } else if (tplane[f10] == 2) {
-                if (-z / n2 > 0.0 && n2 > 1.e-15) d10 = -z / n2;
+        if (cone && tplane[f] != 1) {  // equatorial plane :3068, :3118 (never a "same" candidate)
+            d = 0.0;
+            if (tplane[f] == 2) {
+                if (j == 0) { if (-z / n2 > 0.0 && n2 > 1.e-15) d = -z / n2; }
+                else if (j == 1) { if (-z / n2 > 0.0 && n2 < -1.e-15) d = -z / n2; }
             }
-        }
-        if (do_out) {
-            if (tplane[f11] == 1) {
-                double t = sm[lay.o_tt + f11], tf = sm[lay.o_tf + f11];
-                int mir = (tf > PI / 2.0) ? 1 : ((tf < PI / 2.0) ? -1 : 0);
-                d11 = solve_pick(A1 - A2 * t * t, 2.0 * (B1 - B2 * t * t), C1 - C2 * t * t, 1.e-15, mir, z, n2);
-            } else if (tplane[f11] == 2) {
-                if (-z / n2 > 0.0 && n2 < -1.e-15) d11 = -z / n2;
-            }
-        }
-        if (do_same) {
-            double t = sm[lay.o_tt + f12], tf = sm[lay.o_tf + f12];
-            int mir = (tf > PI / 2.0) ? 1 : ((tf < PI / 2.0) ? -1 : 0);
-            d12 = solve_pick(A1 - A2 * t * t, 2.0 * (B1 - B2 * t * t), C1 - C2 * t * t, 1.e-3, mir, z, n2);
-        }
+        } else d = solve_pick(qa, qb, qc, j == 2 ? 1.e-3 : 1.e-15, mir, z, n2);
+        consider(d, 3 * j + (cone ? 1 : 0), f);
     }
 
     // ---- azimuthal :3292-3350 (full planes; guards as in the reference, including solutions_p(1) in the
@@ -207,7 +216,7 @@ __device__ __forceinline__ void cell_face(const double* __restrict__ sm, const S
             double den = b * n1 * pc - a * n0 * ps;
             if (fabs(den) > 0.0) {
                 sp1 = (a * x * ps - b * y * pc) / den;
-                if (sp1 > 1.e-15 && sp1 < 1.e100) d20 = sp1;
+                if (sp1 > 1.e-15 && sp1 < 1.e100) consider(sp1, 2, f20);
             }
         }
         if (do_out) {
@@ -216,30 +225,17 @@ __device__ __forceinline__ void cell_face(const double* __restrict__ sm, const S
             double guard = plain_guard ? (n1 * pc - n0 * ps) : den;
             if (fabs(guard) > 0.0) {
                 double sp2 = (a * x * ps - b * y * pc) / den;
-                if (sp2 > 1.e-15 && sp1 < 1.e100) d21 = sp2;
+                if (sp2 > 1.e-15 && sp1 < 1.e100) consider(sp2, 5, f21);
             }
         }
     }
-
-    // ---- nearest face :3358-3418: j (inner, outer, same) outer loop, i (r, theta, phi) inner, strict <
-    double fd = 1.e100;
-    int li = -1, lf = 0;
-#define ARTES_TRY(D, I, F, THR) if ((D) > (THR) && (D) < fd) { fd = (D); li = (I); lf = (F); }
-    ARTES_TRY(d00, 0, f00, 1.e-9) ARTES_TRY(d10, 1, f10, 1.e-9) ARTES_TRY(d20, 2, f20, 1.e-9)
-    ARTES_TRY(d01, 0, f01, 1.e-9) ARTES_TRY(d11, 1, f11, 1.e-9) ARTES_TRY(d21, 2, f21, 1.e-9)
-    ARTES_TRY(d02, 0, f02, 1.e-9) ARTES_TRY(d12, 1, f12, 1.e-9)
-    if (li < 0) {
-        fd = 1.e100;
-        ARTES_TRY(d00, 0, f00, 1.e-12) ARTES_TRY(d10, 1, f10, 1.e-12) ARTES_TRY(d20, 2, f20, 1.e-12)
-        ARTES_TRY(d01, 0, f01, 1.e-12) ARTES_TRY(d11, 1, f11, 1.e-12) ARTES_TRY(d21, 2, f21, 1.e-12)
-        ARTES_TRY(d02, 0, f02, 1.e-12) ARTES_TRY(d12, 1, f12, 1.e-12)
-    }
-#undef ARTES_TRY
+    if (sel < 0) { sel = sel12; fd = fd12; }
+    const int li = (sel < 0) ? -1 : ((sel & 15) % 3);
+    const int lf = (sel < 0) ? 0 : (sel >> 4);
     o.dist = fd; o.exit = false; o.err = 0;
     o.nf0 = 0; o.nf1 = 0; o.co0 = 0; o.co1 = 0; o.co2 = 0;
     if (li < 0) { o.err = 31; return; }
     o.nf0 = li + 1; o.nf1 = lf;
-    if (lf == -999) { o.err = 33; return; }
 
     // next_cell :2671-2798
     if (li == 0) {
@@ -510,6 +506,117 @@ __device__ __forceinline__ int sample_angles(const double* __restrict__ sm, cons
     return 0;
 }
 
+
+#if !ARTES_FAITHFUL
+// ---------------------------------------------------------------------------------------------
+// Fast-mode event math.  Same formulas as the reference's spherical trigonometry, with every
+// acos/cos/atan2 round trip replaced by its algebraic identity:
+//   mueller(psi) == (cos 2psi, sin 2psi)                       (src/ARTES.f90:1942-1953 is the sign of sin 2psi)
+//   beta2 = acos(nc2)  ->  cos 2beta2 = 2 nc2^2 - 1, sin 2beta2 = 2 nc2 sqrt(1 - nc2^2)      (:1730-1735)
+//   phi_new = phi_old +- acos(nc) -> rotation of (cos phi_old, sin phi_old) by (nc, +-sqrt(1-nc^2)) (:1999-2050)
+//   the quadrant test of peel_photon (:4904-4914) == sign of (d x det)_z
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void matrix_at_deg(const DevTables& T, int cellidx, double deg, double F[16]) {
+    int lo, up;
+    const double fl = floor(deg);
+    if (deg - fl > 0.5) { up = (int)fl + 2; lo = (int)fl + 1; }
+    else { up = (int)fl + 1; lo = (int)fl; }
+    const double* base = T.M + (size_t)__ldg(T.c2u + cellidx) * (180 * 16);
+    if (up <= 1 || lo >= 180) {
+        const double2* m = reinterpret_cast<const double2*>(base + (up <= 1 ? 0 : 179) * 16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { double2 v = __ldg(m + i); F[2 * i] = v.x; F[2 * i + 1] = v.y; }
+    } else {
+        const double2* m0 = reinterpret_cast<const double2*>(base + (lo - 1) * 16);
+        const double2* m1 = reinterpret_cast<const double2*>(base + (up - 1) * 16);
+        const double w = deg - ((double)lo - 0.5);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double2 v0 = __ldg(m0 + i), v1 = __ldg(m1 + i);
+            F[2 * i] = (v1.x - v0.x) * w + v0.x;
+            F[2 * i + 1] = (v1.y - v0.y) * w + v0.y;
+        }
+    }
+}
+
+// polarization_rotation with the rotation angles given by their double-angle cosines / sines:
+// (c2a, s2a) = mueller(beta); nc2 = cos(beta2); flip = (beta >= pi) selects mueller(-beta2).
+__device__ __forceinline__ int polrot_fast(double c2a, double s2a, bool flip, double nc2, const double Sin[4],
+                                           const double F[16], double Sout[4], bool peeling, int& soft) {
+    if (!(fabs(nc2) < 1.00001)) return 11;
+    nc2 = fmin(fmax(nc2, -1.0), 1.0);
+    double r0 = Sin[0], r1 = c2a * Sin[1] + s2a * Sin[2], r2 = c2a * Sin[2] - s2a * Sin[1], r3 = Sin[3];
+    double s[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s[r] = F[4 * r] * r0 + F[4 * r + 1] * r1 + F[4 * r + 2] * r2 + F[4 * r + 3] * r3;
+    if (!peeling) {
+        if (s[0] > 0.0) { double nrm = r0 / s[0]; s[0] = r0; s[1] *= nrm; s[2] *= nrm; s[3] *= nrm; }
+        else soft = 12;
+    }
+    const double c2 = 2.0 * nc2 * nc2 - 1.0;
+    double s2 = 2.0 * nc2 * sqrt(fmax(1.0 - nc2 * nc2, 0.0));
+    if (flip) s2 = -s2;
+    Sout[0] = s[0];
+    Sout[1] = c2 * s[1] + s2 * s[2];
+    Sout[2] = c2 * s[2] - s2 * s[1];
+    Sout[3] = s[3];
+    return 0;
+}
+#endif
+
+
+#if !ARTES_FAITHFUL
+struct FastAngles { double alpha, sT, deg, cb, sb; bool flip; };
+
+// scattering_angle_sampling :1534-1661 in fast mode: cum(i) of both CDFs is a linear combination of
+// host-built prefix tables, inverted by binary search; returns cos/sin of the sampled angles directly.
+template <bool TRACE>
+__device__ __forceinline__ int sample_angles_fast(const KernelArgs& A, Rng& rng, const double S[4], int cellidx, FastAngles& g) {
+    const DevTables& T = A.T;
+    const int u = __ldg(T.c2u + cellidx);
+    const double p11 = __ldg(T.p1k + 4 * u), p12 = __ldg(T.p1k + 4 * u + 1), p13 = __ldg(T.p1k + 4 * u + 2), p14 = __ldg(T.p1k + 4 * u + 3);
+    const double Ac = p11 * S[0] + p14 * S[3], Bc = p12 * S[1] + p13 * S[2], Cc = p12 * S[2] - p13 * S[1];
+    const double* pc2 = T.cdfA;
+    const double* ps2 = T.cdfA + 181;
+    auto cumA = [&](int i) { return Ac * (double)i + Bc * __ldg(pc2 + i) + Cc * __ldg(ps2 + i); };
+    double xi = rng_next<TRACE>(rng, A);
+    double samp = xi * cumA(180);
+    int lo = 0, hi = 180;  // smallest i in 1..180 with cum(i) >= samp
+    double ylo = 0.0, yhi = cumA(180);
+#pragma unroll 1
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; double y = cumA(mid); if (y >= samp) { hi = mid; yhi = y; } else { lo = mid; ylo = y; } }
+    double fr = (samp - ylo) / (yhi - ylo);
+    if (!(fr == fr)) { rng_next<TRACE>(rng, A); return 6; }
+    fr = fmin(fmax(fr, 0.0), 1.0);
+    double beta = (fr + (double)lo) * (PI / 180.0);
+    xi = rng_next<TRACE>(rng, A);
+    sincos(beta, &g.sb, &g.cb);
+    g.flip = xi > 0.5;                       // beta + pi  (:1589-1590)
+    if (g.flip) { g.sb = -g.sb; g.cb = -g.cb; }
+    const double c2b = g.cb * g.cb - g.sb * g.sb, s2b = 2.0 * g.sb * g.cb;
+    const double w1 = S[0], w2 = c2b * S[1] + s2b * S[2], w3 = c2b * S[2] - s2b * S[1], w4 = S[3];
+    const double2* tab = reinterpret_cast<const double2*>(T.cdfP + (size_t)u * (181 * 4));
+    auto cumP = [&](int i) {
+        double2 q01 = __ldg(tab + 2 * i), q23 = __ldg(tab + 2 * i + 1);
+        return w1 * q01.x + w2 * q01.y + w3 * q23.x + w4 * q23.y;
+    };
+    xi = rng_next<TRACE>(rng, A);
+    yhi = cumP(180); ylo = 0.0;
+    samp = xi * yhi;
+    lo = 0; hi = 180;
+#pragma unroll 1
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; double y = cumP(mid); if (y >= samp) { hi = mid; yhi = y; } else { lo = mid; ylo = y; } }
+    fr = (samp - ylo) / (yhi - ylo);
+    if (!(fr == fr)) return 7;
+    fr = fmin(fmax(fr, 0.0), 1.0);
+    g.deg = fr + (double)lo;
+    sincos(g.deg * (PI / 180.0), &g.sT, &g.alpha);
+    if (g.alpha >= 1.0) { g.alpha = 1.0 - 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
+    if (g.alpha <= -1.0) { g.alpha = -1.0 + 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
+    return 0;
+}
+#endif
+
 // initial_cell :2605-2669
 __device__ __forceinline__ void initial_cell(const double* __restrict__ sm, const SmLayout& lay, const DevTables& T,
                                              double x, double y, double z, int& c0, int& c1, int& c2) {
@@ -531,9 +638,8 @@ __device__ __forceinline__ void tuple_hash(unsigned long long& h, int v) { h ^= 
 // ---------------------------------------------------------------------------------------------
 // the transport kernel
 // ---------------------------------------------------------------------------------------------
-#ifndef ARTES_DEFER_SCATTER
-#define ARTES_DEFER_SCATTER 1   // lanes needed before the (heavy) scattering event runs; 1 = immediately
-#endif
+// Regrouping thresholds are launch parameters (LaunchArgs::defer_events / defer_refill): the number of
+// lanes of a warp that must wait for the heavy events / for new photons before those code paths run.
 
 template <bool TRACE>
 __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant__ KernelArgs A) {
@@ -620,7 +726,9 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
 
     for (;;) {
         // ================= A. refill + emission (emit_photon :1008-1268) =================
-        const unsigned need = __ballot_sync(FULL, ph == PH_NEW);
+        const unsigned need0 = __ballot_sync(FULL, ph == PH_NEW);
+        const unsigned walk0 = __ballot_sync(FULL, ph == PH_PRE || ph == PH_WALK || ph == PH_PEEL);
+        const unsigned need = (__popc(need0) >= L.defer_refill || walk0 == 0u) ? need0 : 0u;
         if (need) {
             const int leader = __ffs(need) - 1;
             unsigned long long base = 0;
@@ -822,8 +930,34 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
             }
         }
 
+        // ================= D. interaction point reached: survival + start of the peel-off =================
+        if (ph == PH_SCAT) {  // :788-815
+            bool alive = L.photon_scattering != 0;
+            if (TRACE && rng.exhausted) alive = false;
+            if (alive) {
+                double xi = rng_next<TRACE>(rng, A);
+                if (xi < L.fstop) alive = false;
+            }
+            if (alive) {
+                const double alb = __ldg(T.albedo + c0 + T.nr * (c1 + T.nt * c2));
+                if (alb < 1.0 && alb > 0.0) {
+                    double gamma = alb / (1.0 - L.fstop);
+                    S[0] = gamma * S[0]; S[1] = gamma * S[1]; S[2] = gamma * S[2]; S[3] = gamma * S[3];
+                }
+                if (S[0] <= L.photon_minimum) alive = false;
+            }
+            if (!alive) retire();
+            else { ++n_peel; pk = PK_SCATTER; start_probe(0); ph = PH_PEEL; }
+        }
+
+        // ---- ballot regrouping: the heavy events below run only when enough lanes of the warp wait for
+        // them (or nobody is left walking), so that their instructions are issued for many lanes at once.
+        const unsigned m_evt = __ballot_sync(FULL, ph == PH_PEELDONE || ph == PH_SCAT2);
+        const unsigned m_walk = __ballot_sync(FULL, ph == PH_PRE || ph == PH_WALK || ph == PH_PEEL);
+        const bool run_events = m_evt && (__popc(m_evt) >= L.defer_events || m_walk == 0u);
+
         // ================= C. a peel walk ended: weight + deposit =================
-        if (ph == PH_PEELDONE) {
+        if (run_events && ph == PH_PEELDONE) {
             const bool ok = peel_exit && tacc < 50.0;
             if (pk == PK_THERMAL) {  // :4571-4596
                 if (ok) {
@@ -856,6 +990,7 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
                     if (mu >= 1.0) mu = 1.0 - 1.e-10;
                     else if (mu <= -1.0) mu = -1.0 + 1.e-10;
                     double F[16];
+#if ARTES_FAITHFUL
                     matrix_at(T, c0 + T.nr * (c1 + T.nt * c2), acos(mu), F);
                     double phi_old = atan2(dy, dx);
                     if (phi_old < 0.0) phi_old = phi_old + 2.0 * PI;
@@ -883,58 +1018,90 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
                             else err_count(53);
                         }
                     }
+#else
+                    matrix_at_deg(T, c0 + T.nr * (c1 + T.nt * c2), acos(mu) * (180.0 / PI), F);
+                    if (!(fabs(dz) < 1.0)) err_count(45);
+                    else {
+                        const double smu = sqrt(1.0 - mu * mu);
+                        double nc = (L.det[2] - dz * mu) / (smu * sqrt(1.0 - dz * dz));
+                        if (!(nc == nc)) err_count(44);
+                        else {
+                            nc = fmin(fmax(nc, -1.0), 1.0);
+                            const double cr = dy * L.det[0] - dx * L.det[1];                 // sin(phi_old - phi_new) > 0 ?
+                            const bool flip = (cr > 0.0) || (cr == 0.0 && dx * L.det[0] + dy * L.det[1] > 0.0);
+                            const double c2a = 2.0 * nc * nc - 1.0;
+                            double s2a = 2.0 * nc * sqrt(fmax(1.0 - nc * nc, 0.0));
+                            if (flip) s2a = -s2a;
+                            const double nc2 = (dz - L.det[2] * mu) / (smu * sqrt(1.0 - L.det[2] * L.det[2]));
+                            double so[4];
+                            int soft = 0;
+                            int e = (fabs(L.det[2]) < 1.0) ? polrot_fast(c2a, s2a, flip, nc2, S, F, so, true, soft) : 16;
+                            if (e) err_count(e);
+                            else if (w * so[0] > 0.0 && w * so[0] < 1.e100) deposit(w * so[0], -(w * so[1]), w * so[2], w * so[3], true);
+                            else err_count(53);
+                        }
+                    }
+#endif
                 }
                 ph = PH_SCAT2;
             }
         }
 
-        // ================= D. interaction point reached: survival + start of the peel-off =================
-        if (ph == PH_SCAT) {  // :788-815
-            bool alive = L.photon_scattering != 0;
-            if (TRACE && rng.exhausted) alive = false;
-            if (alive) {
-                double xi = rng_next<TRACE>(rng, A);
-                if (xi < L.fstop) alive = false;
-            }
-            if (alive) {
-                const double alb = __ldg(T.albedo + c0 + T.nr * (c1 + T.nt * c2));
-                if (alb < 1.0 && alb > 0.0) {
-                    double gamma = alb / (1.0 - L.fstop);
-                    S[0] = gamma * S[0]; S[1] = gamma * S[1]; S[2] = gamma * S[2]; S[3] = gamma * S[3];
-                }
-                if (S[0] <= L.photon_minimum) alive = false;
-            }
-            if (!alive) retire();
-            else { ++n_peel; pk = PK_SCATTER; start_probe(0); ph = PH_PEEL; }
-        }
-
         // ================= E. scattering event (scatter_photon :1434-1532 + polarization_rotation) ==========
-        {
-            const unsigned want = __ballot_sync(FULL, ph == PH_SCAT2);
-            const unsigned walking = __ballot_sync(FULL, ph == PH_PRE || ph == PH_WALK || ph == PH_PEEL || ph == PH_NEW);
-            const bool run_now = want && (ARTES_DEFER_SCATTER <= 1 || __popc(want) >= ARTES_DEFER_SCATTER || walking == 0u);
-            if (run_now && ph == PH_SCAT2) {
-                ++n_sc; ++t_nsc;
-                const int ci = c0 + T.nr * (c1 + T.nt * c2);
-                double alpha, beta, e0 = 0, e1 = 0, e2 = 0;
-                int e = sample_angles<TRACE>(sm, lay, A, rng, S, ci, alpha, beta);
-                if (!e) e = direction_cosine(alpha, beta, dx, dy, dz, e0, e1, e2);
-                if (!e && !(fabs(alpha) < 1.0)) e = 50;
-                if (!e) {
-                    double F[16], Sn[4];
-                    matrix_at(T, ci, acos(alpha), F);
-                    int soft = 0;
-                    e = polarization_rotation(alpha, beta, S, F, dz, e2, Sn, false, soft);
-                    if (soft) err_count(soft);
-                    if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
-                }
-                if (e) { err_count(e); ++n_err; retire(); }
+        if (run_events && ph == PH_SCAT2) {
+            ++n_sc; ++t_nsc;
+            const int ci = c0 + T.nr * (c1 + T.nt * c2);
+            double e0 = 0, e1 = 0, e2 = 0;
+            int e;
+#if ARTES_FAITHFUL
+            double alpha, beta;
+            e = sample_angles<TRACE>(sm, lay, A, rng, S, ci, alpha, beta);
+            if (!e) e = direction_cosine(alpha, beta, dx, dy, dz, e0, e1, e2);
+            if (!e && !(fabs(alpha) < 1.0)) e = 50;
+            if (!e) {
+                double F[16], Sn[4];
+                matrix_at(T, ci, acos(alpha), F);
+                int soft = 0;
+                e = polarization_rotation(alpha, beta, S, F, dz, e2, Sn, false, soft);
+                if (soft) err_count(soft);
+                if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
+            }
+#else
+            FastAngles g;
+            e = sample_angles_fast<TRACE>(A, rng, S, ci, g);
+            if (!e) {
+                // direction_cosine :1962-2052 without the acos / cos round trip
+                const double cto = dz / sqrt(dx * dx + dy * dy + dz * dz);
+                const double sto = sqrt(1.0 - cto * cto);
+                const double ctn = cto * g.alpha + sto * g.sT * g.cb;
+                const double stn = sqrt(1.0 - ctn * ctn);
+                double nc = (g.alpha - ctn * cto) / (stn * sto);
+                if (!(nc == nc)) e = 20;
                 else {
-                    double xi = rng_next<TRACE>(rng, A);  // :845
-                    tau = -log(1.0 - xi);
-                    tau_run = 0.0;
-                    start_probe(0); ph = PH_WALK;
+                    if (nc >= 1.0) nc = 1.0 - 1.e-10; else if (nc <= -1.0) nc = -1.0 + 1.e-10;
+                    const double sD = sqrt(1.0 - nc * nc) * (g.flip ? -1.0 : 1.0);
+                    const double rho = sqrt(dx * dx + dy * dy);
+                    const double cph = rho > 0.0 ? dx / rho : 1.0, sph = rho > 0.0 ? dy / rho : 0.0;
+                    e0 = stn * (cph * nc - sph * sD); e1 = stn * (sph * nc + cph * sD); e2 = ctn;
+                    if (!(fabs(e2) < 1.0)) e = 16;
                 }
+            }
+            if (!e) {
+                double F[16], Sn[4];
+                matrix_at_deg(T, ci, g.deg, F);
+                const double nc2 = (dz - e2 * g.alpha) / (g.sT * sqrt(1.0 - e2 * e2));
+                int soft = 0;
+                e = polrot_fast(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
+                if (soft) err_count(soft);
+                if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
+            }
+#endif
+            if (e) { err_count(e); ++n_err; retire(); }
+            else {
+                double xi = rng_next<TRACE>(rng, A);  // :845
+                tau = -log(1.0 - xi);
+                tau_run = 0.0;
+                start_probe(0); ph = PH_WALK;
             }
         }
 

@@ -187,3 +187,19 @@ def test_oracle_reproduces_golden(oracle_factory, atmospheres, name):
     r = o.run(launch_run)
     np.testing.assert_allclose(r["det"], g["det"], rtol=1e-9, atol=1e-300)
     assert CASES[name]["trace_n"] == len(g["seq_len"])
+
+
+def test_batch_noise_methodology_on_cpu(oracle_factory, atmospheres):
+    """The statistical gate of the GPU tests, exercised CPU-only: the reference's Marsaglia-Zaman stream
+    against the Philox stream through the same oracle must agree within the batch-estimated noise."""
+    from test_gpu_parity import batch_z
+    atm = atmospheres("c4_mie_patches")
+    o, _ = oracle_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    kw = dict(x_max=xm, y_max=xm, nx=12, ny=12, det_phi=math.radians(60.0))
+    K, n = 12, 15000
+    ba = [o.run(make_launch(n_photons=n, seed=100 + i, **kw), rng=OL.RNG_MZ)["det"] for i in range(K)]
+    bb = [o.run(make_launch(n_photons=n, seed=7, photon_id_base=i * n, **kw), rng=OL.RNG_PHILOX)["det"] for i in range(K)]
+    rep = batch_z(ba, bb, min_count=10)
+    for nm, (npix, frac3, zmax, zrms) in rep.items():
+        assert npix > 30 and frac3 <= 0.04 and zmax < 5.5 and zrms < 1.3, rep
