@@ -30,7 +30,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // pi = 4*atan(1) (src/ARTES.f90:9) is the correctly rounded double below.
 constexpr double PI = 3.14159265358979323846;
 
-enum Phase : int { PH_NEW = 0, PH_PRE, PH_WALK, PH_PEEL, PH_PEELDONE, PH_SCAT, PH_SCAT2, PH_IDLE };
+enum Phase : int { PH_NEW = 0, PH_PRE, PH_WALK, PH_PEEL, PH_PEELDONE, PH_SCAT, PH_SCAT2, PH_IDLE, PH_LAMBERT };
 enum PeelKind : int { PK_SCATTER = 0, PK_SURFACE = 1, PK_THERMAL = 2 };
 
 // ---------------------------------------------------------------------------------------------
@@ -636,487 +636,9 @@ __device__ __forceinline__ void initial_cell(const double* __restrict__ sm, cons
 __device__ __forceinline__ void tuple_hash(unsigned long long& h, int v) { h ^= (unsigned)v; h *= 1099511628211ull; }
 
 // ---------------------------------------------------------------------------------------------
-// the transport kernel
+// photon state, event bodies, engines
 // ---------------------------------------------------------------------------------------------
-// Regrouping thresholds are launch parameters (LaunchArgs::defer_events / defer_refill): the number of
-// lanes of a warp that must wait for the heavy events / for new photons before those code paths run.
-
-template <bool TRACE>
-__global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant__ KernelArgs A) {
-    extern __shared__ double sm[];
-    const DevTables& T = A.T;
-    const LaunchArgs& L = A.L;
-    const SmLayout lay(T.nr, T.nt, T.np);
-    {   // stage the grid tables (coalesced)
-        for (int i = threadIdx.x; i <= T.nr; i += blockDim.x) sm[i] = T.rfront[i];
-        for (int i = threadIdx.x; i <= T.nt; i += blockDim.x) {
-            sm[lay.o_tf + i] = T.thetafront[i]; sm[lay.o_tt + i] = T.ttan[i]; sm[lay.o_tc + i] = T.tcos[i];
-            reinterpret_cast<int*>(sm + lay.o_tp)[i] = T.tplane[i];
-        }
-        for (int i = threadIdx.x; i < T.np; i += blockDim.x) {
-            sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i];
-        }
-        for (int i = threadIdx.x; i < 540; i += blockDim.x) sm[lay.o_sb + i] = T.trig[i];
-        __syncthreads();
-    }
-    const int lane = threadIdx.x & 31;
-
-    // ---- per-lane photon state
-    Rng rng; rng.id = 0; rng.nd = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0; rng.exhausted = false;
-    int ph = PH_NEW, pk = PK_SCATTER;
-    double px = 0, py = 0, pz = 0;          // photon position ("home" while a probe walk runs)
-    double dx = 0, dy = 0, dz = 0;          // photon direction
-    double S[4] = {0, 0, 0, 0};             // Stokes vector
-    int c0 = 0, c1 = 0, c2 = 0, f0 = 0, f1 = 0;
-    double tau = 0, tau_run = 0;
-    double wx = 0, wy = 0, wz = 0;          // walker (the point cell_face is evaluated at)
-    int wc0 = 0, wc1 = 0, wc2 = 0, wf0 = 0, wf1 = 0;
-    double tacc = 0;                        // optical depth of the running probe walk (pre-pass / peel)
-    bool peel_exit = false;
-    // counters
-    unsigned long long n_cf = 0;
-    unsigned n_emit = 0, n_sc = 0, n_peel = 0, n_surf = 0, n_err = 0, n_draw = 0;
-    // trace
-    int t_len = 0, t_nsc = 0;
-    unsigned long long t_hash = 1469598103934665603ull;
-
-    auto err_count = [&](int code) { atomicAdd(A.O.err + code, 1ull); };
-    auto record = [&](int a, int b, int c, int d, int e) {
-        if (TRACE) {
-            if (A.R.seq_head && t_len < A.R.max_rec) {
-                int* p = A.R.seq_head + ((size_t)(rng.id - L.id_base) * A.R.max_rec + t_len) * 5;
-                p[0] = a; p[1] = b; p[2] = c; p[3] = d; p[4] = e;
-            }
-            tuple_hash(t_hash, a); tuple_hash(t_hash, b); tuple_hash(t_hash, c); tuple_hash(t_hash, d); tuple_hash(t_hash, e);
-            ++t_len;
-        }
-    };
-    auto retire = [&]() {  // photon finished: publish trace record, ask for a new one
-        if (TRACE) {
-            size_t k = (size_t)(rng.id - L.id_base);
-            A.R.seq_len[k] = t_len; A.R.seq_hash[k] = t_hash;
-            if (A.R.fstate) {
-                double* f = A.R.fstate + k * 8;
-                const bool live = (ph == PH_WALK);
-                f[0] = live ? wx : px; f[1] = live ? wy : py; f[2] = live ? wz : pz;
-                f[3] = S[0]; f[4] = S[1]; f[5] = S[2]; f[6] = S[3]; f[7] = (double)t_nsc;
-            }
-        }
-        n_draw += rng.nd;
-        ph = PH_NEW;
-    };
-    // detector deposit :4947-4972 / :4575-4585 / :4683-4693
-    auto deposit = [&](double W0, double W1, double W2, double W3, bool all4) {
-        double x_im = py * L.cos_dp - px * L.sin_dp;
-        double y_im = pz * L.sin_dt - py * L.cos_dt * L.sin_dp - px * L.cos_dt * L.cos_dp;
-        int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
-        int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
-        if (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) { err_count(60); return; }
-        record(100, ix, iy, 0, 0);
-        const size_t npx = (size_t)L.nx * L.ny;
-        double* d = A.O.det + (size_t)(ix - 1) + (size_t)L.nx * (iy - 1);
-        atomicAdd(d, W0); atomicAdd(d + 4 * npx, W0 * W0); atomicAdd(d + 8 * npx, 1.0);
-        if (all4) {
-            atomicAdd(d + npx, W1); atomicAdd(d + 2 * npx, W2); atomicAdd(d + 3 * npx, W3);
-            atomicAdd(d + 5 * npx, W1 * W1); atomicAdd(d + 6 * npx, W2 * W2); atomicAdd(d + 7 * npx, W3 * W3);
-            atomicAdd(d + 9 * npx, 1.0);
-        }
-    };
-    auto start_probe = [&](int r_shift) { wx = px; wy = py; wz = pz; wc0 = c0 + r_shift; wc1 = c1; wc2 = c2; wf0 = f0; wf1 = f1; tacc = 0.0; };
-
-    for (;;) {
-        // ================= A. refill + emission (emit_photon :1008-1268) =================
-        const unsigned need0 = __ballot_sync(FULL, ph == PH_NEW);
-        const unsigned walk0 = __ballot_sync(FULL, ph == PH_PRE || ph == PH_WALK || ph == PH_PEEL);
-        const unsigned need = (__popc(need0) >= L.defer_refill || walk0 == 0u) ? need0 : 0u;
-        if (need) {
-            const int leader = __ffs(need) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(A.O.counter, (unsigned long long)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            if (ph == PH_NEW) {
-                const unsigned long long k = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
-                if (k >= L.n_photons) ph = PH_IDLE;
-                else {
-                    rng.id = L.id_base + k; rng.nd = 0; rng.exhausted = false;
-                    t_len = 0; t_nsc = 0; t_hash = 1469598103934665603ull;
-                    ++n_emit;
-                    S[0] = 1.0; S[1] = 0.0; S[2] = 0.0; S[3] = 0.0;
-                    int e = 0;
-                    double bias_weight = 1.0;
-                    if (L.photon_source == 1) {
-                        f0 = 1; f1 = T.nr;
-                        double xi, r_disk;
-                        if (L.limb_emission) {
-                            for (;;) { xi = rng_next<TRACE>(rng, A); r_disk = sqrt(xi); if (r_disk > 0.9 || rng.exhausted) break; }
-                        } else { xi = rng_next<TRACE>(rng, A); r_disk = sqrt(xi); }
-                        xi = rng_next<TRACE>(rng, A);
-                        const double phi_disk = 2.0 * PI * xi;
-                        const double R = sm[T.nr];
-                        const double d1 = R * r_disk * sin(phi_disk);
-                        const double d2 = R * r_disk * cos(phi_disk);
-                        dx = -1.0; dy = 0.0; dz = 0.0;
-                        px = sqrt(R * R - d1 * d1 - d2 * d2); py = d1; pz = d2;
-                        if (L.stellar_direction) {  // :1080-1111
-                            double tx = px * L.rot_y_cos + py * 0.0 + pz * L.rot_y_sin;
-                            double ty = px * 0.0 + py * 1.0 + pz * 0.0;
-                            double tz = px * (-L.rot_y_sin) + py * 0.0 + pz * L.rot_y_cos;
-                            px = tx * L.rot_z_cos + ty * (-L.rot_z_sin) + tz * 0.0;
-                            py = tx * L.rot_z_sin + ty * L.rot_z_cos + tz * 0.0;
-                            pz = tx * 0.0 + ty * 0.0 + tz * 1.0;
-                            dx = L.star_dir[0]; dy = L.star_dir[1]; dz = L.star_dir[2];
-                        }
-                        initial_cell(sm, lay, T, px, py, pz, c0, c1, c2);
-                    } else {  // thermal :1117-1266
-                        f0 = 0; f1 = 0;
-                        double xi = rng_next<TRACE>(rng, A);
-                        const int ncdf = (T.nr - T.cell_depth) * T.nt * T.np;
-                        const double samp = xi * __ldg(T.emis_cdf + ncdf - 1);
-                        int lo = -1, hi = ncdf - 1;  // first p with cdf[p] >= samp (== the linear scan of :1132-1155)
-                        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(T.emis_cdf + mid) >= samp) hi = mid; else lo = mid; }
-                        c2 = hi % T.np; c1 = (hi / T.np) % T.nt; c0 = T.cell_depth + hi / (T.np * T.nt);
-                        xi = rng_next<TRACE>(rng, A);
-                        double rs = xi * (sm[c0 + 1] - sm[c0]); rs = sm[c0] + rs;
-                        xi = rng_next<TRACE>(rng, A);
-                        double ct = xi * (sm[lay.o_tc + c1 + 1] - sm[lay.o_tc + c1]); ct = sm[lay.o_tc + c1] + ct;
-                        double st = sqrt(1.0 - ct * ct);
-                        xi = rng_next<TRACE>(rng, A);
-                        double phs;
-                        if (T.np == 1) phs = 2.0 * PI * xi;
-                        else if (c2 < T.np - 1) { phs = xi * (sm[lay.o_pf + c2 + 1] - sm[lay.o_pf + c2]); phs = sm[lay.o_pf + c2] + phs; }
-                        else { phs = xi * (2.0 * PI - sm[lay.o_pf + c2]); phs = sm[lay.o_pf + c2] + phs; }
-                        double cp = cos(phs), sp = sqrt(1.0 - cp * cp);
-                        if (phs > PI) sp = -sp;
-                        px = rs * st * cp; py = rs * st * sp; pz = rs * ct;
-                        px = T.ox * px; py = T.oy * py; pz = T.oz * pz;
-                        if (L.photon_emission == 1) {
-                            xi = rng_next<TRACE>(rng, A);
-                            double al = 2.0 * xi - 1.0;
-                            xi = rng_next<TRACE>(rng, A);
-                            double be = 2.0 * PI * xi;
-                            double cb = cos(be), sb = sqrt(1.0 - cb * cb);
-                            if (be > PI) sb = -sb;
-                            dx = sqrt(1.0 - al * al) * cb; dy = sqrt(1.0 - al * al) * sb; dz = al;
-                        } else {
-                            xi = rng_next<TRACE>(rng, A);
-                            double yb = (1.0 + L.photon_bias) * tan(PI * xi / 2.0) / sqrt(1.0 - L.photon_bias * L.photon_bias);
-                            double ths = acos((1.0 - yb * yb) / (1.0 + yb * yb));
-                            xi = rng_next<TRACE>(rng, A);
-                            double be = 2.0 * PI * xi;
-                            double r0 = px / (T.ox * T.ox), r1 = py / (T.oy * T.oy), r2 = pz / (T.oz * T.oz);
-                            double nrm = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
-                            r0 = r0 / nrm; r1 = r1 / nrm; r2 = r2 / nrm;
-                            e = direction_cosine(cos(PI - ths), be, r0, r1, r2, dx, dy, dz);
-                            bias_weight = (PI * sin(ths) * (1.0 + L.photon_bias * cos(ths))) / (2.0 * sqrt(1.0 - L.photon_bias * L.photon_bias));
-                        }
-                        if (e == 0 && fabs(dz) >= 1.0) err_count(54);
-                    }
-                    if (e) { err_count(e); ++n_err; retire(); }
-                    else if (L.photon_source == 2) {  // :599-621
-                        S[0] = S[0] * bias_weight / __ldg(T.cell_weight + c0 + T.nr * (c1 + T.nt * c2));
-                        atomicAdd(A.O.flux, S[0]);
-                        ++n_peel; pk = PK_THERMAL; start_probe(0); ph = PH_PEEL;
-                    } else { start_probe(0); ph = PH_PRE; }
-                }
-            }
-        }
-
-        // ================= B. one cell crossing for every walking lane =================
-        if (ph == PH_PRE || ph == PH_WALK || ph == PH_PEEL) {
-            const bool peel = (ph == PH_PEEL);
-            const double n0 = peel ? L.det[0] : dx, n1 = peel ? L.det[1] : dy, n2 = peel ? L.det[2] : dz;
-            CellFace o;
-            cell_face(sm, lay, T, wx, wy, wz, n0, n1, n2, wf0, wf1, wc0, wc1, wc2, o);
-            ++n_cf;
-            record(o.nf0, o.nf1, o.co0, o.co1, o.co2);
-            const int wci = wc0 + T.nr * (wc1 + T.nt * wc2);
-            if (o.err) {
-                err_count(o.err);
-                if (ph == PH_PRE) { err_count(2); ++n_err; retire(); }
-                else if (ph == PH_WALK) { err_count(3); ++n_err; retire(); }
-                else if (pk == PK_SCATTER) { err_count(43); ++n_err; retire(); }
-                else if (pk == PK_THERMAL) { err_count(46); err_count(47); ++n_err; retire(); }
-                else { err_count(42); peel_exit = false; ph = PH_PEELDONE; }
-            } else if (ph == PH_WALK) {
-                const double kap = __ldg(T.kext + wci);
-                const double tau_cell = o.dist * kap;
-                if (tau_run + tau_cell > tau) {  // :705-720 / :862-879 interaction inside this cell
-                    const double s = (tau - tau_run) / kap;
-                    px = wx + s * dx; py = wy + s * dy; pz = wz + s * dz;
-                    c0 = wc0; c1 = wc1; c2 = wc2; f0 = 0; f1 = 0;
-                    if (L.flow_global) {  // add_flow_global :4992-5014
-                        double th = acos(pz / sqrt(px * px + py * py + pz * pz)), phh = atan2(py, px);
-                        double* f = A.O.flow3 + (size_t)3 * wci;
-                        atomicAdd(f, (sin(th) * cos(phh) * dx + sin(th) * sin(phh) * dy + cos(th) * dz) * s * S[0]);
-                        atomicAdd(f + 1, (cos(th) * cos(phh) * dx + cos(th) * sin(phh) * dy - sin(th) * dz) * s * S[0]);
-                        atomicAdd(f + 2, (-sin(phh) * dx + cos(phh) * dy) * s * S[0]);
-                    }
-                    ph = PH_SCAT;
-                } else {
-                    wx = wx + o.dist * dx; wy = wy + o.dist * dy; wz = wz + o.dist * dz;
-                    if (L.flow_global) {
-                        double th = acos(wz / sqrt(wx * wx + wy * wy + wz * wz)), phh = atan2(wy, wx);
-                        double* f = A.O.flow3 + (size_t)3 * wci;
-                        atomicAdd(f, (sin(th) * cos(phh) * dx + sin(th) * sin(phh) * dy + cos(th) * dz) * o.dist * S[0]);
-                        atomicAdd(f + 1, (cos(th) * cos(phh) * dx + cos(th) * sin(phh) * dy - sin(th) * dz) * o.dist * S[0]);
-                        atomicAdd(f + 2, (-sin(phh) * dx + cos(phh) * dy) * o.dist * S[0]);
-                    }
-                    if (L.flow_theta) {  // :730-744
-                        double* f = A.O.flow4 + (size_t)4 * wci;
-                        if (o.nf0 == 1) { if (o.co0 > wc0) atomicAdd(f, S[0]); else if (o.co0 < wc0) atomicAdd(f + 1, S[0]); }
-                        else if (o.nf0 == 2) { if (o.co1 > wc1) atomicAdd(f + 2, S[0]); else if (o.co1 < wc1) atomicAdd(f + 3, S[0]); }
-                    }
-                    wf0 = o.nf0; wf1 = o.nf1; wc0 = o.co0; wc1 = o.co1; wc2 = o.co2;
-                    if (o.exit) {
-                        if (L.photon_source == 2) atomicAdd(A.O.flux + 1, S[0]);  // :780 / :953
-                        retire();
-                    } else {
-                        if (o.nf0 == 1 && o.nf1 == T.cell_depth) {  // surface :755-774
-                            ++n_surf;
-                            double xi = rng_next<TRACE>(rng, A);
-                            if (xi > L.surface_albedo) retire();
-                            else {  // lambertian :1369-1402, then peel_surface :4600-4708
-                                double s0 = wx / (T.ox * T.ox), s1 = wy / (T.oy * T.oy), s2 = wz / (T.oz * T.oz);
-                                double nrm = sqrt(s0 * s0 + s1 * s1 + s2 * s2);
-                                s0 = s0 / nrm; s1 = s1 / nrm; s2 = s2 / nrm;
-                                xi = rng_next<TRACE>(rng, A);
-                                double al = sqrt(xi);
-                                xi = rng_next<TRACE>(rng, A);
-                                double be = 2.0 * PI * xi;
-                                double e0, e1, e2;
-                                int e = direction_cosine(al, be, s0, s1, s2, e0, e1, e2);
-                                if (e) { err_count(e); ++n_err; retire(); }
-                                else {
-                                    dx = e0; dy = e1; dz = e2;
-                                    px = wx; py = wy; pz = wz; c0 = wc0; c1 = wc1; c2 = wc2; f0 = wf0; f1 = wf1;
-                                    // cos of the angle between the surface normal and the detector :4628-4634
-                                    double nth = acos(s2 / sqrt(s0 * s0 + s1 * s1 + s2 * s2));
-                                    double nph = atan2(s1, s0);
-                                    if (nph < 0.0) nph = nph + 2.0 * PI;
-                                    double cos_angle = sin(L.det_sph_theta) * cos(L.det_sph_phi) * sin(nth) * cos(nph) +
-                                                       sin(L.det_sph_theta) * sin(L.det_sph_phi) * sin(nth) * sin(nph) +
-                                                       cos(L.det_sph_theta) * cos(nth);
-                                    tau_run = tau_run + tau_cell;
-                                    S[1] = 0.0; S[2] = 0.0; S[3] = 0.0;
-                                    if (cos_angle > 0.0) { ++n_peel; pk = PK_SURFACE; start_probe(1); ph = PH_PEEL; }
-                                    else { c0 = c0 + 1; wc0 = c0; }
-                                }
-                            }
-                        } else tau_run = tau_run + tau_cell;
-                    }
-                }
-            } else {
-                // probe walks: tau pre-pass :633-656 and the three peel walks
-                tacc = tacc + o.dist * __ldg(T.kext + wci);
-                wx = wx + o.dist * n0; wy = wy + o.dist * n1; wz = wz + o.dist * n2;
-                const bool hit_surface = (o.nf0 == 1 && o.nf1 == T.cell_depth);
-                if (o.exit || hit_surface) {
-                    if (ph == PH_PRE) {
-                        // first optical depth :660-685
-                        bool go = true;
-                        if (tacc < 1.e-6 && !hit_surface) { go = false; retire(); }
-                        else if (tacc < 1.e-6 && hit_surface) { double xi = rng_next<TRACE>(rng, A); tau = -log(1.0 - xi); }
-                        else {
-                            double xi = rng_next<TRACE>(rng, A);
-                            if (tacc < 50.0) {
-                                tau = -log(1.0 - xi * (1.0 - exp(-tacc)));
-                                double f = 1.0 - exp(-tacc);
-                                S[0] = S[0] * f; S[1] = S[1] * f; S[2] = S[2] * f; S[3] = S[3] * f;
-                            } else tau = -log(1.0 - xi);
-                        }
-                        if (go) { tau_run = 0.0; start_probe(0); ph = PH_WALK; }
-                    } else { peel_exit = o.exit; ph = PH_PEELDONE; }
-                } else { wf0 = o.nf0; wf1 = o.nf1; wc0 = o.co0; wc1 = o.co1; wc2 = o.co2; }
-            }
-        }
-
-        // ================= D. interaction point reached: survival + start of the peel-off =================
-        if (ph == PH_SCAT) {  // :788-815
-            bool alive = L.photon_scattering != 0;
-            if (TRACE && rng.exhausted) alive = false;
-            if (alive) {
-                double xi = rng_next<TRACE>(rng, A);
-                if (xi < L.fstop) alive = false;
-            }
-            if (alive) {
-                const double alb = __ldg(T.albedo + c0 + T.nr * (c1 + T.nt * c2));
-                if (alb < 1.0 && alb > 0.0) {
-                    double gamma = alb / (1.0 - L.fstop);
-                    S[0] = gamma * S[0]; S[1] = gamma * S[1]; S[2] = gamma * S[2]; S[3] = gamma * S[3];
-                }
-                if (S[0] <= L.photon_minimum) alive = false;
-            }
-            if (!alive) retire();
-            else { ++n_peel; pk = PK_SCATTER; start_probe(0); ph = PH_PEEL; }
-        }
-
-        // ---- ballot regrouping: the heavy events below run only when enough lanes of the warp wait for
-        // them (or nobody is left walking), so that their instructions are issued for many lanes at once.
-        const unsigned m_evt = __ballot_sync(FULL, ph == PH_PEELDONE || ph == PH_SCAT2);
-        const unsigned m_walk = __ballot_sync(FULL, ph == PH_PRE || ph == PH_WALK || ph == PH_PEEL);
-        const bool run_events = m_evt && (__popc(m_evt) >= L.defer_events || m_walk == 0u);
-
-        // ================= C. a peel walk ended: weight + deposit =================
-        if (run_events && ph == PH_PEELDONE) {
-            const bool ok = peel_exit && tacc < 50.0;
-            if (pk == PK_THERMAL) {  // :4571-4596
-                if (ok) {
-                    double w = exp(-tacc) / (4.0 * PI);
-                    double W0 = w * S[0];
-                    if (W0 > 0.0 && W0 < 1.e100) deposit(W0, 0, 0, 0, false); else err_count(51);
-                }
-                start_probe(0); ph = PH_PRE;
-            } else if (pk == PK_SURFACE) {  // :4675-4704
-                if (ok) {
-                    double s0 = px / (T.ox * T.ox), s1 = py / (T.oy * T.oy), s2 = pz / (T.oz * T.oz);
-                    double nrm = sqrt(s0 * s0 + s1 * s1 + s2 * s2);
-                    s0 = s0 / nrm; s1 = s1 / nrm; s2 = s2 / nrm;
-                    double nth = acos(s2 / sqrt(s0 * s0 + s1 * s1 + s2 * s2));
-                    double nph = atan2(s1, s0);
-                    if (nph < 0.0) nph = nph + 2.0 * PI;
-                    double cos_angle = sin(L.det_sph_theta) * cos(L.det_sph_phi) * sin(nth) * cos(nph) +
-                                       sin(L.det_sph_theta) * sin(L.det_sph_phi) * sin(nth) * sin(nph) +
-                                       cos(L.det_sph_theta) * cos(nth);
-                    double w = exp(-tacc) * cos_angle / PI;
-                    double W0 = w * S[0];
-                    if (W0 > 0.0 && W0 < 1.e100) deposit(W0, 0, 0, 0, false); else err_count(52);
-                }
-                c0 = c0 + 1;  // :770
-                start_probe(0); ph = PH_WALK;
-            } else {  // peel_photon :4763-4986
-                if (ok) {
-                    const double w = exp(-tacc);
-                    double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
-                    if (mu >= 1.0) mu = 1.0 - 1.e-10;
-                    else if (mu <= -1.0) mu = -1.0 + 1.e-10;
-                    double F[16];
-#if ARTES_FAITHFUL
-                    matrix_at(T, c0 + T.nr * (c1 + T.nt * c2), acos(mu), F);
-                    double phi_old = atan2(dy, dx);
-                    if (phi_old < 0.0) phi_old = phi_old + 2.0 * PI;
-                    if (phi_old > 2.0 * PI) phi_old = phi_old - 2.0 * PI;
-                    const double phi_new = L.det_atan2;
-                    if (!(fabs(dz) < 1.0)) err_count(45);
-                    else {
-                        double nc = (L.det[2] - dz * mu) / (sqrt(1.0 - mu * mu) * sqrt(1.0 - dz * dz));
-                        double phs = 0.0;
-                        bool good = true;
-                        if (fabs(nc) < 1.0) phs = acos(nc);
-                        else if (nc >= 1.0) phs = 0.0 + 1.e-10;
-                        else if (nc <= -1.0) phs = PI - 1.e-10;
-                        else { good = false; err_count(44); }
-                        if (good) {
-                            if (phi_old - phi_new >= 0.0 && phi_old - phi_new < PI) phs = 2.0 * PI - phs;
-                            if (2.0 * PI + phi_old - phi_new >= 0.0 && 2.0 * PI + phi_old - phi_new < PI) phs = 2.0 * PI - phs;
-                            if (phs < 0.0) phs = phs + 2.0 * PI;
-                            double so[4];
-                            int soft = 0;
-                            int e = polarization_rotation(mu, phs, S, F, dz, L.det[2], so, true, soft);
-                            if (soft) err_count(soft);
-                            if (e) err_count(e);
-                            else if (w * so[0] > 0.0 && w * so[0] < 1.e100) deposit(w * so[0], -(w * so[1]), w * so[2], w * so[3], true);
-                            else err_count(53);
-                        }
-                    }
-#else
-                    matrix_at_deg(T, c0 + T.nr * (c1 + T.nt * c2), acos(mu) * (180.0 / PI), F);
-                    if (!(fabs(dz) < 1.0)) err_count(45);
-                    else {
-                        const double smu = sqrt(1.0 - mu * mu);
-                        double nc = (L.det[2] - dz * mu) / (smu * sqrt(1.0 - dz * dz));
-                        if (!(nc == nc)) err_count(44);
-                        else {
-                            nc = fmin(fmax(nc, -1.0), 1.0);
-                            const double cr = dy * L.det[0] - dx * L.det[1];                 // sin(phi_old - phi_new) > 0 ?
-                            const bool flip = (cr > 0.0) || (cr == 0.0 && dx * L.det[0] + dy * L.det[1] > 0.0);
-                            const double c2a = 2.0 * nc * nc - 1.0;
-                            double s2a = 2.0 * nc * sqrt(fmax(1.0 - nc * nc, 0.0));
-                            if (flip) s2a = -s2a;
-                            const double nc2 = (dz - L.det[2] * mu) / (smu * sqrt(1.0 - L.det[2] * L.det[2]));
-                            double so[4];
-                            int soft = 0;
-                            int e = (fabs(L.det[2]) < 1.0) ? polrot_fast(c2a, s2a, flip, nc2, S, F, so, true, soft) : 16;
-                            if (e) err_count(e);
-                            else if (w * so[0] > 0.0 && w * so[0] < 1.e100) deposit(w * so[0], -(w * so[1]), w * so[2], w * so[3], true);
-                            else err_count(53);
-                        }
-                    }
-#endif
-                }
-                ph = PH_SCAT2;
-            }
-        }
-
-        // ================= E. scattering event (scatter_photon :1434-1532 + polarization_rotation) ==========
-        if (run_events && ph == PH_SCAT2) {
-            ++n_sc; ++t_nsc;
-            const int ci = c0 + T.nr * (c1 + T.nt * c2);
-            double e0 = 0, e1 = 0, e2 = 0;
-            int e;
-#if ARTES_FAITHFUL
-            double alpha, beta;
-            e = sample_angles<TRACE>(sm, lay, A, rng, S, ci, alpha, beta);
-            if (!e) e = direction_cosine(alpha, beta, dx, dy, dz, e0, e1, e2);
-            if (!e && !(fabs(alpha) < 1.0)) e = 50;
-            if (!e) {
-                double F[16], Sn[4];
-                matrix_at(T, ci, acos(alpha), F);
-                int soft = 0;
-                e = polarization_rotation(alpha, beta, S, F, dz, e2, Sn, false, soft);
-                if (soft) err_count(soft);
-                if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
-            }
-#else
-            FastAngles g;
-            e = sample_angles_fast<TRACE>(A, rng, S, ci, g);
-            if (!e) {
-                // direction_cosine :1962-2052 without the acos / cos round trip
-                const double cto = dz / sqrt(dx * dx + dy * dy + dz * dz);
-                const double sto = sqrt(1.0 - cto * cto);
-                const double ctn = cto * g.alpha + sto * g.sT * g.cb;
-                const double stn = sqrt(1.0 - ctn * ctn);
-                double nc = (g.alpha - ctn * cto) / (stn * sto);
-                if (!(nc == nc)) e = 20;
-                else {
-                    if (nc >= 1.0) nc = 1.0 - 1.e-10; else if (nc <= -1.0) nc = -1.0 + 1.e-10;
-                    const double sD = sqrt(1.0 - nc * nc) * (g.flip ? -1.0 : 1.0);
-                    const double rho = sqrt(dx * dx + dy * dy);
-                    const double cph = rho > 0.0 ? dx / rho : 1.0, sph = rho > 0.0 ? dy / rho : 0.0;
-                    e0 = stn * (cph * nc - sph * sD); e1 = stn * (sph * nc + cph * sD); e2 = ctn;
-                    if (!(fabs(e2) < 1.0)) e = 16;
-                }
-            }
-            if (!e) {
-                double F[16], Sn[4];
-                matrix_at_deg(T, ci, g.deg, F);
-                const double nc2 = (dz - e2 * g.alpha) / (g.sT * sqrt(1.0 - e2 * e2));
-                int soft = 0;
-                e = polrot_fast(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
-                if (soft) err_count(soft);
-                if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
-            }
-#endif
-            if (e) { err_count(e); ++n_err; retire(); }
-            else {
-                double xi = rng_next<TRACE>(rng, A);  // :845
-                tau = -log(1.0 - xi);
-                tau_run = 0.0;
-                start_probe(0); ph = PH_WALK;
-            }
-        }
-
-        if (__all_sync(FULL, ph == PH_IDLE)) break;
-    }
-
-    // ---- flush event counters (warp reduce, one atomic per warp and counter)
-    unsigned long long v[7] = {n_emit, n_cf, n_sc, n_peel, n_surf, n_draw, n_err};
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        unsigned long long x = v[k];
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
-        if (lane == 0 && x) atomicAdd(A.O.stats + k, x);
-    }
-}
+#include "engine.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // isolated cell_face evaluations (unit-test hook)

@@ -74,7 +74,7 @@ typedef struct artes_stats_t {
     uint64_t n_surface;    /* surface hits                          */
     uint64_t n_draws;      /* random numbers consumed               */
     uint64_t n_error;      /* photons dropped through an error path */
-    uint64_t reserved;
+    uint64_t reserved;     /* kernels launched by the call (all devices of the context) */
     double   kernel_ms;    /* CUDA-event time of the transport kernel(s), max over this ctx's devices */
     double   reduce_ms;    /* CUDA-event time of the NCCL reduce (0 if single device)                 */
     double   h2d_ms;       /* last table upload                                                        */
