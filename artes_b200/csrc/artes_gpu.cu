@@ -25,6 +25,7 @@ namespace artes {
 namespace faithful {
 size_t smem_bytes(int nr, int nt, int np);
 cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+cudaError_t launch_regroup(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
 cudaError_t wf_prepare(const KernelArgs& a, bool trace, int sm_count, WfGeom* g);
@@ -34,6 +35,7 @@ cudaError_t wf_enqueue(const KernelArgs& a, const PoolArgs& q, bool trace, const
 namespace fast {
 size_t smem_bytes(int nr, int nt, int np);
 cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+cudaError_t launch_regroup(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
 cudaError_t wf_prepare(const KernelArgs& a, bool trace, int sm_count, WfGeom* g);
@@ -202,10 +204,17 @@ void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
     a.star_dir[2] = 1.0 * std::cos(td);
 }
 
-bool use_wavefront() {
-    static const bool wf = [] { const char* v = std::getenv("ARTES_ENGINE"); return !(v && std::strcmp(v, "persistent") == 0); }();
-    return wf;
+// ARTES_ENGINE = regroup (default) | wavefront | persistent
+int engine_kind() {
+    static const int k = [] {
+        const char* v = std::getenv("ARTES_ENGINE");
+        if (v && std::strcmp(v, "persistent") == 0) return 0;
+        if (v && std::strcmp(v, "wavefront") == 0) return 1;
+        return 2;
+    }();
+    return k;
 }
+bool use_wavefront() { return engine_kind() == 1; }
 
 int ensure_pool(artes_gpu_ctx* ctx, DeviceState& d, size_t want, bool trace) {
     static const size_t cap_env = [] { const char* v = std::getenv("ARTES_POOL"); return v && *v ? (size_t)std::atoll(v) : (size_t)(1u << 20); }();
@@ -543,8 +552,11 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
                 d.kargs = a;
                 d.wf_active = true;
             } else {
-                cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, false, d.sm_count, d.stream)
-                                                                 : fast::launch_transport(a, false, d.sm_count, d.stream);
+                cudaError_t e;
+                if (engine_kind() == 2) e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_regroup(a, false, d.sm_count, d.stream)
+                                                                             : fast::launch_regroup(a, false, d.sm_count, d.stream);
+                else e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, false, d.sm_count, d.stream)
+                                                          : fast::launch_transport(a, false, d.sm_count, d.stream);
                 if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
                 d.launches = 1; d.passes = 1;
             }
@@ -698,8 +710,11 @@ int artes_gpu_trace(artes_gpu_ctx* ctx, const artes_launch_t* L, const double* x
         rc = run_wavefront(ctx, L->mode == ARTES_MODE_FAITHFUL, true);
         if (rc) return rc;
     } else {
-        cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, true, d.sm_count, d.stream)
-                                                         : fast::launch_transport(a, true, d.sm_count, d.stream);
+        cudaError_t e;
+        if (engine_kind() == 2) e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_regroup(a, true, d.sm_count, d.stream)
+                                                                     : fast::launch_regroup(a, true, d.sm_count, d.stream);
+        else e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, true, d.sm_count, d.stream)
+                                                  : fast::launch_transport(a, true, d.sm_count, d.stream);
         if (e != cudaSuccess) return fail(ctx, -2, std::string("trace launch: ") + cudaGetErrorString(e));
     }
     CU(cudaMemcpyAsync(seq_len, d_len, n * sizeof(int), cudaMemcpyDeviceToHost, d.stream));

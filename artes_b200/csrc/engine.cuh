@@ -22,6 +22,7 @@ struct Photon {
     Rng rng;
     int ph, pk;
     bool peel_exit;
+    bool at_walker;             // a retiring photon reports the walker position (it was in a transport walk)
     double px, py, pz;          // photon position ("home" while a probe walk runs)
     double dx, dy, dz;          // photon direction
     double S[4];                // Stokes vector
@@ -56,6 +57,10 @@ struct Ctx {
     const KernelArgs& A;
     __device__ __forceinline__ Ctx(const double* s, const KernelArgs& a) : sm(s), lay(a.T.nr, a.T.nt, a.T.np), A(a) {}
 };
+
+#if !ARTES_FAITHFUL
+#include "ray.cuh"
+#endif
 
 __device__ __forceinline__ void stage_tables(double* sm, const DevTables& T) {
     const SmLayout lay(T.nr, T.nt, T.np);
@@ -93,12 +98,13 @@ __device__ __forceinline__ void retire(const KernelArgs& A, Photon& P, Counters&
         A.R.seq_len[k] = P.t_len; A.R.seq_hash[k] = P.t_hash;
         if (A.R.fstate) {
             double* f = A.R.fstate + k * 8;
-            const bool live = (P.ph == PH_WALK);
+            const bool live = (P.ph == PH_WALK) || P.at_walker;
             f[0] = live ? P.wx : P.px; f[1] = live ? P.wy : P.py; f[2] = live ? P.wz : P.pz;
             f[3] = P.S[0]; f[4] = P.S[1]; f[5] = P.S[2]; f[6] = P.S[3]; f[7] = (double)P.t_nsc;
         }
     }
     C.n_draw += P.rng.nd;
+    P.at_walker = false;
     P.ph = PH_NEW;
 }
 
@@ -164,7 +170,7 @@ __device__ __forceinline__ void ev_emit(const Ctx& X, Photon& P, Counters& C, un
     P.t_len = 0; P.t_nsc = 0; P.t_hash = 1469598103934665603ull;
     ++C.n_emit;
     P.S[0] = 1.0; P.S[1] = 0.0; P.S[2] = 0.0; P.S[3] = 0.0;
-    P.tau = 0.0; P.tau_run = 0.0; P.peel_exit = false; P.pk = PK_SCATTER;
+    P.tau = 0.0; P.tau_run = 0.0; P.peel_exit = false; P.at_walker = false; P.pk = PK_SCATTER;
     int e = 0;
     double bias_weight = 1.0;
     if (L.photon_source == 1) {
@@ -276,52 +282,60 @@ __device__ __forceinline__ void ev_survive(const Ctx& X, Photon& P, Counters& C)
 // On return P.ph tells what comes next: PH_PRE / PH_WALK / PH_PEEL (keep walking), PH_SCAT (interaction
 // reached -> ev_survive), PH_PEELDONE (-> ev_peel_done), PH_LAMBERT (surface reflection event), PH_NEW (retired).
 template <bool TRACE>
+__device__ __forceinline__ void apply_crossing(const Ctx& X, Photon& P, Counters& C, const CellFace& o, double n0, double n1, double n2);
+
+template <bool TRACE>
 __device__ __forceinline__ void ev_cross(const Ctx& X, Photon& P, Counters& C) {
-    const KernelArgs& A = X.A;
-    const DevTables& T = A.T;
-    const LaunchArgs& L = A.L;
+    const LaunchArgs& L = X.A.L;
     const bool peel = (P.ph == PH_PEEL);
     const double n0 = peel ? L.det[0] : P.dx, n1 = peel ? L.det[1] : P.dy, n2 = peel ? L.det[2] : P.dz;
     CellFace o;
-    cell_face(X.sm, X.lay, T, P.wx, P.wy, P.wz, n0, n1, n2, P.wf0, P.wf1, P.wc0, P.wc1, P.wc2, o);
+    cell_face(X.sm, X.lay, X.A.T, P.wx, P.wy, P.wz, n0, n1, n2, P.wf0, P.wf1, P.wc0, P.wc1, P.wc2, o);
+    apply_crossing<TRACE>(X, P, C, o, n0, n1, n2);
+}
+
+// What one crossing does to the photon, given the geometry result `o` along direction (n0,n1,n2).
+// Touches only the "hot" walker state (w, wc, wf, tau, tau_run, tacc, S[0] for the flow counters); whatever
+// needs the random stream or the full Stokes vector is left to a follow-up handler chosen through P.ph:
+//   PH_PREDONE -> ev_pre_done, PH_SCAT -> ev_survive, PH_SURFHIT -> ev_surface_hit, PH_RETIRE -> ev_retire.
+template <bool TRACE>
+__device__ __forceinline__ void apply_crossing(const Ctx& X, Photon& P, Counters& C, const CellFace& o, double n0, double n1, double n2) {
+    const KernelArgs& A = X.A;
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
     ++C.n_cf;
     record<TRACE>(A, P, o.nf0, o.nf1, o.co0, o.co1, o.co2);
     const int wci = P.wc0 + T.nr * (P.wc1 + T.nt * P.wc2);
     if (o.err) {
         err_count(A, o.err);
-        if (P.ph == PH_PRE) { err_count(A, 2); ++C.n_err; retire<TRACE>(A, P, C); }
-        else if (P.ph == PH_WALK) { err_count(A, 3); ++C.n_err; retire<TRACE>(A, P, C); }
-        else if (P.pk == PK_SCATTER) { err_count(A, 43); ++C.n_err; retire<TRACE>(A, P, C); }
-        else if (P.pk == PK_THERMAL) { err_count(A, 46); err_count(A, 47); ++C.n_err; retire<TRACE>(A, P, C); }
-        else { err_count(A, 42); P.peel_exit = false; P.ph = PH_PEELDONE; }
+        P.peel_exit = false;                      // not a grid exit
+        P.at_walker = (P.ph == PH_WALK);
+        if (P.ph == PH_PRE) { err_count(A, 2); ++C.n_err; P.ph = PH_RETIRE; }
+        else if (P.ph == PH_WALK) { err_count(A, 3); ++C.n_err; P.ph = PH_RETIRE; }
+        else if (P.pk == PK_SCATTER) { err_count(A, 43); ++C.n_err; P.ph = PH_RETIRE; }
+        else if (P.pk == PK_THERMAL) { err_count(A, 46); err_count(A, 47); ++C.n_err; P.ph = PH_RETIRE; }
+        else { err_count(A, 42); P.ph = PH_PEELDONE; }
     } else if (P.ph == PH_WALK) {
         const double kap = __ldg(T.kext + wci);
         const double tau_cell = o.dist * kap;
         if (P.tau_run + tau_cell > P.tau) {  // :705-720 / :862-879 interaction inside this cell
             const double s = (P.tau - P.tau_run) / kap;
-            P.px = P.wx + s * P.dx; P.py = P.wy + s * P.dy; P.pz = P.wz + s * P.dz;
+            P.px = P.wx + s * n0; P.py = P.wy + s * n1; P.pz = P.wz + s * n2;
             P.c0 = P.wc0; P.c1 = P.wc1; P.c2 = P.wc2; P.f0 = 0; P.f1 = 0;
-            if (L.flow_global) add_flow_global(A, P.px, P.py, P.pz, P.dx, P.dy, P.dz, P.S[0], s, wci);
+            if (L.flow_global) add_flow_global(A, P.px, P.py, P.pz, n0, n1, n2, P.S[0], s, wci);
             P.ph = PH_SCAT;
         } else {
-            P.wx = P.wx + o.dist * P.dx; P.wy = P.wy + o.dist * P.dy; P.wz = P.wz + o.dist * P.dz;
-            if (L.flow_global) add_flow_global(A, P.wx, P.wy, P.wz, P.dx, P.dy, P.dz, P.S[0], o.dist, wci);
+            P.wx = P.wx + o.dist * n0; P.wy = P.wy + o.dist * n1; P.wz = P.wz + o.dist * n2;
+            if (L.flow_global) add_flow_global(A, P.wx, P.wy, P.wz, n0, n1, n2, P.S[0], o.dist, wci);
             if (L.flow_theta) {  // :730-744
                 double* f = A.O.flow4 + (size_t)4 * wci;
                 if (o.nf0 == 1) { if (o.co0 > P.wc0) atomicAdd(f, P.S[0]); else if (o.co0 < P.wc0) atomicAdd(f + 1, P.S[0]); }
                 else if (o.nf0 == 2) { if (o.co1 > P.wc1) atomicAdd(f + 2, P.S[0]); else if (o.co1 < P.wc1) atomicAdd(f + 3, P.S[0]); }
             }
             P.wf0 = o.nf0; P.wf1 = o.nf1; P.wc0 = o.co0; P.wc1 = o.co1; P.wc2 = o.co2;
-            if (o.exit) {
-                if (L.photon_source == 2) atomicAdd(A.O.flux + 1, P.S[0]);  // :780 / :953
-                retire<TRACE>(A, P, C);
-            } else if (o.nf0 == 1 && o.nf1 == T.cell_depth) {  // surface :755-774
-                ++C.n_surf;
-                double xi = rng_next<TRACE>(P.rng, A);
-                P.tau_run = P.tau_run + tau_cell;      // :776 (only matters if the photon is reflected)
-                if (xi > L.surface_albedo) retire<TRACE>(A, P, C);
-                else P.ph = PH_LAMBERT;
-            } else P.tau_run = P.tau_run + tau_cell;
+            P.tau_run = P.tau_run + tau_cell;      // :776 (after a grid exit / absorption it is never read again)
+            if (o.exit) { P.peel_exit = true; P.at_walker = true; P.ph = PH_RETIRE; }
+            else if (o.nf0 == 1 && o.nf1 == T.cell_depth) { ++C.n_surf; P.ph = PH_SURFHIT; }   // surface :755-774
         }
     } else {
         // probe walks: tau pre-pass :633-656 and the three peel walks
@@ -329,23 +343,54 @@ __device__ __forceinline__ void ev_cross(const Ctx& X, Photon& P, Counters& C) {
         P.wx = P.wx + o.dist * n0; P.wy = P.wy + o.dist * n1; P.wz = P.wz + o.dist * n2;
         const bool hit_surface = (o.nf0 == 1 && o.nf1 == T.cell_depth);
         if (o.exit || hit_surface) {
-            if (P.ph == PH_PRE) {
-                // first optical depth :660-685
-                bool go = true;
-                if (P.tacc < 1.e-6 && !hit_surface) { go = false; retire<TRACE>(A, P, C); }
-                else if (P.tacc < 1.e-6 && hit_surface) { double xi = rng_next<TRACE>(P.rng, A); P.tau = -log(1.0 - xi); }
-                else {
-                    double xi = rng_next<TRACE>(P.rng, A);
-                    if (P.tacc < 50.0) {
-                        P.tau = -log(1.0 - xi * (1.0 - exp(-P.tacc)));
-                        double f = 1.0 - exp(-P.tacc);
-                        P.S[0] = P.S[0] * f; P.S[1] = P.S[1] * f; P.S[2] = P.S[2] * f; P.S[3] = P.S[3] * f;
-                    } else P.tau = -log(1.0 - xi);
-                }
-                if (go) { P.tau_run = 0.0; start_probe(P, 0); P.ph = PH_WALK; }
-            } else { P.peel_exit = o.exit; P.ph = PH_PEELDONE; }
+            P.peel_exit = o.exit;
+            P.ph = (P.ph == PH_PRE) ? PH_PREDONE : PH_PEELDONE;
         } else { P.wf0 = o.nf0; P.wf1 = o.nf1; P.wc0 = o.co0; P.wc1 = o.co1; P.wc2 = o.co2; }
     }
+}
+
+// first optical depth :660-685 (the pre-pass ended on the grid boundary, peel_exit, or on the surface)
+template <bool TRACE>
+__device__ __forceinline__ void ev_pre_done(const Ctx& X, Photon& P, Counters& C) {
+    const KernelArgs& A = X.A;
+    const bool hit_surface = !P.peel_exit;
+    if (P.tacc < 1.e-6 && !hit_surface) { retire<TRACE>(A, P, C); return; }
+    if (P.tacc < 1.e-6 && hit_surface) { double xi = rng_next<TRACE>(P.rng, A); P.tau = -log(1.0 - xi); }
+    else {
+        double xi = rng_next<TRACE>(P.rng, A);
+        if (P.tacc < 50.0) {
+            P.tau = -log(1.0 - xi * (1.0 - exp(-P.tacc)));
+            double f = 1.0 - exp(-P.tacc);
+            P.S[0] = P.S[0] * f; P.S[1] = P.S[1] * f; P.S[2] = P.S[2] * f; P.S[3] = P.S[3] * f;
+        } else P.tau = -log(1.0 - xi);
+    }
+    P.tau_run = 0.0; start_probe(P, 0); P.ph = PH_WALK;
+}
+
+// the walk reached the surface :755-764: absorbed, or on to the Lambert reflection event
+template <bool TRACE>
+__device__ __forceinline__ void ev_surface_hit(const Ctx& X, Photon& P, Counters& C) {
+    const KernelArgs& A = X.A;
+    double xi = rng_next<TRACE>(P.rng, A);
+    if (xi > A.L.surface_albedo) { P.at_walker = true; retire<TRACE>(A, P, C); }
+    else P.ph = PH_LAMBERT;
+}
+
+// a photon left the grid (peel_exit) or was dropped by an error path while walking
+template <bool TRACE>
+__device__ __forceinline__ void ev_retire(const Ctx& X, Photon& P, Counters& C) {
+    const KernelArgs& A = X.A;
+    if (P.peel_exit && A.L.photon_source == 2) atomicAdd(A.O.flux + 1, P.S[0]);  // :780 / :953
+    retire<TRACE>(A, P, C);
+}
+
+// every cheap follow-up of a crossing, for the engines that keep the whole photon in registers
+template <bool TRACE>
+__device__ __forceinline__ void cheap_handlers(const Ctx& X, Photon& P, Counters& C) {
+    if (P.ph == PH_PREDONE) ev_pre_done<TRACE>(X, P, C);
+    else if (P.ph == PH_SURFHIT) ev_surface_hit<TRACE>(X, P, C);
+    else if (P.ph == PH_RETIRE) ev_retire<TRACE>(X, P, C);
+    if (P.ph == PH_SCAT) ev_survive<TRACE>(X, P, C);
 }
 
 // ================= surface reflection: lambertian :1369-1402, then the start of peel_surface :4600-4650 ==========
@@ -532,7 +577,7 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
     const LaunchArgs& L = A.L;
     const int lane = threadIdx.x & 31;
     Photon P;
-    P.ph = PH_NEW; P.rng.nd = 0; P.rng.id = 0; P.rng.exhausted = false;
+    P.ph = PH_NEW; P.rng.nd = 0; P.rng.id = 0; P.rng.exhausted = false; P.at_walker = false;
     Counters C; C.zero();
 
     for (;;) {
@@ -552,10 +597,8 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
             }
         }
         // B. one cell crossing for every walking lane
-        if (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL) ev_cross<TRACE>(X, P, C);
+        if (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL) { ev_cross<TRACE>(X, P, C); cheap_handlers<TRACE>(X, P, C); }
         if (P.ph == PH_LAMBERT) ev_lambert<TRACE>(X, P, C);
-        // D. survival + peel start (cheap, immediate)
-        if (P.ph == PH_SCAT) ev_survive<TRACE>(X, P, C);
         // C, E. heavy events run once enough lanes of the warp wait for them
         const unsigned m_evt = __ballot_sync(FULL, P.ph == PH_PEELDONE || P.ph == PH_SCAT2);
         const unsigned m_walk = __ballot_sync(FULL, P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL);
@@ -567,9 +610,7 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
     C.flush(A.O.stats);
 }
 
-// =====================================================================================================
-// Engine 2: wavefront.  Photon pool in HBM (SoA), queues of slot indices, three kernels per pass.
-// =====================================================================================================
+
 __device__ __forceinline__ unsigned long long pack_cf(int c0, int c1, int c2, int f0, int f1) {
     return (unsigned long long)(unsigned)((c0 + 1) & 0xffff) | ((unsigned long long)(unsigned)(c1 & 0xffff) << 16) |
            ((unsigned long long)(unsigned)(c2 & 0xffff) << 32) | ((unsigned long long)(unsigned)(f0 & 3) << 48) |
@@ -580,6 +621,225 @@ __device__ __forceinline__ void unpack_cf(unsigned long long v, int& c0, int& c1
     f0 = (int)((v >> 48) & 3); f1 = (int)((v >> 50) & 0x3fff);
 }
 
+// =====================================================================================================
+// Engine 3: regroup.  Every warp owns 64 photons whose state lives in shared memory; the 32 lanes march
+// the photons that are ready to walk, and as soon as a photon needs a heavy event its lane parks it in its
+// slot and picks up another ready photon.  When 32 photons wait (peel deposit + scattering, Lambert
+// reflection, or an empty slot to emit into) the whole warp runs that event code once, fully converged,
+// and the photons become ready again.  No lane idles while others march, no event runs for a fraction of
+// a warp, and nothing leaves the SM: this is the "regroup by next event with ballot / compaction" design.
+// =====================================================================================================
+constexpr int RG_SLOTS = 64;     // photons per warp
+constexpr int RG_STRIDE = 23;    // doubles per slot, odd -> conflict-free when lanes touch distinct slots
+// slot layout (doubles): 0-2 p | 3-5 d | 6-9 S | 10 tau | 11 tau_run | 12 tacc | 13-15 w | 16 hcf | 17 wcf | 18 id |
+//                        19 nd, misc | 20 t_len, t_nsc | 21 t_hash
+
+__device__ __forceinline__ unsigned long long d2u(double v) { return (unsigned long long)__double_as_longlong(v); }
+__device__ __forceinline__ double u2d(unsigned long long v) { return __longlong_as_double((long long)v); }
+__device__ __forceinline__ unsigned pack_misc(const Photon& P) {
+    return (unsigned)P.ph | ((unsigned)P.pk << 4) | ((P.peel_exit ? 1u : 0u) << 6) | ((P.rng.exhausted ? 1u : 0u) << 7) |
+           ((P.at_walker ? 1u : 0u) << 8);
+}
+__device__ __forceinline__ void unpack_misc(unsigned m, Photon& P) {
+    P.ph = (int)(m & 15u); P.pk = (int)((m >> 4) & 3u); P.peel_exit = ((m >> 6) & 1u) != 0u;
+    P.rng.exhausted = ((m >> 7) & 1u) != 0u; P.at_walker = ((m >> 8) & 1u) != 0u;
+}
+
+// hot = what a marching lane keeps in registers
+template <bool TRACE>
+__device__ __forceinline__ void slot_store_hot(double* sl, const Photon& P) {
+    sl[10] = P.tau; sl[11] = P.tau_run; sl[12] = P.tacc; sl[13] = P.wx; sl[14] = P.wy; sl[15] = P.wz;
+    sl[17] = u2d(pack_cf(P.wc0, P.wc1, P.wc2, P.wf0, P.wf1));
+    sl[19] = u2d((unsigned long long)P.rng.nd | ((unsigned long long)pack_misc(P) << 32));
+    if (TRACE) { sl[20] = u2d((unsigned long long)(unsigned)P.t_len | ((unsigned long long)(unsigned)P.t_nsc << 32)); sl[21] = u2d(P.t_hash); }
+}
+template <bool TRACE>
+__device__ __forceinline__ void slot_load_hot(const double* sl, Photon& P) {
+    P.S[0] = sl[6];
+    P.tau = sl[10]; P.tau_run = sl[11]; P.tacc = sl[12]; P.wx = sl[13]; P.wy = sl[14]; P.wz = sl[15];
+    unpack_cf(d2u(sl[17]), P.wc0, P.wc1, P.wc2, P.wf0, P.wf1);
+    const unsigned long long nm = d2u(sl[19]);
+    P.rng.nd = (unsigned)nm; unpack_misc((unsigned)(nm >> 32), P);
+    if (TRACE) { const unsigned long long t = d2u(sl[20]); P.t_len = (int)(unsigned)t; P.t_nsc = (int)(unsigned)(t >> 32); P.t_hash = d2u(sl[21]); }
+}
+// cold = the rest (home position, direction, Stokes vector, random stream)
+template <bool TRACE>
+__device__ __forceinline__ void slot_load_cold(const double* sl, Photon& P, unsigned long long seed, bool with_home) {
+    if (with_home) { P.px = sl[0]; P.py = sl[1]; P.pz = sl[2]; unpack_cf(d2u(sl[16]), P.c0, P.c1, P.c2, P.f0, P.f1); }
+    P.dx = sl[3]; P.dy = sl[4]; P.dz = sl[5];
+    P.S[0] = sl[6]; P.S[1] = sl[7]; P.S[2] = sl[8]; P.S[3] = sl[9];
+    P.rng.id = d2u(sl[18]);
+    if (!TRACE && (P.rng.nd & 3u)) philox_block(P.rng.id, P.rng.nd >> 2, seed, P.rng);
+}
+__device__ __forceinline__ void slot_store_cold(double* sl, const Photon& P) {
+    sl[0] = P.px; sl[1] = P.py; sl[2] = P.pz; sl[3] = P.dx; sl[4] = P.dy; sl[5] = P.dz;
+    sl[6] = P.S[0]; sl[7] = P.S[1]; sl[8] = P.S[2]; sl[9] = P.S[3];
+    sl[16] = u2d(pack_cf(P.c0, P.c1, P.c2, P.f0, P.f1));
+    sl[18] = u2d(P.rng.id);
+}
+
+__device__ __forceinline__ int nth_set_bit64(unsigned long long m, int n) {   // position of the n-th (0-based) set bit
+    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const int cl = __popc(lo);
+    return (n < cl) ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - cl + 1);
+}
+__device__ __forceinline__ unsigned long long warp_or64(bool pred, int bit) {
+    const unsigned long long v = pred ? (1ull << bit) : 0ull;
+    const unsigned lo = __reduce_or_sync(FULL, (unsigned)v), hi = __reduce_or_sync(FULL, (unsigned)(v >> 32));
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(128, 4) regroup_kernel(const __grid_constant__ KernelArgs A) {
+    extern __shared__ double sm[];
+    stage_tables(sm, A.T);
+    const Ctx X(sm, A);
+    const LaunchArgs& L = A.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* slots = sm + X.lay.total + (size_t)warp * RG_SLOTS * RG_STRIDE;
+    unsigned long long ready = 0ull, pend = 0ull, freem = ~0ull;   // warp-uniform slot sets
+    bool supply = true;                                            // photons left to emit (warp-uniform)
+    Counters C; C.zero();
+    Photon P;                        // the photon this lane is marching (hot fields; cold ones only transiently)
+    P.ph = PH_NEW; P.at_walker = false; P.rng.exhausted = false; P.rng.nd = 0; P.rng.id = 0;
+    int cur = -1;
+    double n0 = 0, n1 = 0, n2 = 0;   // walker direction
+#if !ARTES_FAITHFUL
+    Ray R;
+    bool need_ray = false;
+#endif
+
+    for (;;) {
+        const unsigned marching = __ballot_sync(FULL, cur >= 0);
+        const int n_pend = __popcll(pend), n_free = supply ? __popcll(freem) : 0;
+        const int items = n_pend + n_free;
+        if (marching == 0u && ready == 0ull && items == 0) break;
+
+        // ------------------------------------------------------------------ event round (converged)
+        if (items >= 32 || (marching == 0u && ready == 0ull)) {
+            __syncwarp();
+            int my = -1;
+            bool is_emit = false;
+            if (lane < n_pend) my = nth_set_bit64(pend, lane);
+            else if (lane - n_pend < n_free) { my = nth_set_bit64(freem, lane - n_pend); is_emit = true; }
+            unsigned long long k = 0;
+            {   // photon ids for the emitting lanes, warp-aggregated
+                const unsigned em = __ballot_sync(FULL, is_emit);
+                unsigned long long k0 = 0;
+                if (em) {
+                    const int leader = __ffs(em) - 1;
+                    if (lane == leader) k0 = atomicAdd(A.O.counter, (unsigned long long)__popc(em));
+                    k0 = __shfl_sync(FULL, k0, leader);
+                }
+                k = k0 + (unsigned long long)__popc(em & ((1u << lane) - 1u));
+                const bool dry = is_emit && k >= L.n_photons;
+                if (dry) { is_emit = false; my = -1; }
+                if (__any_sync(FULL, dry)) supply = false;
+            }
+            bool now_ready = false, now_free = false;
+            const bool was_pend = (my >= 0) && !is_emit;
+            if (my >= 0) {
+                double* sl = slots + my * RG_STRIDE;
+                Photon E;
+                if (is_emit) ev_emit<TRACE>(X, E, C, k);
+                else {
+                    slot_load_hot<TRACE>(sl, E);
+                    slot_load_cold<TRACE>(sl, E, L.seed, true);
+                    if (E.ph == PH_LAMBERT) ev_lambert<TRACE>(X, E, C);
+                    else {
+                        ev_peel_done<TRACE>(X, E, C);
+                        if (E.ph == PH_SCAT2) ev_scatter<TRACE>(X, E, C);
+                    }
+                }
+                if (E.ph == PH_NEW) now_free = !is_emit;        // a failed emission leaves the slot free as it was
+                else { slot_store_cold(sl, E); slot_store_hot<TRACE>(sl, E); now_ready = true; }
+            }
+            const int bit = my < 0 ? 0 : my;
+            pend &= ~warp_or64(was_pend, bit);
+            freem = (freem & ~warp_or64(is_emit && now_ready, bit)) | warp_or64(now_free, bit);
+            ready |= warp_or64(now_ready, bit);
+            __syncwarp();
+            continue;
+        }
+
+        // ------------------------------------------------------------------ empty lanes pick up ready photons
+        {
+            const unsigned empty = __ballot_sync(FULL, cur < 0);
+            if (empty && ready) {
+                const int rank = __popc(empty & ((1u << lane) - 1u));
+                bool took = false;
+                if (cur < 0 && rank < __popcll(ready)) {
+                    cur = nth_set_bit64(ready, rank);
+                    const double* sl = slots + cur * RG_STRIDE;
+                    slot_load_hot<TRACE>(sl, P);
+                    if (P.ph == PH_PEEL) { n0 = L.det[0]; n1 = L.det[1]; n2 = L.det[2]; }
+                    else { n0 = sl[3]; n1 = sl[4]; n2 = sl[5]; }
+                    if (TRACE) P.rng.id = d2u(sl[18]);
+#if !ARTES_FAITHFUL
+                    need_ray = true;
+#endif
+                    took = true;
+                }
+                ready &= ~warp_or64(took, took ? cur : 0);
+            }
+        }
+
+        // ------------------------------------------------------------------ one crossing for every marching lane
+#if !ARTES_FAITHFUL
+        {   // new rays are set up when enough lanes need one (or nobody can step)
+            const unsigned m_setup = __ballot_sync(FULL, cur >= 0 && need_ray);
+            const unsigned m_go = __ballot_sync(FULL, cur >= 0 && !need_ray);
+            if (m_setup && (__popc(m_setup) >= L.defer_refill || m_go == 0u)) {
+                if (cur >= 0 && need_ray) { ray_setup(X, P, R, n0, n1, n2); need_ray = false; }
+            }
+        }
+        const bool step = cur >= 0 && !need_ray;
+#else
+        const bool step = cur >= 0;
+#endif
+        bool to_pend = false, to_free = false;
+        if (step) {
+            double* sl = slots + cur * RG_STRIDE;
+            CellFace o;
+#if ARTES_FAITHFUL
+            cell_face(X.sm, X.lay, A.T, P.wx, P.wy, P.wz, n0, n1, n2, P.wf0, P.wf1, P.wc0, P.wc1, P.wc2, o);
+            apply_crossing<TRACE>(X, P, C, o, n0, n1, n2);
+#else
+            int axis;
+            ray_next(A.T, P, R, o, axis);
+            const int ph0 = P.ph;
+            apply_crossing<TRACE>(X, P, C, o, n0, n1, n2);
+            if (P.ph == ph0) ray_advance(X, P, R, axis);
+#endif
+            if (P.ph == PH_PREDONE || P.ph == PH_SCAT || P.ph == PH_SURFHIT || P.ph == PH_RETIRE) {
+                // cheap follow-ups that need the random stream / Stokes vector: fetch them from the slot
+                slot_load_cold<TRACE>(sl, P, L.seed, P.ph != PH_SCAT);
+                cheap_handlers<TRACE>(X, P, C);
+                if (P.ph != PH_NEW) {
+                    slot_store_cold(sl, P);
+                    if (P.ph == PH_PEEL) { n0 = L.det[0]; n1 = L.det[1]; n2 = L.det[2]; }
+                    else { n0 = P.dx; n1 = P.dy; n2 = P.dz; }
+#if !ARTES_FAITHFUL
+                    need_ray = true;
+#endif
+                }
+            }
+            if (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT) { slot_store_hot<TRACE>(sl, P); to_pend = true; }
+            else if (P.ph == PH_NEW) to_free = true;
+        }
+        if (__any_sync(FULL, to_pend || to_free)) {
+            const int bit = cur < 0 ? 0 : cur;
+            pend |= warp_or64(to_pend, bit);
+            freem |= warp_or64(to_free, bit);
+            if (to_pend || to_free) cur = -1;
+        }
+    }
+    C.flush(A.O.stats);
+}
+
+// =====================================================================================================
+// Engine 2: wavefront.  Photon pool in HBM (SoA), queues of slot indices, three kernels per pass.
+// =====================================================================================================
 // what the march kernel needs of a photon
 template <bool TRACE>
 __device__ __forceinline__ void pool_load_all(const PoolArgs& Q, int s, Photon& P) {
@@ -593,6 +853,7 @@ __device__ __forceinline__ void pool_load_all(const PoolArgs& Q, int s, Photon& 
     P.rng.id = Q.id[s];
     const unsigned m = Q.misc[s];
     P.ph = (int)(m & 15u); P.pk = (int)((m >> 4) & 3u); P.peel_exit = ((m >> 6) & 1u) != 0u; P.rng.exhausted = ((m >> 7) & 1u) != 0u;
+    P.at_walker = false;
     P.rng.nd = Q.nd[s];
     if (!TRACE && (P.rng.nd & 3u)) philox_block(P.rng.id, P.rng.nd >> 2, Q.seed, P.rng);   // rebuild the buffered block
     if (TRACE) { P.t_len = Q.t_len[s]; P.t_nsc = Q.t_nsc[s]; P.t_hash = Q.t_hash[s]; }
@@ -680,6 +941,10 @@ __global__ void __launch_bounds__(128, 4) wf_march_kernel(const __grid_constant_
     P.ph = PH_NEW;
     int slot = -1;
     bool drained = false;
+#if !ARTES_FAITHFUL
+    Ray R;
+    bool need_ray = true;
+#endif
     for (;;) {
         // refill free lanes from the march queue
         const unsigned need = __ballot_sync(FULL, slot < 0 && !drained);
@@ -690,19 +955,53 @@ __global__ void __launch_bounds__(128, 4) wf_march_kernel(const __grid_constant_
             base = __shfl_sync(FULL, base, leader);
             if (slot < 0 && !drained) {
                 const unsigned i = base + __popc(need & ((1u << lane) - 1u));
-                if (i < n_in) { slot = q_in[i]; pool_load_all<TRACE>(Q, slot, P); }
+                if (i < n_in) {
+                    slot = q_in[i]; pool_load_all<TRACE>(Q, slot, P);
+#if !ARTES_FAITHFUL
+                    need_ray = true;
+#endif
+                }
                 else drained = true;
             }
         }
         if (__all_sync(FULL, slot < 0)) break;
         bool to_event = false, to_free = false;
+#if ARTES_FAITHFUL
         if (slot >= 0) {
             ev_cross<TRACE>(X, P, C);
-            if (P.ph == PH_SCAT) ev_survive<TRACE>(X, P, C);
+            cheap_handlers<TRACE>(X, P, C);
             to_event = (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT);
             to_free = (P.ph == PH_NEW);
             if (to_event) pool_store_all<TRACE>(Q, slot, P);
         }
+#else
+        // fast mode: incremental ray marching (ray.cuh).  A new ray is set up when a photon was fetched or
+        // its walk changed (pre-pass -> walk, interaction -> peel); those set-ups are ballot-deferred.
+        {
+            const unsigned m_setup = __ballot_sync(FULL, slot >= 0 && need_ray);
+            const unsigned m_go = __ballot_sync(FULL, slot >= 0 && !need_ray);
+            if (m_setup && (__popc(m_setup) >= A.L.defer_refill || m_go == 0u)) {
+                if (slot >= 0 && need_ray) {
+                    const bool peel = (P.ph == PH_PEEL);
+                    ray_setup(X, P, R, peel ? A.L.det[0] : P.dx, peel ? A.L.det[1] : P.dy, peel ? A.L.det[2] : P.dz);
+                    need_ray = false;
+                }
+            }
+        }
+        if (slot >= 0 && !need_ray) {
+            CellFace o;
+            int axis;
+            ray_next(A.T, P, R, o, axis);
+            const int ph0 = P.ph;
+            apply_crossing<TRACE>(X, P, C, o, R.n0, R.n1, R.n2);
+            cheap_handlers<TRACE>(X, P, C);
+            if (P.ph == ph0) ray_advance(X, P, R, axis);
+            else need_ray = true;
+            to_event = (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT);
+            to_free = (P.ph == PH_NEW);
+            if (to_event) pool_store_all<TRACE>(Q, slot, P);
+        }
+#endif
         if (__any_sync(FULL, to_event || to_free)) {
             queue_push(Q.q_event, Q.ctl + Q_NEVENT, to_event, slot);
             queue_push(Q.q_free, Q.ctl + Q_NFREE, to_free, slot);

@@ -30,7 +30,8 @@ constexpr unsigned FULL = 0xffffffffu;
 // pi = 4*atan(1) (src/ARTES.f90:9) is the correctly rounded double below.
 constexpr double PI = 3.14159265358979323846;
 
-enum Phase : int { PH_NEW = 0, PH_PRE, PH_WALK, PH_PEEL, PH_PEELDONE, PH_SCAT, PH_SCAT2, PH_IDLE, PH_LAMBERT };
+enum Phase : int { PH_NEW = 0, PH_PRE, PH_WALK, PH_PEEL, PH_PEELDONE, PH_SCAT, PH_SCAT2, PH_IDLE, PH_LAMBERT,
+                   PH_PREDONE, PH_SURFHIT, PH_RETIRE };
 enum PeelKind : int { PK_SCATTER = 0, PK_SURFACE = 1, PK_THERMAL = 2 };
 
 // ---------------------------------------------------------------------------------------------
@@ -175,26 +176,29 @@ __device__ __forceinline__ void cell_face(const double* __restrict__ sm, const S
         if (d > 1.e-12 && (d < fd12 || (d == fd12 && ord < (sel12 & 15)))) { fd12 = d; sel12 = ord | (face << 4); }
     };
 
-    // One solver body for all quadrics: the loop keeps the warp converged (every lane solves its k-th
-    // candidate in the same instruction stream) and keeps the kernel small enough for the instruction cache.
-#pragma unroll 1
-    for (int k = 0; k < 6; ++k) {
-        if (!((act >> k) & 1u)) continue;
+    // One solver body for all quadrics.  Every lane walks through ITS OWN list of existing candidates
+    // (bit scan of `act`), so the i-th trip of the loop solves the i-th candidate of every lane in one
+    // converged instruction stream: ~4 trips with nearly all lanes busy instead of 6-8 inlined solver
+    // copies that each run for a subset of the lanes.  The per-candidate arithmetic is unchanged.
+    while (act) {
+        const int k = __ffs(act) - 1;
+        act &= act - 1u;
         const bool cone = k >= 3;
         const int j = cone ? k - 3 : k;
         const int f = (int)(((cone ? packC : packS) >> (16 * j)) & 0xffffull);
-        double qa = qa_s, qb = qb_s, qc;
+        const double v = sm[cone ? lay.o_tt + f : f];                // tan(theta_f) or r_f
+        const double tf = sm[lay.o_tf + (cone ? f : 0)];
+        const int tp = cone ? tplane[f] : 1;
+        const double vv = v * v;
         int mir = 0;
+        if (cone) mir = (tf > PI / 2.0) ? 1 : ((tf < PI / 2.0) ? -1 : 0);
+        const double qa = cone ? A1 - A2 * v * v : qa_s;
+        const double qb = cone ? 2.0 * (B1 - B2 * v * v) : qb_s;
+        const double qc = cone ? C1 - C2 * v * v : qc_s - vv;
         double d;
-        if (!cone) { const double r = sm[f]; qc = qc_s - r * r; }
-        else {
-            const double t = sm[lay.o_tt + f], tf = sm[lay.o_tf + f];
-            mir = (tf > PI / 2.0) ? 1 : ((tf < PI / 2.0) ? -1 : 0);
-            qa = A1 - A2 * t * t; qb = 2.0 * (B1 - B2 * t * t); qc = C1 - C2 * t * t;
-        }
-        if (cone && tplane[f] != 1) {  // equatorial plane :3068, :3118 (never a "same" candidate)
+        if (tp != 1) {  // equatorial plane :3068, :3118 (never a "same" candidate)
             d = 0.0;
-            if (tplane[f] == 2) {
+            if (tp == 2) {
                 if (j == 0) { if (-z / n2 > 0.0 && n2 > 1.e-15) d = -z / n2; }
                 else if (j == 1) { if (-z / n2 > 0.0 && n2 < -1.e-15) d = -z / n2; }
             }

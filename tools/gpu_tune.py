@@ -17,5 +17,5 @@ for m in modes:
     r = t.gpu.run(t.launch_struct(n, seed=2))
     st = r["stats"]
     print(f"{name} {m} ev={os.environ.get('ARTES_DEFER_EVENTS','-')} rf={os.environ.get('ARTES_DEFER_REFILL','-')} "
-          f"n={n} kernel {st['kernel_ms']:.1f} ms -> {n/st['kernel_ms']*1e3:.4e} pkt/s  cf/pkt {st['n_cell_face']/n:.1f} sc/pkt {st['n_scatter']/n:.2f} I={r['det'][0,0].sum():.6e}", flush=True)
+          f"n={n} kernel {st['kernel_ms']:.1f} ms -> {n/st['kernel_ms']*1e3:.4e} pkt/s  launches {st['reserved']} cf/pkt {st['n_cell_face']/n:.1f} sc/pkt {st['n_scatter']/n:.2f} I={r['det'][0,0].sum():.6e}", flush=True)
     t.close()
