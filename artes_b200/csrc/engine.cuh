@@ -135,7 +135,7 @@ __device__ __forceinline__ void start_probe(Photon& P, int r_shift) {
 }
 
 // cos of the angle between the (oblate) surface normal at (x,y,z) and the detector :4609-4634
-__device__ __forceinline__ double surface_cos_angle(const KernelArgs& A, double x, double y, double z) {
+__device__ __noinline__ double surface_cos_angle(const KernelArgs& A, double x, double y, double z) {
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
     double s0 = x / (T.ox * T.ox), s1 = y / (T.oy * T.oy), s2 = z / (T.oz * T.oz);
@@ -149,7 +149,7 @@ __device__ __forceinline__ double surface_cos_angle(const KernelArgs& A, double 
 }
 
 // add_flow_global :4992-5014
-__device__ __forceinline__ void add_flow_global(const KernelArgs& A, double x, double y, double z, double dx, double dy, double dz,
+__device__ __noinline__ void add_flow_global(const KernelArgs& A, double x, double y, double z, double dx, double dy, double dz,
                                                 double e, double dist, int cellidx) {
     double th = acos(z / sqrt(x * x + y * y + z * z)), phh = atan2(y, x);
     double* f = A.O.flow3 + (size_t)3 * cellidx;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void add_flow_global(const KernelArgs& A, double x, d
 }
 
 // ================= A. emission: photon k of this launch (emit_photon :1008-1268) =================
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void ev_emit(const Ctx& X, Photon& P, Counters& C, unsigned long long k) {
     const KernelArgs& A = X.A;
     const DevTables& T = A.T;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void ev_emit(const Ctx& X, Photon& P, Counters& C, un
     P.tau = 0.0; P.tau_run = 0.0; P.peel_exit = false; P.at_walker = false; P.pk = PK_SCATTER;
     int e = 0;
     double bias_weight = 1.0;
-    if (L.photon_source == 1) {
+    if (!GEN || L.photon_source == 1) {
         P.f0 = 1; P.f1 = T.nr;
         double xi, r_disk;
         if (L.limb_emission) {
@@ -247,7 +247,7 @@ __device__ __forceinline__ void ev_emit(const Ctx& X, Photon& P, Counters& C, un
         if (e == 0 && fabs(P.dz) >= 1.0) err_count(A, 54);
     }
     if (e) { err_count(A, e); ++C.n_err; retire<TRACE>(A, P, C); }
-    else if (L.photon_source == 2) {  // :599-621
+    else if (GEN && L.photon_source == 2) {  // :599-621
         P.S[0] = P.S[0] * bias_weight / __ldg(T.cell_weight + P.c0 + T.nr * (P.c1 + T.nt * P.c2));
         atomicAdd(A.O.flux, P.S[0]);
         ++C.n_peel; P.pk = PK_THERMAL; start_probe(P, 0); P.ph = PH_PEEL;
@@ -281,24 +281,24 @@ __device__ __forceinline__ void ev_survive(const Ctx& X, Photon& P, Counters& C)
 // ================= B. one cell crossing of the walk the photon is in =================
 // On return P.ph tells what comes next: PH_PRE / PH_WALK / PH_PEEL (keep walking), PH_SCAT (interaction
 // reached -> ev_survive), PH_PEELDONE (-> ev_peel_done), PH_LAMBERT (surface reflection event), PH_NEW (retired).
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void apply_crossing(const Ctx& X, Photon& P, Counters& C, const CellFace& o, double n0, double n1, double n2);
 
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void ev_cross(const Ctx& X, Photon& P, Counters& C) {
     const LaunchArgs& L = X.A.L;
     const bool peel = (P.ph == PH_PEEL);
     const double n0 = peel ? L.det[0] : P.dx, n1 = peel ? L.det[1] : P.dy, n2 = peel ? L.det[2] : P.dz;
     CellFace o;
     cell_face(X.sm, X.lay, X.A.T, P.wx, P.wy, P.wz, n0, n1, n2, P.wf0, P.wf1, P.wc0, P.wc1, P.wc2, o);
-    apply_crossing<TRACE>(X, P, C, o, n0, n1, n2);
+    apply_crossing<TRACE, GEN>(X, P, C, o, n0, n1, n2);
 }
 
 // What one crossing does to the photon, given the geometry result `o` along direction (n0,n1,n2).
 // Touches only the "hot" walker state (w, wc, wf, tau, tau_run, tacc, S[0] for the flow counters); whatever
 // needs the random stream or the full Stokes vector is left to a follow-up handler chosen through P.ph:
 //   PH_PREDONE -> ev_pre_done, PH_SCAT -> ev_survive, PH_SURFHIT -> ev_surface_hit, PH_RETIRE -> ev_retire.
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void apply_crossing(const Ctx& X, Photon& P, Counters& C, const CellFace& o, double n0, double n1, double n2) {
     const KernelArgs& A = X.A;
     const DevTables& T = A.T;
@@ -322,12 +322,12 @@ __device__ __forceinline__ void apply_crossing(const Ctx& X, Photon& P, Counters
             const double s = (P.tau - P.tau_run) / kap;
             P.px = P.wx + s * n0; P.py = P.wy + s * n1; P.pz = P.wz + s * n2;
             P.c0 = P.wc0; P.c1 = P.wc1; P.c2 = P.wc2; P.f0 = 0; P.f1 = 0;
-            if (L.flow_global) add_flow_global(A, P.px, P.py, P.pz, n0, n1, n2, P.S[0], s, wci);
+            if (GEN && L.flow_global) add_flow_global(A, P.px, P.py, P.pz, n0, n1, n2, P.S[0], s, wci);
             P.ph = PH_SCAT;
         } else {
             P.wx = P.wx + o.dist * n0; P.wy = P.wy + o.dist * n1; P.wz = P.wz + o.dist * n2;
-            if (L.flow_global) add_flow_global(A, P.wx, P.wy, P.wz, n0, n1, n2, P.S[0], o.dist, wci);
-            if (L.flow_theta) {  // :730-744
+            if (GEN && L.flow_global) add_flow_global(A, P.wx, P.wy, P.wz, n0, n1, n2, P.S[0], o.dist, wci);
+            if (GEN && L.flow_theta) {  // :730-744
                 double* f = A.O.flow4 + (size_t)4 * wci;
                 if (o.nf0 == 1) { if (o.co0 > P.wc0) atomicAdd(f, P.S[0]); else if (o.co0 < P.wc0) atomicAdd(f + 1, P.S[0]); }
                 else if (o.nf0 == 2) { if (o.co1 > P.wc1) atomicAdd(f + 2, P.S[0]); else if (o.co1 < P.wc1) atomicAdd(f + 3, P.S[0]); }
@@ -355,41 +355,41 @@ __device__ __forceinline__ void ev_pre_done(const Ctx& X, Photon& P, Counters& C
     const KernelArgs& A = X.A;
     const bool hit_surface = !P.peel_exit;
     if (P.tacc < 1.e-6 && !hit_surface) { retire<TRACE>(A, P, C); return; }
-    if (P.tacc < 1.e-6 && hit_surface) { double xi = rng_next<TRACE>(P.rng, A); P.tau = -log(1.0 - xi); }
-    else {
-        double xi = rng_next<TRACE>(P.rng, A);
-        if (P.tacc < 50.0) {
-            P.tau = -log(1.0 - xi * (1.0 - exp(-P.tacc)));
-            double f = 1.0 - exp(-P.tacc);
-            P.S[0] = P.S[0] * f; P.S[1] = P.S[1] * f; P.S[2] = P.S[2] * f; P.S[3] = P.S[3] * f;
-        } else P.tau = -log(1.0 - xi);
+    // one draw in every branch of :666-685; the forced first interaction rescales the Stokes vector
+    const double xi = rng_next<TRACE>(P.rng, A);
+    double arg = 1.0 - xi;
+    if (!(P.tacc < 1.e-6) && P.tacc < 50.0) {
+        const double f = 1.0 - exp(-P.tacc);
+        arg = 1.0 - xi * f;
+        P.S[0] = P.S[0] * f; P.S[1] = P.S[1] * f; P.S[2] = P.S[2] * f; P.S[3] = P.S[3] * f;
     }
+    P.tau = -log(arg);
     P.tau_run = 0.0; start_probe(P, 0); P.ph = PH_WALK;
 }
 
 // the walk reached the surface :755-764: absorbed, or on to the Lambert reflection event
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void ev_surface_hit(const Ctx& X, Photon& P, Counters& C) {
     const KernelArgs& A = X.A;
     double xi = rng_next<TRACE>(P.rng, A);
-    if (xi > A.L.surface_albedo) { P.at_walker = true; retire<TRACE>(A, P, C); }
+    if (!GEN || xi > A.L.surface_albedo) { P.at_walker = true; retire<TRACE>(A, P, C); }
     else P.ph = PH_LAMBERT;
 }
 
 // a photon left the grid (peel_exit) or was dropped by an error path while walking
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void ev_retire(const Ctx& X, Photon& P, Counters& C) {
     const KernelArgs& A = X.A;
-    if (P.peel_exit && A.L.photon_source == 2) atomicAdd(A.O.flux + 1, P.S[0]);  // :780 / :953
+    if (GEN && P.peel_exit && A.L.photon_source == 2) atomicAdd(A.O.flux + 1, P.S[0]);  // :780 / :953
     retire<TRACE>(A, P, C);
 }
 
 // every cheap follow-up of a crossing, for the engines that keep the whole photon in registers
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void cheap_handlers(const Ctx& X, Photon& P, Counters& C) {
     if (P.ph == PH_PREDONE) ev_pre_done<TRACE>(X, P, C);
-    else if (P.ph == PH_SURFHIT) ev_surface_hit<TRACE>(X, P, C);
-    else if (P.ph == PH_RETIRE) ev_retire<TRACE>(X, P, C);
+    else if (P.ph == PH_SURFHIT) ev_surface_hit<TRACE, GEN>(X, P, C);
+    else if (P.ph == PH_RETIRE) ev_retire<TRACE, GEN>(X, P, C);
     if (P.ph == PH_SCAT) ev_survive<TRACE>(X, P, C);
 }
 
@@ -418,20 +418,20 @@ __device__ __forceinline__ void ev_lambert(const Ctx& X, Photon& P, Counters& C)
 }
 
 // ================= C. a peel walk ended: weight + deposit =================
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __device__ __forceinline__ void ev_peel_done(const Ctx& X, Photon& P, Counters& C) {
     const KernelArgs& A = X.A;
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
     const bool ok = P.peel_exit && P.tacc < 50.0;
-    if (P.pk == PK_THERMAL) {  // :4571-4596
+    if (GEN && P.pk == PK_THERMAL) {  // :4571-4596
         if (ok) {
             double w = exp(-P.tacc) / (4.0 * PI);
             double W0 = w * P.S[0];
             if (W0 > 0.0 && W0 < 1.e100) deposit<TRACE>(A, P, W0, 0, 0, 0, false); else err_count(A, 51);
         }
         start_probe(P, 0); P.ph = PH_PRE;
-    } else if (P.pk == PK_SURFACE) {  // :4675-4704
+    } else if (GEN && P.pk == PK_SURFACE) {  // :4675-4704
         if (ok) {
             const double cos_angle = surface_cos_angle(A, P.px, P.py, P.pz);
             double w = exp(-P.tacc) * cos_angle / PI;
@@ -569,7 +569,7 @@ __device__ __forceinline__ void ev_scatter(const Ctx& X, Photon& P, Counters& C)
 // =====================================================================================================
 // Engine 1: persistent lanes (one lane keeps one photon), events ballot-deferred
 // =====================================================================================================
-template <bool TRACE>
+template <bool TRACE, bool GEN>
 __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double sm[];
     stage_tables(sm, A.T);
@@ -579,6 +579,11 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
     Photon P;
     P.ph = PH_NEW; P.rng.nd = 0; P.rng.id = 0; P.rng.exhausted = false; P.at_walker = false;
     Counters C; C.zero();
+#if !ARTES_FAITHFUL && ARTES_PERSISTENT_RAY
+    Ray R;
+    int upd = 0, ray_ph = -1;      // ray_ph: the walk the current ray belongs to (-1: none)
+    double rn0 = 0, rn1 = 0, rn2 = 0;
+#endif
 
     for (;;) {
         // A. refill: new photons are emitted when enough lanes are free (or nobody walks any more)
@@ -593,17 +598,39 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
             if (P.ph == PH_NEW) {
                 const unsigned long long k = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
                 if (k >= L.n_photons) P.ph = PH_IDLE;
-                else ev_emit<TRACE>(X, P, C, k);
+                else ev_emit<TRACE, GEN>(X, P, C, k);
             }
         }
         // B. one cell crossing for every walking lane
-        if (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL) { ev_cross<TRACE>(X, P, C); cheap_handlers<TRACE>(X, P, C); }
-        if (P.ph == PH_LAMBERT) ev_lambert<TRACE>(X, P, C);
+#if ARTES_FAITHFUL || !ARTES_PERSISTENT_RAY
+        if (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL) { ev_cross<TRACE, GEN>(X, P, C); cheap_handlers<TRACE, GEN>(X, P, C); }
+#else
+        {   // fast mode: incremental ray marching (ray.cuh); a walk that just started first solves its three axes
+            const bool walking = (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL);
+            if (walking && ray_ph != P.ph) {
+                const bool peel = (P.ph == PH_PEEL);
+                rn0 = peel ? L.det[0] : P.dx; rn1 = peel ? L.det[1] : P.dy; rn2 = peel ? L.det[2] : P.dz;
+                ray_setup(X, P, R, rn0, rn1, rn2); upd = ray_axes(A.T); ray_ph = P.ph;
+            }
+            if (walking && upd) ray_update(X, R, upd, P.wc0, P.wc1, P.wc2, rn0, rn1, rn2);
+            if (walking && upd == 0) {
+                CellFace o;
+                int axis;
+                ray_next(A.T, P, R, o, axis);
+                const int ph0 = P.ph;
+                apply_crossing<TRACE, GEN>(X, P, C, o, rn0, rn1, rn2);
+                if (P.ph == ph0) { R.t = (axis == 0) ? R.tr : ((axis == 1) ? R.tt : R.tp); upd = 1 << axis; }
+                else ray_ph = -1;
+                cheap_handlers<TRACE, GEN>(X, P, C);
+            }
+        }
+#endif
+        if (GEN && P.ph == PH_LAMBERT) { ev_lambert<TRACE>(X, P, C); }
         // C, E. heavy events run once enough lanes of the warp wait for them
         const unsigned m_evt = __ballot_sync(FULL, P.ph == PH_PEELDONE || P.ph == PH_SCAT2);
         const unsigned m_walk = __ballot_sync(FULL, P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL);
         const bool run_events = m_evt && (__popc(m_evt) >= L.defer_events || m_walk == 0u);
-        if (run_events && P.ph == PH_PEELDONE) ev_peel_done<TRACE>(X, P, C);
+        if (run_events && P.ph == PH_PEELDONE) ev_peel_done<TRACE, GEN>(X, P, C);
         if (run_events && P.ph == PH_SCAT2) ev_scatter<TRACE>(X, P, C);
         if (__all_sync(FULL, P.ph == PH_IDLE)) break;
     }
@@ -689,8 +716,36 @@ __device__ __forceinline__ unsigned long long warp_or64(bool pred, int bit) {
     return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
 
+
+// One heavy event on the photon in slot `sl` (or an emission into it), kept out of line: the march loop then
+// holds no event code and keeps its registers, and the event code sees a clean register file.
+// Returns x: 1 = slot now ready to march, 2 = slot now free, 0 = untouched; y,z,w: packed counter increments.
+template <bool TRACE>
+__device__ __noinline__ uint4 rg_event_fn(const KernelArgs* Ap, const double* sm, double* sl, int is_emit, unsigned long long k) {
+    constexpr bool GEN = true;
+    const KernelArgs& A = *Ap;
+    const Ctx X(sm, A);
+    Counters C; C.zero();
+    Photon E;
+    if (is_emit) ev_emit<TRACE, GEN>(X, E, C, k);
+    else {
+        slot_load_hot<TRACE>(sl, E);
+        slot_load_cold<TRACE>(sl, E, A.L.seed, true);
+        if (E.ph == PH_LAMBERT) ev_lambert<TRACE>(X, E, C);
+        else {
+            ev_peel_done<TRACE, GEN>(X, E, C);
+            if (E.ph == PH_SCAT2) ev_scatter<TRACE>(X, E, C);
+        }
+    }
+    unsigned res;
+    if (E.ph == PH_NEW) res = is_emit ? 0u : 2u;     // a failed emission leaves the slot free as it was
+    else { slot_store_cold(sl, E); slot_store_hot<TRACE>(sl, E); res = 1u; }
+    return make_uint4(res | (C.n_emit << 8) | (C.n_err << 16), C.n_sc | (C.n_peel << 16), C.n_draw, C.n_surf);
+}
+
 template <bool TRACE>
 __global__ void __launch_bounds__(128, 4) regroup_kernel(const __grid_constant__ KernelArgs A) {
+    constexpr bool GEN = true;
     extern __shared__ double sm[];
     stage_tables(sm, A.T);
     const Ctx X(sm, A);
@@ -707,6 +762,7 @@ __global__ void __launch_bounds__(128, 4) regroup_kernel(const __grid_constant__
 #if !ARTES_FAITHFUL
     Ray R;
     bool need_ray = false;
+    int upd = 0;
 #endif
 
     for (;;) {
@@ -739,20 +795,10 @@ __global__ void __launch_bounds__(128, 4) regroup_kernel(const __grid_constant__
             bool now_ready = false, now_free = false;
             const bool was_pend = (my >= 0) && !is_emit;
             if (my >= 0) {
-                double* sl = slots + my * RG_STRIDE;
-                Photon E;
-                if (is_emit) ev_emit<TRACE>(X, E, C, k);
-                else {
-                    slot_load_hot<TRACE>(sl, E);
-                    slot_load_cold<TRACE>(sl, E, L.seed, true);
-                    if (E.ph == PH_LAMBERT) ev_lambert<TRACE>(X, E, C);
-                    else {
-                        ev_peel_done<TRACE>(X, E, C);
-                        if (E.ph == PH_SCAT2) ev_scatter<TRACE>(X, E, C);
-                    }
-                }
-                if (E.ph == PH_NEW) now_free = !is_emit;        // a failed emission leaves the slot free as it was
-                else { slot_store_cold(sl, E); slot_store_hot<TRACE>(sl, E); now_ready = true; }
+                const uint4 r = rg_event_fn<TRACE>(&A, sm, slots + my * RG_STRIDE, is_emit ? 1 : 0, k);
+                now_ready = (r.x & 255u) == 1u; now_free = (r.x & 255u) == 2u;
+                C.n_emit += (r.x >> 8) & 255u; C.n_err += r.x >> 16; C.n_sc += r.y & 0xffffu; C.n_peel += r.y >> 16;
+                C.n_draw += r.z; C.n_surf += r.w;
             }
             const int bit = my < 0 ? 0 : my;
             pend &= ~warp_or64(was_pend, bit);
@@ -786,14 +832,11 @@ __global__ void __launch_bounds__(128, 4) regroup_kernel(const __grid_constant__
 
         // ------------------------------------------------------------------ one crossing for every marching lane
 #if !ARTES_FAITHFUL
-        {   // new rays are set up when enough lanes need one (or nobody can step)
-            const unsigned m_setup = __ballot_sync(FULL, cur >= 0 && need_ray);
-            const unsigned m_go = __ballot_sync(FULL, cur >= 0 && !need_ray);
-            if (m_setup && (__popc(m_setup) >= L.defer_refill || m_go == 0u)) {
-                if (cur >= 0 && need_ray) { ray_setup(X, P, R, n0, n1, n2); need_ray = false; }
-            }
-        }
-        const bool step = cur >= 0 && !need_ray;
+        // fast mode: a fresh ray first gets its constants, then every lane with a pending axis solves ONE
+        // axis per trip (same converged solver for all); a lane steps once nothing is pending.
+        if (cur >= 0 && need_ray) { ray_setup(X, P, R, n0, n1, n2); upd = ray_axes(A.T); need_ray = false; }
+        if (cur >= 0 && upd) ray_update(X, R, upd, P.wc0, P.wc1, P.wc2, n0, n1, n2);
+        const bool step = cur >= 0 && upd == 0;
 #else
         const bool step = cur >= 0;
 #endif
@@ -803,18 +846,18 @@ __global__ void __launch_bounds__(128, 4) regroup_kernel(const __grid_constant__
             CellFace o;
 #if ARTES_FAITHFUL
             cell_face(X.sm, X.lay, A.T, P.wx, P.wy, P.wz, n0, n1, n2, P.wf0, P.wf1, P.wc0, P.wc1, P.wc2, o);
-            apply_crossing<TRACE>(X, P, C, o, n0, n1, n2);
+            apply_crossing<TRACE, GEN>(X, P, C, o, n0, n1, n2);
 #else
             int axis;
             ray_next(A.T, P, R, o, axis);
             const int ph0 = P.ph;
-            apply_crossing<TRACE>(X, P, C, o, n0, n1, n2);
-            if (P.ph == ph0) ray_advance(X, P, R, axis);
+            apply_crossing<TRACE, GEN>(X, P, C, o, n0, n1, n2);
+            if (P.ph == ph0) { R.t = (axis == 0) ? R.tr : ((axis == 1) ? R.tt : R.tp); upd = 1 << axis; }
 #endif
             if (P.ph == PH_PREDONE || P.ph == PH_SCAT || P.ph == PH_SURFHIT || P.ph == PH_RETIRE) {
                 // cheap follow-ups that need the random stream / Stokes vector: fetch them from the slot
                 slot_load_cold<TRACE>(sl, P, L.seed, P.ph != PH_SCAT);
-                cheap_handlers<TRACE>(X, P, C);
+                cheap_handlers<TRACE, GEN>(X, P, C);
                 if (P.ph != PH_NEW) {
                     slot_store_cold(sl, P);
                     if (P.ph == PH_PEEL) { n0 = L.det[0]; n1 = L.det[1]; n2 = L.det[2]; }
@@ -895,6 +938,7 @@ enum { Q_NMARCH0 = 0, Q_NMARCH1 = 1, Q_NEVENT = 2, Q_NFREE = 3, Q_CURSOR = 4, Q_
 // ---- emit: every free slot takes the next photon id, if any is left -----------------------------------
 template <bool TRACE>
 __global__ void __launch_bounds__(128) wf_emit_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ PoolArgs Q) {
+    constexpr bool GEN = true;
     extern __shared__ double sm[];
     stage_tables(sm, A.T);
     const Ctx X(sm, A);
@@ -917,7 +961,7 @@ __global__ void __launch_bounds__(128) wf_emit_kernel(const __grid_constant__ Ke
         if (have && k < A.L.n_photons) {
             slot = Q.q_free[i];
             Photon P;
-            ev_emit<TRACE>(X, P, C, k);
+            ev_emit<TRACE, GEN>(X, P, C, k);
             if (P.ph != PH_NEW) { pool_store_all<TRACE>(Q, slot, P); go = true; }
             // an emission error retires the photon at once: the slot is simply not re-queued this pass
         }
@@ -929,6 +973,7 @@ __global__ void __launch_bounds__(128) wf_emit_kernel(const __grid_constant__ Ke
 // ---- march: persistent lanes pull photons and walk them to their next heavy event -----------------------
 template <bool TRACE>
 __global__ void __launch_bounds__(128, 4) wf_march_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ PoolArgs Q) {
+    constexpr bool GEN = true;
     extern __shared__ double sm[];
     stage_tables(sm, A.T);
     const Ctx X(sm, A);
@@ -944,6 +989,8 @@ __global__ void __launch_bounds__(128, 4) wf_march_kernel(const __grid_constant_
 #if !ARTES_FAITHFUL
     Ray R;
     bool need_ray = true;
+    int upd = 0;
+    double rn0 = 0, rn1 = 0, rn2 = 0;
 #endif
     for (;;) {
         // refill free lanes from the march queue
@@ -968,34 +1015,28 @@ __global__ void __launch_bounds__(128, 4) wf_march_kernel(const __grid_constant_
         bool to_event = false, to_free = false;
 #if ARTES_FAITHFUL
         if (slot >= 0) {
-            ev_cross<TRACE>(X, P, C);
-            cheap_handlers<TRACE>(X, P, C);
+            ev_cross<TRACE, GEN>(X, P, C);
+            cheap_handlers<TRACE, GEN>(X, P, C);
             to_event = (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT);
             to_free = (P.ph == PH_NEW);
             if (to_event) pool_store_all<TRACE>(Q, slot, P);
         }
 #else
-        // fast mode: incremental ray marching (ray.cuh).  A new ray is set up when a photon was fetched or
-        // its walk changed (pre-pass -> walk, interaction -> peel); those set-ups are ballot-deferred.
-        {
-            const unsigned m_setup = __ballot_sync(FULL, slot >= 0 && need_ray);
-            const unsigned m_go = __ballot_sync(FULL, slot >= 0 && !need_ray);
-            if (m_setup && (__popc(m_setup) >= A.L.defer_refill || m_go == 0u)) {
-                if (slot >= 0 && need_ray) {
-                    const bool peel = (P.ph == PH_PEEL);
-                    ray_setup(X, P, R, peel ? A.L.det[0] : P.dx, peel ? A.L.det[1] : P.dy, peel ? A.L.det[2] : P.dz);
-                    need_ray = false;
-                }
-            }
+        // fast mode: incremental ray marching (ray.cuh)
+        if (slot >= 0 && need_ray) {
+            const bool peel = (P.ph == PH_PEEL);
+            rn0 = peel ? A.L.det[0] : P.dx; rn1 = peel ? A.L.det[1] : P.dy; rn2 = peel ? A.L.det[2] : P.dz;
+            ray_setup(X, P, R, rn0, rn1, rn2); upd = ray_axes(A.T); need_ray = false;
         }
-        if (slot >= 0 && !need_ray) {
+        if (slot >= 0 && upd) ray_update(X, R, upd, P.wc0, P.wc1, P.wc2, rn0, rn1, rn2);
+        if (slot >= 0 && upd == 0) {
             CellFace o;
             int axis;
             ray_next(A.T, P, R, o, axis);
             const int ph0 = P.ph;
-            apply_crossing<TRACE>(X, P, C, o, R.n0, R.n1, R.n2);
-            cheap_handlers<TRACE>(X, P, C);
-            if (P.ph == ph0) ray_advance(X, P, R, axis);
+            apply_crossing<TRACE, GEN>(X, P, C, o, rn0, rn1, rn2);
+            cheap_handlers<TRACE, GEN>(X, P, C);
+            if (P.ph == ph0) { R.t = (axis == 0) ? R.tr : ((axis == 1) ? R.tt : R.tp); upd = 1 << axis; }
             else need_ray = true;
             to_event = (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT);
             to_free = (P.ph == PH_NEW);
@@ -1014,6 +1055,7 @@ __global__ void __launch_bounds__(128, 4) wf_march_kernel(const __grid_constant_
 // ---- event: deposit + scattering (or the continuation of a surface / thermal peel), fully converged ------
 template <bool TRACE>
 __global__ void __launch_bounds__(128) wf_event_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ PoolArgs Q) {
+    constexpr bool GEN = true;
     extern __shared__ double sm[];
     stage_tables(sm, A.T);
     const Ctx X(sm, A);
@@ -1032,7 +1074,7 @@ __global__ void __launch_bounds__(128) wf_event_kernel(const __grid_constant__ K
             pool_load_all<TRACE>(Q, slot, P);
             if (P.ph == PH_LAMBERT) ev_lambert<TRACE>(X, P, C);
             else {
-                ev_peel_done<TRACE>(X, P, C);
+                ev_peel_done<TRACE, GEN>(X, P, C);
                 if (P.ph == PH_SCAT2) ev_scatter<TRACE>(X, P, C);
             }
             if (P.ph == PH_NEW) freed = true;

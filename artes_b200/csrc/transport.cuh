@@ -22,6 +22,9 @@
 #ifndef ARTES_FAITHFUL
 #error "define ARTES_FAITHFUL to 0 or 1"
 #endif
+#ifndef ARTES_PERSISTENT_RAY
+#define ARTES_PERSISTENT_RAY 1   // fast mode: the persistent engine marches rays incrementally (ray.cuh)
+#endif
 
 namespace artes {
 namespace ARTES_NS {
@@ -58,7 +61,8 @@ struct Rng {
     bool exhausted;
 };
 
-__device__ __forceinline__ void philox_block(unsigned long long id, unsigned blk, unsigned long long seed, Rng& r) {
+// (kept out of line: ~100 integer instructions needed once per four draws at some twenty call sites)
+__device__ __noinline__ uint4 philox4(unsigned long long id, unsigned blk, unsigned long long seed) {
     unsigned c0 = (unsigned)id, c1 = (unsigned)(id >> 32), c2 = blk, c3 = 0u;
     unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
 #pragma unroll
@@ -69,7 +73,11 @@ __device__ __forceinline__ void philox_block(unsigned long long id, unsigned blk
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    r.b0 = c0; r.b1 = c1; r.b2 = c2; r.b3 = c3;
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ void philox_block(unsigned long long id, unsigned blk, unsigned long long seed, Rng& r) {
+    const uint4 v = philox4(id, blk, seed);
+    r.b0 = v.x; r.b1 = v.y; r.b2 = v.z; r.b3 = v.w;
 }
 
 template <bool TRACE>

@@ -13,7 +13,7 @@ import numpy as np
 from .abi import ABI_VERSION, ERR_SLOTS, NCCL_ID_BYTES, Launch, Stats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libartes_gpu.so")
+LIB_PATH = os.environ.get("ARTES_GPU_LIB") or os.path.join(_HERE, "libartes_gpu.so")
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
