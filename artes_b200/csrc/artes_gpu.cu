@@ -25,22 +25,14 @@ namespace artes {
 namespace faithful {
 size_t smem_bytes(int nr, int nt, int np);
 cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
-cudaError_t launch_regroup(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
-cudaError_t wf_prepare(const KernelArgs& a, bool trace, int sm_count, WfGeom* g);
-cudaError_t wf_init(const PoolArgs& q, cudaStream_t stream);
-cudaError_t wf_enqueue(const KernelArgs& a, const PoolArgs& q, bool trace, const WfGeom& g, int passes, cudaStream_t stream, int* launches);
 }  // namespace faithful
 namespace fast {
 size_t smem_bytes(int nr, int nt, int np);
 cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
-cudaError_t launch_regroup(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
-cudaError_t wf_prepare(const KernelArgs& a, bool trace, int sm_count, WfGeom* g);
-cudaError_t wf_init(const PoolArgs& q, cudaStream_t stream);
-cudaError_t wf_enqueue(const KernelArgs& a, const PoolArgs& q, bool trace, const WfGeom& g, int passes, cudaStream_t stream, int* launches);
 }  // namespace fast
 cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
 }  // namespace artes
@@ -92,14 +84,7 @@ struct DeviceState {
     unsigned long long* out_u = nullptr;   // [err 64 | stats 8 | counter 1]
     ncclComm_t comm = nullptr;
     unsigned long long n_photons = 0;
-    // wavefront engine
-    PoolArgs pool{};
-    std::vector<void*> pool_allocs;
-    unsigned* host_inflight = nullptr;      // mapped pinned
-    WfGeom geom{};
-    KernelArgs kargs{};
-    bool wf_active = false;
-    int launches = 0, passes = 0;
+    int launches = 0;
 };
 
 }  // namespace
@@ -204,75 +189,6 @@ void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
     a.star_dir[2] = 1.0 * std::cos(td);
 }
 
-// ARTES_ENGINE = regroup (default) | wavefront | persistent
-int engine_kind() {
-    static const int k = [] {
-        const char* v = std::getenv("ARTES_ENGINE");
-        if (v && std::strcmp(v, "persistent") == 0) return 0;
-        if (v && std::strcmp(v, "wavefront") == 0) return 1;
-        return 2;
-    }();
-    return k;
-}
-bool use_wavefront() { return engine_kind() == 1; }
-
-int ensure_pool(artes_gpu_ctx* ctx, DeviceState& d, size_t want, bool trace) {
-    static const size_t cap_env = [] { const char* v = std::getenv("ARTES_POOL"); return v && *v ? (size_t)std::atoll(v) : (size_t)(1u << 20); }();
-    size_t cap = std::min(std::max<size_t>(want, 1024), std::max<size_t>(cap_env, 1024));
-    cap = (cap + 31) & ~(size_t)31;
-    if (d.pool.capacity >= cap && (!trace || d.pool.t_hash)) { return 0; }
-    free_pool(d.pool_allocs);
-    PoolArgs q{};
-    q.capacity = cap;
-    auto dalloc = [&](void** p, size_t bytes) -> int { CU(cudaMalloc(p, bytes)); d.pool_allocs.push_back(*p); return 0; };
-    int rc = 0;
-    rc |= dalloc((void**)&q.d, 16 * cap * sizeof(double));
-    rc |= dalloc((void**)&q.hcf, cap * 8); rc |= dalloc((void**)&q.wcf, cap * 8); rc |= dalloc((void**)&q.id, cap * 8);
-    rc |= dalloc((void**)&q.t_hash, cap * 8);
-    rc |= dalloc((void**)&q.nd, cap * 4); rc |= dalloc((void**)&q.misc, cap * 4);
-    rc |= dalloc((void**)&q.t_len, cap * 4); rc |= dalloc((void**)&q.t_nsc, cap * 4);
-    rc |= dalloc((void**)&q.q_march, 2 * cap * 4); rc |= dalloc((void**)&q.q_event, cap * 4); rc |= dalloc((void**)&q.q_free, cap * 4);
-    rc |= dalloc((void**)&q.ctl, 16 * 4);
-    if (rc) return rc;
-    if (!d.host_inflight) CU(cudaHostAlloc((void**)&d.host_inflight, sizeof(unsigned), cudaHostAllocMapped));
-    CU(cudaHostGetDevicePointer((void**)&q.host_inflight, d.host_inflight, 0));
-    d.pool = q;
-    return 0;
-}
-
-// Runs the wavefront passes of every device of the context to completion (host loop over batches).
-int run_wavefront(artes_gpu_ctx* ctx, bool faithful, bool trace) {
-    const int batch = 8;
-    for (auto& d : ctx->devs) {
-        if (!d.wf_active) continue;
-        CU(cudaSetDevice(d.dev));
-        cudaError_t e = faithful ? faithful::wf_prepare(d.kargs, trace, d.sm_count, &d.geom) : fast::wf_prepare(d.kargs, trace, d.sm_count, &d.geom);
-        if (e == cudaSuccess) e = faithful ? faithful::wf_init(d.pool, d.stream) : fast::wf_init(d.pool, d.stream);
-        if (e != cudaSuccess) return fail(ctx, -2, std::string("wavefront prepare: ") + cudaGetErrorString(e));
-        *d.host_inflight = 1u;
-        d.launches = 1; d.passes = 0;
-    }
-    for (;;) {
-        bool any = false;
-        for (auto& d : ctx->devs) {
-            if (!d.wf_active) continue;
-            CU(cudaSetDevice(d.dev));
-            cudaError_t e = faithful ? faithful::wf_enqueue(d.kargs, d.pool, trace, d.geom, batch, d.stream, &d.launches)
-                                     : fast::wf_enqueue(d.kargs, d.pool, trace, d.geom, batch, d.stream, &d.launches);
-            if (e != cudaSuccess) return fail(ctx, -2, std::string("wavefront launch: ") + cudaGetErrorString(e));
-            d.passes += batch;
-        }
-        for (auto& d : ctx->devs) {
-            if (!d.wf_active) continue;
-            CU(cudaSetDevice(d.dev));
-            CU(cudaStreamSynchronize(d.stream));
-            if (*d.host_inflight == 0u) d.wf_active = false; else any = true;
-        }
-        if (!any) break;
-    }
-    return 0;
-}
-
 int check_launch(artes_gpu_ctx* ctx, const artes_launch_t* L) {
     if (!ctx) return fail(nullptr, -1, "null context");
     if (!L || L->struct_size != sizeof(artes_launch_t)) return fail(ctx, -1, "artes_launch_t: struct_size mismatch (ABI)");
@@ -342,8 +258,6 @@ int artes_gpu_destroy(artes_gpu_ctx* ctx) {
         if (d.comm && g_nccl.ok) g_nccl.CommDestroy(d.comm);
         free_pool(d.grid_allocs);
         free_pool(d.wl_allocs);
-        free_pool(d.pool_allocs);
-        if (d.host_inflight) cudaFreeHost(d.host_inflight);
         if (d.out_d) cudaFree(d.out_d);
         if (d.out_u) cudaFree(d.out_u);
         for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
@@ -543,30 +457,15 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
         a.O.stats = d.out_u + ARTES_ERR_SLOTS;
         a.O.counter = d.out_u + ARTES_ERR_SLOTS + 8;
         CU(cudaEventRecord(d.ev[0], d.stream));
-        d.wf_active = false;
+        d.launches = 0;
         if (a.L.n_photons > 0) {
-            if (use_wavefront()) {
-                rc = ensure_pool(ctx, d, (size_t)std::min<unsigned long long>(a.L.n_photons, 1ull << 30), false);
-                if (rc) return rc;
-                d.pool.seed = a.L.seed;
-                d.kargs = a;
-                d.wf_active = true;
-            } else {
-                cudaError_t e;
-                if (engine_kind() == 2) e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_regroup(a, false, d.sm_count, d.stream)
-                                                                             : fast::launch_regroup(a, false, d.sm_count, d.stream);
-                else e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, false, d.sm_count, d.stream)
-                                                          : fast::launch_transport(a, false, d.sm_count, d.stream);
-                if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
-                d.launches = 1; d.passes = 1;
-            }
+            cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, false, d.sm_count, d.stream)
+                                                             : fast::launch_transport(a, false, d.sm_count, d.stream);
+            if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
+            d.launches = 1;
         }
+        CU(cudaEventRecord(d.ev[1], d.stream));
     }
-    if (use_wavefront()) {   // the pass loop polls the in-flight count: this engine completes before returning
-        rc = run_wavefront(ctx, L->mode == ARTES_MODE_FAITHFUL, false);
-        if (rc) return rc;
-    }
-    for (auto& d : ctx->devs) { CU(cudaSetDevice(d.dev)); CU(cudaEventRecord(d.ev[1], d.stream)); }
     // NCCL sum of the packed accumulators (the thread sum of :959-975 across devices / ranks)
     const bool reduce = (ndev > 1) || ctx->rank_comm;
     if (reduce) {
@@ -700,23 +599,9 @@ int artes_gpu_trace(artes_gpu_ctx* ctx, const artes_launch_t* L, const double* x
     a.O.err = d.out_u; a.O.stats = d.out_u + ARTES_ERR_SLOTS; a.O.counter = d.out_u + ARTES_ERR_SLOTS + 8;
     a.R.xi = d_xi; a.R.max_draws = max_draws; a.R.max_rec = d_head ? max_rec : 0;
     a.R.seq_len = d_len; a.R.seq_hash = d_hash; a.R.seq_head = d_head; a.R.fstate = d_f;
-    if (use_wavefront()) {
-        rc = ensure_pool(ctx, d, (size_t)n, true);
-        if (rc) return rc;
-        d.pool.seed = a.L.seed;
-        d.kargs = a;
-        for (auto& o : ctx->devs) o.wf_active = false;
-        d.wf_active = true;
-        rc = run_wavefront(ctx, L->mode == ARTES_MODE_FAITHFUL, true);
-        if (rc) return rc;
-    } else {
-        cudaError_t e;
-        if (engine_kind() == 2) e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_regroup(a, true, d.sm_count, d.stream)
-                                                                     : fast::launch_regroup(a, true, d.sm_count, d.stream);
-        else e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, true, d.sm_count, d.stream)
-                                                  : fast::launch_transport(a, true, d.sm_count, d.stream);
-        if (e != cudaSuccess) return fail(ctx, -2, std::string("trace launch: ") + cudaGetErrorString(e));
-    }
+    cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, true, d.sm_count, d.stream)
+                                                     : fast::launch_transport(a, true, d.sm_count, d.stream);
+    if (e != cudaSuccess) return fail(ctx, -2, std::string("trace launch: ") + cudaGetErrorString(e));
     CU(cudaMemcpyAsync(seq_len, d_len, n * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
     CU(cudaMemcpyAsync(seq_hash, d_hash, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
     if (d_head) CU(cudaMemcpyAsync(seq_head, d_head, (size_t)n * max_rec * 5 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));

@@ -1,4 +1,4 @@
-// engine.cuh -- photon state, the five event bodies, and the two engines that schedule them.
+// engine.cuh -- photon state, the event bodies, and the persistent kernel that schedules them.
 // Included from transport.cuh (inside namespace artes::ARTES_NS).
 //
 // Event bodies (each a restatement of one part of radiative_transfer, src/ARTES.f90:546-955):
@@ -10,13 +10,11 @@
 //   ev_peel_done C  detector deposit of peel_photon :4763-4986, peel_surface :4675-4704, peel_thermal :4571-4596
 //   ev_scatter   E  scatter_photon :1434-1532 + polarization_rotation :1663-1932 + next tau :845-846
 //
-// Engines:
-//   transport_kernel   "persistent" engine: one lane owns one photon until it dies; B runs converged for
-//                      all walking lanes, C/E/A are ballot-deferred until enough lanes wait.
-//   wf_* kernels       "wavefront" engine: photons live in an HBM pool (SoA); a persistent march kernel
-//                      pulls photons from a queue and runs B/D until the next heavy event, then hands the
-//                      photon to the queue of that event; converged event / emit kernels process those
-//                      queues and feed the march queue of the next pass.
+// Engine: transport_kernel -- persistent lanes.  One lane owns one photon until it dies; the crossing step B
+// runs converged for all walking lanes, the heavy events C/E/A are ballot-deferred until enough lanes of the
+// warp wait for them.  Two other schedulers were built and measured in round 1 (git history: "wavefront" =
+// HBM photon pool + march/event/emit kernels with device queues; "regroup" = 64 photons per warp in shared
+// memory with fully converged event rounds); both lost to this one on every configuration.
 
 struct Photon {
     Rng rng;
@@ -569,7 +567,7 @@ __device__ __forceinline__ void ev_scatter(const Ctx& X, Photon& P, Counters& C)
 // =====================================================================================================
 // Engine 1: persistent lanes (one lane keeps one photon), events ballot-deferred
 // =====================================================================================================
-template <bool TRACE, bool GEN>
+template <bool TRACE, bool GEN, bool RAY>
 __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double sm[];
     stage_tables(sm, A.T);
@@ -579,7 +577,7 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
     Photon P;
     P.ph = PH_NEW; P.rng.nd = 0; P.rng.id = 0; P.rng.exhausted = false; P.at_walker = false;
     Counters C; C.zero();
-#if !ARTES_FAITHFUL && ARTES_PERSISTENT_RAY
+#if !ARTES_FAITHFUL
     Ray R;
     int upd = 0, ray_ph = -1;      // ray_ph: the walk the current ray belongs to (-1: none)
     double rn0 = 0, rn1 = 0, rn2 = 0;
@@ -602,10 +600,12 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
             }
         }
         // B. one cell crossing for every walking lane
-#if ARTES_FAITHFUL || !ARTES_PERSISTENT_RAY
+#if ARTES_FAITHFUL
         if (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL) { ev_cross<TRACE, GEN>(X, P, C); cheap_handlers<TRACE, GEN>(X, P, C); }
 #else
-        {   // fast mode: incremental ray marching (ray.cuh); a walk that just started first solves its three axes
+        if (!RAY) {
+            if (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL) { ev_cross<TRACE, GEN>(X, P, C); cheap_handlers<TRACE, GEN>(X, P, C); }
+        } else {   // incremental ray marching (ray.cuh); a walk that just started first solves its axes, one per trip
             const bool walking = (P.ph == PH_PRE || P.ph == PH_WALK || P.ph == PH_PEEL);
             if (walking && ray_ph != P.ph) {
                 const bool peel = (P.ph == PH_PEEL);
@@ -635,479 +635,4 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
         if (__all_sync(FULL, P.ph == PH_IDLE)) break;
     }
     C.flush(A.O.stats);
-}
-
-
-__device__ __forceinline__ unsigned long long pack_cf(int c0, int c1, int c2, int f0, int f1) {
-    return (unsigned long long)(unsigned)((c0 + 1) & 0xffff) | ((unsigned long long)(unsigned)(c1 & 0xffff) << 16) |
-           ((unsigned long long)(unsigned)(c2 & 0xffff) << 32) | ((unsigned long long)(unsigned)(f0 & 3) << 48) |
-           ((unsigned long long)(unsigned)(f1 & 0x3fff) << 50);
-}
-__device__ __forceinline__ void unpack_cf(unsigned long long v, int& c0, int& c1, int& c2, int& f0, int& f1) {
-    c0 = (int)(v & 0xffff) - 1; c1 = (int)((v >> 16) & 0xffff); c2 = (int)((v >> 32) & 0xffff);
-    f0 = (int)((v >> 48) & 3); f1 = (int)((v >> 50) & 0x3fff);
-}
-
-// =====================================================================================================
-// Engine 3: regroup.  Every warp owns 64 photons whose state lives in shared memory; the 32 lanes march
-// the photons that are ready to walk, and as soon as a photon needs a heavy event its lane parks it in its
-// slot and picks up another ready photon.  When 32 photons wait (peel deposit + scattering, Lambert
-// reflection, or an empty slot to emit into) the whole warp runs that event code once, fully converged,
-// and the photons become ready again.  No lane idles while others march, no event runs for a fraction of
-// a warp, and nothing leaves the SM: this is the "regroup by next event with ballot / compaction" design.
-// =====================================================================================================
-constexpr int RG_SLOTS = 64;     // photons per warp
-constexpr int RG_STRIDE = 23;    // doubles per slot, odd -> conflict-free when lanes touch distinct slots
-// slot layout (doubles): 0-2 p | 3-5 d | 6-9 S | 10 tau | 11 tau_run | 12 tacc | 13-15 w | 16 hcf | 17 wcf | 18 id |
-//                        19 nd, misc | 20 t_len, t_nsc | 21 t_hash
-
-__device__ __forceinline__ unsigned long long d2u(double v) { return (unsigned long long)__double_as_longlong(v); }
-__device__ __forceinline__ double u2d(unsigned long long v) { return __longlong_as_double((long long)v); }
-__device__ __forceinline__ unsigned pack_misc(const Photon& P) {
-    return (unsigned)P.ph | ((unsigned)P.pk << 4) | ((P.peel_exit ? 1u : 0u) << 6) | ((P.rng.exhausted ? 1u : 0u) << 7) |
-           ((P.at_walker ? 1u : 0u) << 8);
-}
-__device__ __forceinline__ void unpack_misc(unsigned m, Photon& P) {
-    P.ph = (int)(m & 15u); P.pk = (int)((m >> 4) & 3u); P.peel_exit = ((m >> 6) & 1u) != 0u;
-    P.rng.exhausted = ((m >> 7) & 1u) != 0u; P.at_walker = ((m >> 8) & 1u) != 0u;
-}
-
-// hot = what a marching lane keeps in registers
-template <bool TRACE>
-__device__ __forceinline__ void slot_store_hot(double* sl, const Photon& P) {
-    sl[10] = P.tau; sl[11] = P.tau_run; sl[12] = P.tacc; sl[13] = P.wx; sl[14] = P.wy; sl[15] = P.wz;
-    sl[17] = u2d(pack_cf(P.wc0, P.wc1, P.wc2, P.wf0, P.wf1));
-    sl[19] = u2d((unsigned long long)P.rng.nd | ((unsigned long long)pack_misc(P) << 32));
-    if (TRACE) { sl[20] = u2d((unsigned long long)(unsigned)P.t_len | ((unsigned long long)(unsigned)P.t_nsc << 32)); sl[21] = u2d(P.t_hash); }
-}
-template <bool TRACE>
-__device__ __forceinline__ void slot_load_hot(const double* sl, Photon& P) {
-    P.S[0] = sl[6];
-    P.tau = sl[10]; P.tau_run = sl[11]; P.tacc = sl[12]; P.wx = sl[13]; P.wy = sl[14]; P.wz = sl[15];
-    unpack_cf(d2u(sl[17]), P.wc0, P.wc1, P.wc2, P.wf0, P.wf1);
-    const unsigned long long nm = d2u(sl[19]);
-    P.rng.nd = (unsigned)nm; unpack_misc((unsigned)(nm >> 32), P);
-    if (TRACE) { const unsigned long long t = d2u(sl[20]); P.t_len = (int)(unsigned)t; P.t_nsc = (int)(unsigned)(t >> 32); P.t_hash = d2u(sl[21]); }
-}
-// cold = the rest (home position, direction, Stokes vector, random stream)
-template <bool TRACE>
-__device__ __forceinline__ void slot_load_cold(const double* sl, Photon& P, unsigned long long seed, bool with_home) {
-    if (with_home) { P.px = sl[0]; P.py = sl[1]; P.pz = sl[2]; unpack_cf(d2u(sl[16]), P.c0, P.c1, P.c2, P.f0, P.f1); }
-    P.dx = sl[3]; P.dy = sl[4]; P.dz = sl[5];
-    P.S[0] = sl[6]; P.S[1] = sl[7]; P.S[2] = sl[8]; P.S[3] = sl[9];
-    P.rng.id = d2u(sl[18]);
-    if (!TRACE && (P.rng.nd & 3u)) philox_block(P.rng.id, P.rng.nd >> 2, seed, P.rng);
-}
-__device__ __forceinline__ void slot_store_cold(double* sl, const Photon& P) {
-    sl[0] = P.px; sl[1] = P.py; sl[2] = P.pz; sl[3] = P.dx; sl[4] = P.dy; sl[5] = P.dz;
-    sl[6] = P.S[0]; sl[7] = P.S[1]; sl[8] = P.S[2]; sl[9] = P.S[3];
-    sl[16] = u2d(pack_cf(P.c0, P.c1, P.c2, P.f0, P.f1));
-    sl[18] = u2d(P.rng.id);
-}
-
-__device__ __forceinline__ int nth_set_bit64(unsigned long long m, int n) {   // position of the n-th (0-based) set bit
-    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
-    const int cl = __popc(lo);
-    return (n < cl) ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - cl + 1);
-}
-__device__ __forceinline__ unsigned long long warp_or64(bool pred, int bit) {
-    const unsigned long long v = pred ? (1ull << bit) : 0ull;
-    const unsigned lo = __reduce_or_sync(FULL, (unsigned)v), hi = __reduce_or_sync(FULL, (unsigned)(v >> 32));
-    return (unsigned long long)lo | ((unsigned long long)hi << 32);
-}
-
-
-// One heavy event on the photon in slot `sl` (or an emission into it), kept out of line: the march loop then
-// holds no event code and keeps its registers, and the event code sees a clean register file.
-// Returns x: 1 = slot now ready to march, 2 = slot now free, 0 = untouched; y,z,w: packed counter increments.
-template <bool TRACE>
-__device__ __noinline__ uint4 rg_event_fn(const KernelArgs* Ap, const double* sm, double* sl, int is_emit, unsigned long long k) {
-    constexpr bool GEN = true;
-    const KernelArgs& A = *Ap;
-    const Ctx X(sm, A);
-    Counters C; C.zero();
-    Photon E;
-    if (is_emit) ev_emit<TRACE, GEN>(X, E, C, k);
-    else {
-        slot_load_hot<TRACE>(sl, E);
-        slot_load_cold<TRACE>(sl, E, A.L.seed, true);
-        if (E.ph == PH_LAMBERT) ev_lambert<TRACE>(X, E, C);
-        else {
-            ev_peel_done<TRACE, GEN>(X, E, C);
-            if (E.ph == PH_SCAT2) ev_scatter<TRACE>(X, E, C);
-        }
-    }
-    unsigned res;
-    if (E.ph == PH_NEW) res = is_emit ? 0u : 2u;     // a failed emission leaves the slot free as it was
-    else { slot_store_cold(sl, E); slot_store_hot<TRACE>(sl, E); res = 1u; }
-    return make_uint4(res | (C.n_emit << 8) | (C.n_err << 16), C.n_sc | (C.n_peel << 16), C.n_draw, C.n_surf);
-}
-
-template <bool TRACE>
-__global__ void __launch_bounds__(128, 4) regroup_kernel(const __grid_constant__ KernelArgs A) {
-    constexpr bool GEN = true;
-    extern __shared__ double sm[];
-    stage_tables(sm, A.T);
-    const Ctx X(sm, A);
-    const LaunchArgs& L = A.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* slots = sm + X.lay.total + (size_t)warp * RG_SLOTS * RG_STRIDE;
-    unsigned long long ready = 0ull, pend = 0ull, freem = ~0ull;   // warp-uniform slot sets
-    bool supply = true;                                            // photons left to emit (warp-uniform)
-    Counters C; C.zero();
-    Photon P;                        // the photon this lane is marching (hot fields; cold ones only transiently)
-    P.ph = PH_NEW; P.at_walker = false; P.rng.exhausted = false; P.rng.nd = 0; P.rng.id = 0;
-    int cur = -1;
-    double n0 = 0, n1 = 0, n2 = 0;   // walker direction
-#if !ARTES_FAITHFUL
-    Ray R;
-    bool need_ray = false;
-    int upd = 0;
-#endif
-
-    for (;;) {
-        const unsigned marching = __ballot_sync(FULL, cur >= 0);
-        const int n_pend = __popcll(pend), n_free = supply ? __popcll(freem) : 0;
-        const int items = n_pend + n_free;
-        if (marching == 0u && ready == 0ull && items == 0) break;
-
-        // ------------------------------------------------------------------ event round (converged)
-        if (items >= 32 || (marching == 0u && ready == 0ull)) {
-            __syncwarp();
-            int my = -1;
-            bool is_emit = false;
-            if (lane < n_pend) my = nth_set_bit64(pend, lane);
-            else if (lane - n_pend < n_free) { my = nth_set_bit64(freem, lane - n_pend); is_emit = true; }
-            unsigned long long k = 0;
-            {   // photon ids for the emitting lanes, warp-aggregated
-                const unsigned em = __ballot_sync(FULL, is_emit);
-                unsigned long long k0 = 0;
-                if (em) {
-                    const int leader = __ffs(em) - 1;
-                    if (lane == leader) k0 = atomicAdd(A.O.counter, (unsigned long long)__popc(em));
-                    k0 = __shfl_sync(FULL, k0, leader);
-                }
-                k = k0 + (unsigned long long)__popc(em & ((1u << lane) - 1u));
-                const bool dry = is_emit && k >= L.n_photons;
-                if (dry) { is_emit = false; my = -1; }
-                if (__any_sync(FULL, dry)) supply = false;
-            }
-            bool now_ready = false, now_free = false;
-            const bool was_pend = (my >= 0) && !is_emit;
-            if (my >= 0) {
-                const uint4 r = rg_event_fn<TRACE>(&A, sm, slots + my * RG_STRIDE, is_emit ? 1 : 0, k);
-                now_ready = (r.x & 255u) == 1u; now_free = (r.x & 255u) == 2u;
-                C.n_emit += (r.x >> 8) & 255u; C.n_err += r.x >> 16; C.n_sc += r.y & 0xffffu; C.n_peel += r.y >> 16;
-                C.n_draw += r.z; C.n_surf += r.w;
-            }
-            const int bit = my < 0 ? 0 : my;
-            pend &= ~warp_or64(was_pend, bit);
-            freem = (freem & ~warp_or64(is_emit && now_ready, bit)) | warp_or64(now_free, bit);
-            ready |= warp_or64(now_ready, bit);
-            __syncwarp();
-            continue;
-        }
-
-        // ------------------------------------------------------------------ empty lanes pick up ready photons
-        {
-            const unsigned empty = __ballot_sync(FULL, cur < 0);
-            if (empty && ready) {
-                const int rank = __popc(empty & ((1u << lane) - 1u));
-                bool took = false;
-                if (cur < 0 && rank < __popcll(ready)) {
-                    cur = nth_set_bit64(ready, rank);
-                    const double* sl = slots + cur * RG_STRIDE;
-                    slot_load_hot<TRACE>(sl, P);
-                    if (P.ph == PH_PEEL) { n0 = L.det[0]; n1 = L.det[1]; n2 = L.det[2]; }
-                    else { n0 = sl[3]; n1 = sl[4]; n2 = sl[5]; }
-                    if (TRACE) P.rng.id = d2u(sl[18]);
-#if !ARTES_FAITHFUL
-                    need_ray = true;
-#endif
-                    took = true;
-                }
-                ready &= ~warp_or64(took, took ? cur : 0);
-            }
-        }
-
-        // ------------------------------------------------------------------ one crossing for every marching lane
-#if !ARTES_FAITHFUL
-        // fast mode: a fresh ray first gets its constants, then every lane with a pending axis solves ONE
-        // axis per trip (same converged solver for all); a lane steps once nothing is pending.
-        if (cur >= 0 && need_ray) { ray_setup(X, P, R, n0, n1, n2); upd = ray_axes(A.T); need_ray = false; }
-        if (cur >= 0 && upd) ray_update(X, R, upd, P.wc0, P.wc1, P.wc2, n0, n1, n2);
-        const bool step = cur >= 0 && upd == 0;
-#else
-        const bool step = cur >= 0;
-#endif
-        bool to_pend = false, to_free = false;
-        if (step) {
-            double* sl = slots + cur * RG_STRIDE;
-            CellFace o;
-#if ARTES_FAITHFUL
-            cell_face(X.sm, X.lay, A.T, P.wx, P.wy, P.wz, n0, n1, n2, P.wf0, P.wf1, P.wc0, P.wc1, P.wc2, o);
-            apply_crossing<TRACE, GEN>(X, P, C, o, n0, n1, n2);
-#else
-            int axis;
-            ray_next(A.T, P, R, o, axis);
-            const int ph0 = P.ph;
-            apply_crossing<TRACE, GEN>(X, P, C, o, n0, n1, n2);
-            if (P.ph == ph0) { R.t = (axis == 0) ? R.tr : ((axis == 1) ? R.tt : R.tp); upd = 1 << axis; }
-#endif
-            if (P.ph == PH_PREDONE || P.ph == PH_SCAT || P.ph == PH_SURFHIT || P.ph == PH_RETIRE) {
-                // cheap follow-ups that need the random stream / Stokes vector: fetch them from the slot
-                slot_load_cold<TRACE>(sl, P, L.seed, P.ph != PH_SCAT);
-                cheap_handlers<TRACE, GEN>(X, P, C);
-                if (P.ph != PH_NEW) {
-                    slot_store_cold(sl, P);
-                    if (P.ph == PH_PEEL) { n0 = L.det[0]; n1 = L.det[1]; n2 = L.det[2]; }
-                    else { n0 = P.dx; n1 = P.dy; n2 = P.dz; }
-#if !ARTES_FAITHFUL
-                    need_ray = true;
-#endif
-                }
-            }
-            if (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT) { slot_store_hot<TRACE>(sl, P); to_pend = true; }
-            else if (P.ph == PH_NEW) to_free = true;
-        }
-        if (__any_sync(FULL, to_pend || to_free)) {
-            const int bit = cur < 0 ? 0 : cur;
-            pend |= warp_or64(to_pend, bit);
-            freem |= warp_or64(to_free, bit);
-            if (to_pend || to_free) cur = -1;
-        }
-    }
-    C.flush(A.O.stats);
-}
-
-// =====================================================================================================
-// Engine 2: wavefront.  Photon pool in HBM (SoA), queues of slot indices, three kernels per pass.
-// =====================================================================================================
-// what the march kernel needs of a photon
-template <bool TRACE>
-__device__ __forceinline__ void pool_load_all(const PoolArgs& Q, int s, Photon& P) {
-    const size_t M = Q.capacity;
-    const double* d = Q.d + s;
-    P.px = d[0 * M]; P.py = d[1 * M]; P.pz = d[2 * M]; P.dx = d[3 * M]; P.dy = d[4 * M]; P.dz = d[5 * M];
-    P.S[0] = d[6 * M]; P.S[1] = d[7 * M]; P.S[2] = d[8 * M]; P.S[3] = d[9 * M];
-    P.tau = d[10 * M]; P.tau_run = d[11 * M]; P.tacc = d[12 * M]; P.wx = d[13 * M]; P.wy = d[14 * M]; P.wz = d[15 * M];
-    unpack_cf(Q.hcf[s], P.c0, P.c1, P.c2, P.f0, P.f1);
-    unpack_cf(Q.wcf[s], P.wc0, P.wc1, P.wc2, P.wf0, P.wf1);
-    P.rng.id = Q.id[s];
-    const unsigned m = Q.misc[s];
-    P.ph = (int)(m & 15u); P.pk = (int)((m >> 4) & 3u); P.peel_exit = ((m >> 6) & 1u) != 0u; P.rng.exhausted = ((m >> 7) & 1u) != 0u;
-    P.at_walker = false;
-    P.rng.nd = Q.nd[s];
-    if (!TRACE && (P.rng.nd & 3u)) philox_block(P.rng.id, P.rng.nd >> 2, Q.seed, P.rng);   // rebuild the buffered block
-    if (TRACE) { P.t_len = Q.t_len[s]; P.t_nsc = Q.t_nsc[s]; P.t_hash = Q.t_hash[s]; }
-}
-
-template <bool TRACE>
-__device__ __forceinline__ void pool_store_all(const PoolArgs& Q, int s, const Photon& P) {
-    const size_t M = Q.capacity;
-    double* d = Q.d + s;
-    d[0 * M] = P.px; d[1 * M] = P.py; d[2 * M] = P.pz; d[3 * M] = P.dx; d[4 * M] = P.dy; d[5 * M] = P.dz;
-    d[6 * M] = P.S[0]; d[7 * M] = P.S[1]; d[8 * M] = P.S[2]; d[9 * M] = P.S[3];
-    d[10 * M] = P.tau; d[11 * M] = P.tau_run; d[12 * M] = P.tacc; d[13 * M] = P.wx; d[14 * M] = P.wy; d[15 * M] = P.wz;
-    Q.hcf[s] = pack_cf(P.c0, P.c1, P.c2, P.f0, P.f1);
-    Q.wcf[s] = pack_cf(P.wc0, P.wc1, P.wc2, P.wf0, P.wf1);
-    Q.id[s] = P.rng.id;
-    Q.nd[s] = P.rng.nd;
-    Q.misc[s] = (unsigned)P.ph | ((unsigned)P.pk << 4) | ((P.peel_exit ? 1u : 0u) << 6) | ((P.rng.exhausted ? 1u : 0u) << 7);
-    if (TRACE) { Q.t_len[s] = P.t_len; Q.t_nsc[s] = P.t_nsc; Q.t_hash[s] = P.t_hash; }
-}
-
-// warp-aggregated append of `slot` to queue q (counter *n) for the lanes with `pred`
-// (must be reached by all 32 lanes of the warp)
-__device__ __forceinline__ void queue_push(int* q, unsigned* n, bool pred, int slot) {
-    const unsigned m = __ballot_sync(FULL, pred);
-    if (!m) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(n, (unsigned)__popc(m));
-    base = __shfl_sync(FULL, base, leader);
-    if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = slot;
-}
-
-// queue control block in device memory
-//   ctl[0] n_march[0]   ctl[1] n_march[1]   ctl[2] n_event   ctl[3] n_free   ctl[4] march cursor
-//   ctl[5] cur (which march queue is being consumed)         ctl[6] photons in flight after the pass
-enum { Q_NMARCH0 = 0, Q_NMARCH1 = 1, Q_NEVENT = 2, Q_NFREE = 3, Q_CURSOR = 4, Q_CUR = 5, Q_INFLIGHT = 6 };
-
-// ---- emit: every free slot takes the next photon id, if any is left -----------------------------------
-template <bool TRACE>
-__global__ void __launch_bounds__(128) wf_emit_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ PoolArgs Q) {
-    constexpr bool GEN = true;
-    extern __shared__ double sm[];
-    stage_tables(sm, A.T);
-    const Ctx X(sm, A);
-    Counters C; C.zero();
-    const unsigned n_free = Q.ctl[Q_NFREE];
-    const unsigned nxt = Q.ctl[Q_CUR] ^ 1u;
-    int* q_out = Q.q_march + (size_t)nxt * Q.capacity;
-    const int lane = threadIdx.x & 31;
-    for (unsigned base_i = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base_i < n_free; base_i += gridDim.x * blockDim.x) {
-        const unsigned i = base_i + lane;
-        const bool have = i < n_free;
-        // photon ids are handed out warp-aggregated
-        const unsigned m = __ballot_sync(FULL, have);
-        unsigned long long k0 = 0;
-        if (lane == 0) k0 = atomicAdd(A.O.counter, (unsigned long long)__popc(m));
-        k0 = __shfl_sync(FULL, k0, 0);
-        const unsigned long long k = k0 + __popc(m & ((1u << lane) - 1u));
-        bool go = false;
-        int slot = 0;
-        if (have && k < A.L.n_photons) {
-            slot = Q.q_free[i];
-            Photon P;
-            ev_emit<TRACE, GEN>(X, P, C, k);
-            if (P.ph != PH_NEW) { pool_store_all<TRACE>(Q, slot, P); go = true; }
-            // an emission error retires the photon at once: the slot is simply not re-queued this pass
-        }
-        queue_push(q_out, Q.ctl + nxt, go, slot);
-    }
-    C.flush(A.O.stats);
-}
-
-// ---- march: persistent lanes pull photons and walk them to their next heavy event -----------------------
-template <bool TRACE>
-__global__ void __launch_bounds__(128, 4) wf_march_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ PoolArgs Q) {
-    constexpr bool GEN = true;
-    extern __shared__ double sm[];
-    stage_tables(sm, A.T);
-    const Ctx X(sm, A);
-    Counters C; C.zero();
-    const unsigned cur = Q.ctl[Q_CUR];
-    const unsigned n_in = Q.ctl[cur];
-    const int* q_in = Q.q_march + (size_t)cur * Q.capacity;
-    const int lane = threadIdx.x & 31;
-    Photon P;
-    P.ph = PH_NEW;
-    int slot = -1;
-    bool drained = false;
-#if !ARTES_FAITHFUL
-    Ray R;
-    bool need_ray = true;
-    int upd = 0;
-    double rn0 = 0, rn1 = 0, rn2 = 0;
-#endif
-    for (;;) {
-        // refill free lanes from the march queue
-        const unsigned need = __ballot_sync(FULL, slot < 0 && !drained);
-        if (need) {
-            const int leader = __ffs(need) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(Q.ctl + Q_CURSOR, (unsigned)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            if (slot < 0 && !drained) {
-                const unsigned i = base + __popc(need & ((1u << lane) - 1u));
-                if (i < n_in) {
-                    slot = q_in[i]; pool_load_all<TRACE>(Q, slot, P);
-#if !ARTES_FAITHFUL
-                    need_ray = true;
-#endif
-                }
-                else drained = true;
-            }
-        }
-        if (__all_sync(FULL, slot < 0)) break;
-        bool to_event = false, to_free = false;
-#if ARTES_FAITHFUL
-        if (slot >= 0) {
-            ev_cross<TRACE, GEN>(X, P, C);
-            cheap_handlers<TRACE, GEN>(X, P, C);
-            to_event = (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT);
-            to_free = (P.ph == PH_NEW);
-            if (to_event) pool_store_all<TRACE>(Q, slot, P);
-        }
-#else
-        // fast mode: incremental ray marching (ray.cuh)
-        if (slot >= 0 && need_ray) {
-            const bool peel = (P.ph == PH_PEEL);
-            rn0 = peel ? A.L.det[0] : P.dx; rn1 = peel ? A.L.det[1] : P.dy; rn2 = peel ? A.L.det[2] : P.dz;
-            ray_setup(X, P, R, rn0, rn1, rn2); upd = ray_axes(A.T); need_ray = false;
-        }
-        if (slot >= 0 && upd) ray_update(X, R, upd, P.wc0, P.wc1, P.wc2, rn0, rn1, rn2);
-        if (slot >= 0 && upd == 0) {
-            CellFace o;
-            int axis;
-            ray_next(A.T, P, R, o, axis);
-            const int ph0 = P.ph;
-            apply_crossing<TRACE, GEN>(X, P, C, o, rn0, rn1, rn2);
-            cheap_handlers<TRACE, GEN>(X, P, C);
-            if (P.ph == ph0) { R.t = (axis == 0) ? R.tr : ((axis == 1) ? R.tt : R.tp); upd = 1 << axis; }
-            else need_ray = true;
-            to_event = (P.ph == PH_PEELDONE || P.ph == PH_LAMBERT);
-            to_free = (P.ph == PH_NEW);
-            if (to_event) pool_store_all<TRACE>(Q, slot, P);
-        }
-#endif
-        if (__any_sync(FULL, to_event || to_free)) {
-            queue_push(Q.q_event, Q.ctl + Q_NEVENT, to_event, slot);
-            queue_push(Q.q_free, Q.ctl + Q_NFREE, to_free, slot);
-            if (to_event || to_free) slot = -1;
-        }
-    }
-    C.flush(A.O.stats);
-}
-
-// ---- event: deposit + scattering (or the continuation of a surface / thermal peel), fully converged ------
-template <bool TRACE>
-__global__ void __launch_bounds__(128) wf_event_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ PoolArgs Q) {
-    constexpr bool GEN = true;
-    extern __shared__ double sm[];
-    stage_tables(sm, A.T);
-    const Ctx X(sm, A);
-    Counters C; C.zero();
-    const unsigned n_ev = Q.ctl[Q_NEVENT];
-    const unsigned nxt = Q.ctl[Q_CUR] ^ 1u;
-    int* q_out = Q.q_march + (size_t)nxt * Q.capacity;
-    const int lane = threadIdx.x & 31;
-    for (unsigned base_i = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base_i < n_ev; base_i += gridDim.x * blockDim.x) {
-        const unsigned i = base_i + lane;
-        bool go = false, freed = false;
-        int slot = 0;
-        if (i < n_ev) {
-            slot = Q.q_event[i];
-            Photon P;
-            pool_load_all<TRACE>(Q, slot, P);
-            if (P.ph == PH_LAMBERT) ev_lambert<TRACE>(X, P, C);
-            else {
-                ev_peel_done<TRACE, GEN>(X, P, C);
-                if (P.ph == PH_SCAT2) ev_scatter<TRACE>(X, P, C);
-            }
-            if (P.ph == PH_NEW) freed = true;
-            else { pool_store_all<TRACE>(Q, slot, P); go = true; }
-        }
-        queue_push(q_out, Q.ctl + nxt, go, slot);
-        queue_push(Q.q_free, Q.ctl + Q_NFREE, freed, slot);
-    }
-    C.flush(A.O.stats);
-}
-
-// ---- queue bookkeeping between the stages (one thread) ---------------------------------------------------
-// stage 0: before event+emit of a pass   stage 1: after them (flip queues, publish the in-flight count)
-__global__ void wf_ctl_kernel(PoolArgs Q, int stage) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (stage == 0) {
-        Q.ctl[Q.ctl[Q_CUR] ^ 1u] = 0u;   // the queue the event / emit kernels append to
-        Q.ctl[Q_CURSOR] = 0u;
-    } else {
-        const unsigned nxt = Q.ctl[Q_CUR] ^ 1u;
-        Q.ctl[Q_CUR] = nxt;
-        Q.ctl[Q_NEVENT] = 0u;
-        Q.ctl[Q_NFREE] = 0u;
-        Q.ctl[Q_INFLIGHT] = Q.ctl[nxt];
-        *Q.host_inflight = Q.ctl[nxt];
-    }
-}
-
-__global__ void wf_init_kernel(PoolArgs Q) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Q.capacity) Q.q_free[i] = (int)i;
-    if (i == 0) {
-        Q.ctl[Q_NMARCH0] = 0u; Q.ctl[Q_NMARCH1] = 0u; Q.ctl[Q_NEVENT] = 0u; Q.ctl[Q_NFREE] = (unsigned)Q.capacity;
-        Q.ctl[Q_CURSOR] = 0u; Q.ctl[Q_CUR] = 0u; Q.ctl[Q_INFLIGHT] = 0u;
-    }
 }

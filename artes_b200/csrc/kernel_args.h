@@ -67,24 +67,6 @@ struct TraceArgs {
     double* fstate;                  // [n][8] or null
 };
 
-// Photon pool + queues of the wavefront engine (HBM, SoA over `capacity` slots).
-struct PoolArgs {
-    size_t capacity;
-    double* d;                        // [16][capacity]: px py pz dx dy dz S0..S3 tau tau_run tacc wx wy wz
-    unsigned long long* hcf;          // packed photon cell + face
-    unsigned long long* wcf;          // packed walker cell + face
-    unsigned long long* id;           // global photon id (Philox counter)
-    unsigned* nd;                     // draws consumed
-    unsigned* misc;                   // phase | peel kind << 4 | peel_exit << 6 | stream exhausted << 7
-    int* t_len; int* t_nsc; unsigned long long* t_hash;   // trace recorder (test hook)
-    int* q_march;                     // [2][capacity]
-    int* q_event;                     // [capacity]
-    int* q_free;                      // [capacity]
-    unsigned* ctl;                    // queue control block, see engine.cuh
-    unsigned* host_inflight;          // mapped pinned word: photons in flight after the last pass
-    unsigned long long seed;
-};
-
 struct KernelArgs {
     DevTables T;
     LaunchArgs L;
@@ -94,6 +76,5 @@ struct KernelArgs {
 
 // Host-side launchers, one pair per arithmetic mode (separate translation units: the faithful one is
 // compiled with -fmad=false).
-struct WfGeom { unsigned g_march, g_aux; size_t smem; };
 
 }  // namespace artes

@@ -22,9 +22,7 @@
 #ifndef ARTES_FAITHFUL
 #error "define ARTES_FAITHFUL to 0 or 1"
 #endif
-#ifndef ARTES_PERSISTENT_RAY
-#define ARTES_PERSISTENT_RAY 1   // fast mode: the persistent engine marches rays incrementally (ray.cuh)
-#endif
+
 
 namespace artes {
 namespace ARTES_NS {
