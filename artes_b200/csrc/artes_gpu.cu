@@ -33,6 +33,8 @@ size_t smem_bytes(int nr, int nt, int np);
 cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
+bool engine2_supports(const KernelArgs& a);
+cudaError_t launch_transport2(const KernelArgs& a, int sm_count, cudaStream_t stream);
 }  // namespace fast
 cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
 }  // namespace artes
@@ -159,6 +161,9 @@ void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
     // warp regrouping thresholds; tunable for experiments through the environment
     static const int defer_events = env_int("ARTES_DEFER_EVENTS", 12), defer_refill = env_int("ARTES_DEFER_REFILL", 4);
     a.defer_events = defer_events; a.defer_refill = defer_refill;
+    static const int e2_trips = env_int("ARTES_E2_TRIPS", 2);
+    static const int e2_cfg = env_int("ARTES_E2_CFG", 32) & 31;      // block shape, see launch_transport2
+    a.e2_trips = e2_trips; a.e2_pad = e2_cfg;
     a.fstop = L.fstop; a.photon_minimum = L.photon_minimum; a.photon_bias = L.photon_bias;
     a.surface_albedo = L.surface_albedo; a.theta_star = L.theta_star; a.phi_star = L.phi_star;
     a.x_max = L.x_max; a.y_max = L.y_max;
@@ -459,8 +464,12 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
         CU(cudaEventRecord(d.ev[0], d.stream));
         d.launches = 0;
         if (a.L.n_photons > 0) {
-            cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, false, d.sm_count, d.stream)
-                                                             : fast::launch_transport(a, false, d.sm_count, d.stream);
+            // fast mode: the ray/event engine wherever it applies (ARTES_ENGINE=1 forces the persistent-lane engine)
+            static const int engine = env_int("ARTES_ENGINE", 2);
+            cudaError_t e;
+            if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, false, d.sm_count, d.stream);
+            else if (engine == 2 && fast::engine2_supports(a)) e = fast::launch_transport2(a, d.sm_count, d.stream);
+            else e = fast::launch_transport(a, false, d.sm_count, d.stream);
             if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
             d.launches = 1;
         }

@@ -1,0 +1,647 @@
+// engine2.cuh -- the fast-mode production engine: ray marchers + block-level event batches.
+// Included from transport.cuh (inside namespace artes::ARTES_NS), fast translation unit only.
+//
+// Why a second engine.  ncu on the persistent-lane engine (engine.cuh) at C4: 13 of 32 lanes active on
+// average, 35 % issue utilisation, `no_instruction` (i-cache) the top stall, 12 900 thread instructions
+// per scattering cycle (profiles/r01_g_*).  The lanes diverge because every lane runs its own photon's
+// whole life -- emission, first optical depth, survival, peel-off weight, CDF sampling, deposit -- inline
+// between cell crossings.  Here the photon's life is cut into RAYS and EVENTS:
+//
+//   ray     a straight segment through the r-theta-phi grid (tau pre-pass :633-656, transport walk
+//           :691-778 / :850-941, peel-off walk :4739-4761).  A lane ("marcher") owns one ray at a time and
+//           does nothing but step it radially; its whole state is ~24 registers.
+//   event   everything else.  A photon lives in a shared-memory SLOT.  When its ray ends the marcher
+//           writes (t, tau) back to the slot and pushes the slot on the list of the event it needs;
+//           after every few trips the block synchronises and ALL threads of the block work through
+//           the lists, 32 same-type events per warp, fully converged.  Each event ends by setting up
+//           the slot's next ray and pushing the slot on the ready list, from which free marchers claim.
+//
+//   EMIT  emit_photon :1008-1115 (star)                     -> pre-pass ray
+//   PRE   first optical depth :660-685                      -> transport ray
+//   H     interaction: survival :791-813, peel-off weight + pixel (peel_photon :4763-4951 without the
+//         e^-tau factor), scatter_photon + polarization_rotation :819-823, next tau :845   -> peel ray
+//   DEP   e^-tau, detector deposit :4955-4972               -> transport ray
+//   RES   a theta or phi face was crossed: move the cell index, re-solve that axis        -> same ray
+//
+// Geometry.  Along X(t) = X0 + t n every bounding surface is a fixed quadric in t (ray.cuh).  The three
+// axes are independent crossing sequences that only need merging by t:
+//   r      |X|^2 has one minimum: inward the next sphere is the inner one (if the ray reaches it), after
+//          the turning point the outer one: t = -hb/qa -+ sqrt(D0 + r_k^2/qa): one sqrt, no division
+//   theta  cos(theta) has one extremum (g(t) = g0 + g1 t is the sign of its derivative): try the face in
+//          the direction of motion, then the other one
+//   phi    the azimuth is monotonic (sign of the angular momentum L_z): one linear solve
+// Radial crossings dominate by far (10 km layers against 10^4 km wide theta/phi cells), so only the
+// radial re-solve is in the marcher; theta/phi crossings are RES events.
+//
+// The draw order of the random stream and every physical formula are those of the oracle, so for the
+// same Philox stream the trajectories agree with the oracle's to rounding.
+//
+// Scope: star source, black surface, no flow counters, no trace (the configurations the benchmark and
+// the reference's default artes.in use).  Anything else runs on the persistent-lane engine.
+
+namespace e2 {
+
+// A block has NT marcher lanes and NP >= NT photon slots: with more photons than lanes a lane whose ray
+// ended finds another ready ray at once, and a round collects enough events to keep every warp busy in
+// the event phase.  RC = ring capacity of the lists (power of two >= NP).
+
+enum : int { K_PRE = 0, K_WALK = 1, K_PEEL = 2, K_DEAD = 3 };
+enum : int { L_EMIT = 0, L_PRE, L_H, L_DEP, L_RES, L_RDY, N_LISTS };
+enum : int { O_NONE = 0, O_LIMIT, O_EXIT, O_SURF, O_REST, O_RESP, O_ERR, O_DEAD };
+// info word: bits 0-1 kind, 2 radial inward, 3 next theta face is the upper one, 4 phi increasing, 8-11 outcome
+enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16 };
+
+// slot fields (structure of arrays, [field][NP])
+enum : int { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_S0, F_S1, F_S2, F_S3, F_TAU, F_W0, F_W1, F_W2, F_W3,
+             F_T, F_ACC, F_TR, F_TT, F_TP, F_HBN, F_D0, F_IQ, F_LIM, NF_D };
+enum : int { I_CELL = 0, I_HCELL, I_INFO, I_PIX, I_ND, I_IDLO, I_IDHI, NF_I };
+
+__host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c < np_slots) c <<= 1; return c; }
+
+struct Lay {
+    int o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_sd, n_tab;   // offsets in doubles
+    size_t bytes;
+    __host__ __device__ Lay(int nr, int nt, int np, int NP) {
+        o_tf = nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
+        o_tp = o_pf + np; o_sd = o_tp + (nt + 2) / 2 + 1; n_tab = o_sd;
+        bytes = (size_t)(o_sd + NF_D * NP) * 8 + (size_t)NF_I * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
+    }
+};
+
+template <int NP>
+struct ShT {                     // pointers into the block's shared memory
+    const double* r; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
+    const int* tplane;
+    double* sd; int* si; short* q; int* head; int* tail; int* misc;   // misc[0] = slots retired for good
+    static constexpr int RC = ring_cap(NP);
+    __device__ __forceinline__ double& D(int f, int s) const { return sd[f * NP + s]; }
+    __device__ __forceinline__ int& I(int f, int s) const { return si[f * NP + s]; }
+    __device__ __forceinline__ short& Q(int l, int pos) const { return q[l * RC + (pos & (RC - 1))]; }
+};
+
+__device__ __forceinline__ int pack_cell(int c0, int c1, int c2) { return c0 | (c1 << 10) | (c2 << 20); }
+
+// Philox draws nd .. nd+4 of photon `id` (at most two counter blocks)
+struct Draws {
+    uint4 a, b;
+    unsigned off;
+    __device__ __forceinline__ Draws(unsigned long long id, unsigned nd, unsigned long long seed, int count) {
+        off = nd & 3u;
+        a = philox4(id, nd >> 2, seed);
+        b = a;
+        if (off + (unsigned)count > 4u) b = philox4(id, (nd >> 2) + 1u, seed);
+    }
+    __device__ __forceinline__ double get(int i) const {
+        const unsigned j = off + (unsigned)i, w = j & 3u;
+        const unsigned x = (j < 4u) ? ((w == 0u) ? a.x : (w == 1u) ? a.y : (w == 2u) ? a.z : a.w)
+                                    : ((w == 0u) ? b.x : (w == 1u) ? b.y : (w == 2u) ? b.z : b.w);
+        return ((double)x + 0.5) * (1.0 / 4294967296.0);
+    }
+};
+
+// quadric constants of a ray, event side
+struct RayK { double A1, A2, B1, B2, C1, C2, g0, g1, Xx, Xy, Nx, Ny, z0, n2; };
+
+__device__ __forceinline__ void ray_consts(const DevTables& T, double x, double y, double z, double n0, double n1, double n2,
+                                           RayK& K, double& hbn, double& D0, double& iq) {
+    const double a = 1.0 / T.ox, b = 1.0 / T.oy, c = 1.0 / T.oz;
+    K.A1 = a * a * n0 * n0 + b * b * n1 * n1; K.A2 = c * c * n2 * n2;
+    K.B1 = a * a * x * n0 + b * b * y * n1;   K.B2 = c * c * z * n2;
+    K.C1 = a * a * x * x + b * b * y * y;     K.C2 = c * c * z * z;
+    const double qa = K.A1 + K.A2, hb = K.B1 + K.B2, Cs = K.C1 + K.C2;
+    iq = 1.0 / qa; hbn = -hb * iq; D0 = fma(hbn, hbn, -(Cs * iq));
+    K.g0 = n2 * Cs - z * hb; K.g1 = n2 * hb - z * qa;      // sign of d(cos theta)/dt = sign(g0 + g1 t)
+    K.Xx = a * x; K.Xy = b * y; K.Nx = a * n0; K.Ny = b * n1; K.z0 = z; K.n2 = n2;
+}
+
+// first radial crossing of a fresh ray in cell c0 (sface = radial face the ray starts on, or -1)
+template <class Sh>
+__device__ __forceinline__ double radial_first(const Sh& X, int c0, int sface, double hbn, double D0, double iq, int& inward) {
+    inward = hbn > 0.0;
+    if (inward) {
+        const double r = X.r[c0], disc = fma(r * r, iq, D0);
+        if (disc >= 0.0) { const double t = hbn - sqrt(disc); if (t > 1.e-15) return t; }
+        inward = 0;
+    }
+    const double r = X.r[c0 + 1], disc = fma(r * r, iq, D0);
+    if (disc >= 0.0) {
+        const double t = hbn + sqrt(disc);
+        if (t > ((sface == c0 + 1) ? 1.e-3 : 1.e-15)) return t;     // same-face threshold :2944
+    }
+    return RAY_NONE;
+}
+
+template <class Sh>
+__device__ __forceinline__ double cone_root(const Sh& X, int k, double t, const RayK& K) {
+    const int tp = X.tplane[k];
+    if (tp != 1) {   // equatorial plane :3068 / :3118
+        if (tp != 2 || K.n2 == 0.0) return RAY_NONE;
+        const double r = -K.z0 / K.n2;
+        return (r > t) ? r : RAY_NONE;
+    }
+    const double tn = X.ttan[k], T2 = tn * tn, tf = X.tf[k];
+    const int hs = (tf < PI / 2.0) ? 1 : ((tf > PI / 2.0) ? -1 : 0);
+    return quadric_next(K.A1 - K.A2 * T2, K.B1 - K.B2 * T2, K.C1 - K.C2 * T2, hs, t, K.z0, K.n2);
+}
+
+// next polar crossing after parameter t from cell c1: face in the direction of motion first, then the other
+template <class Sh>
+__device__ __forceinline__ double theta_next(const Sh& X, int nt, int c1, double t, const RayK& K, int& upper) {
+    bool down = (K.g0 + K.g1 * t) > 0.0;     // cos(theta) increasing: towards the lower face index
+    upper = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int k = down ? c1 : c1 + 1;
+        if (k != 0 && k != nt) {
+            const double tk = cone_root(X, k, t, K);
+            if (tk < RAY_NONE) { upper = down ? 0 : 1; return tk; }
+        }
+        down = !down;
+    }
+    return RAY_NONE;
+}
+
+template <class Sh>
+__device__ __forceinline__ double phi_next(const Sh& X, int np, int c2, double t, const RayK& K, int& up) {
+    up = (K.Xx * K.Ny - K.Xy * K.Nx) > 0.0;
+    if (np <= 1) return RAY_NONE;
+    const int k = up ? ((c2 + 1 == np) ? 0 : c2 + 1) : c2;
+    const double ps = X.ps[k], pc = X.pc[k];
+    const double den = K.Ny * pc - K.Nx * ps;
+    if (den == 0.0) return RAY_NONE;
+    const double r = (K.Xx * ps - K.Xy * pc) / den;
+    return (r > t) ? r : RAY_NONE;
+}
+
+// set up the next ray of slot s: origin (x,y,z) in cell (c0,c1,c2), direction n
+template <class Sh>
+__device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s, double x, double y, double z,
+                                          double n0, double n1, double n2, int c0, int c1, int c2, int sface, int kind, double lim) {
+    RayK K;
+    double hbn, D0, iq;
+    ray_consts(T, x, y, z, n0, n1, n2, K, hbn, D0, iq);
+    int inward, upper = 0, up = 0;
+    const double tr = radial_first(X, c0, sface, hbn, D0, iq, inward);
+    const double tt = (T.nt > 1) ? theta_next(X, T.nt, c1, 0.0, K, upper) : RAY_NONE;
+    const double tp = phi_next(X, T.np, c2, 0.0, K, up);
+    X.D(F_T, s) = 0.0; X.D(F_ACC, s) = 0.0; X.D(F_TR, s) = tr; X.D(F_TT, s) = tt; X.D(F_TP, s) = tp;
+    X.D(F_HBN, s) = hbn; X.D(F_D0, s) = D0; X.D(F_IQ, s) = iq; X.D(F_LIM, s) = lim;
+    X.I(I_CELL, s) = pack_cell(c0, c1, c2);
+    X.I(I_INFO, s) = kind | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
+}
+
+struct Cnt {
+    unsigned long long n_cf;
+    unsigned n_emit, n_sc, n_peel, n_surf, n_err, n_draw;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// events (called warp-converged: every lane of the warp handles one slot of the same list; !valid lanes idle)
+// ---------------------------------------------------------------------------------------------------
+
+// EMIT: star emission (emit_photon :1008-1115 + initial_cell).  Returns true if a ray was set up.
+template <class Sh>
+__device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
+    const int lane = threadIdx.x & 31;
+    const unsigned vm = __ballot_sync(FULL, valid);
+    unsigned long long base = 0;
+    const int leader = __ffs(vm) - 1;
+    if (lane == leader) base = atomicAdd(A.O.counter, (unsigned long long)__popc(vm));
+    base = __shfl_sync(FULL, base, leader < 0 ? 0 : leader);
+    if (!valid) return false;
+    C.n_draw += (unsigned)X.I(I_ND, s);          // draws of the photon that lived in this slot before
+    X.I(I_ND, s) = 0;
+    const unsigned long long k = base + (unsigned long long)__popc(vm & ((1u << lane) - 1u));
+    if (k >= L.n_photons) { atomicAdd(X.misc, 1); return false; }
+    ++C.n_emit;
+    const unsigned long long id = L.id_base + k;
+    X.I(I_IDLO, s) = (int)(unsigned)id; X.I(I_IDHI, s) = (int)(unsigned)(id >> 32);
+    unsigned nd = 0;
+    double xi, r_disk;
+    if (L.limb_emission) {
+        for (;;) { Draws d(id, nd, L.seed, 1); xi = d.get(0); ++nd; r_disk = sqrt(xi); if (r_disk > 0.9) break; }
+    } else { Draws d(id, nd, L.seed, 1); xi = d.get(0); ++nd; r_disk = sqrt(xi); }
+    { Draws d(id, nd, L.seed, 1); xi = d.get(0); ++nd; }
+    const double phi_disk = 2.0 * PI * xi;
+    const double R = X.r[T.nr];
+    double sphi, cphi;
+    sincos(phi_disk, &sphi, &cphi);
+    const double d1 = R * r_disk * sphi, d2 = R * r_disk * cphi;
+    double dx = -1.0, dy = 0.0, dz = 0.0;
+    double px = sqrt(R * R - d1 * d1 - d2 * d2), py = d1, pz = d2;
+    if (L.stellar_direction) {  // :1080-1111
+        const double tx = px * L.rot_y_cos + pz * L.rot_y_sin, ty = py, tz = px * (-L.rot_y_sin) + pz * L.rot_y_cos;
+        px = tx * L.rot_z_cos + ty * (-L.rot_z_sin); py = tx * L.rot_z_sin + ty * L.rot_z_cos; pz = tz;
+        dx = L.star_dir[0]; dy = L.star_dir[1]; dz = L.star_dir[2];
+    }
+    // initial_cell :2605-2669
+    int c0 = T.nr - 1, c1 = 0, c2 = 0;
+    {
+        const double r = sqrt(px * px + py * py + pz * pz);
+        const double theta = acos(pz / r);
+        double phi = atan2(py, px);
+        if (phi < 0.0) phi = phi + 2.0 * PI;
+        for (int j = 0; j < T.nt; ++j) if (theta > X.tf[j] && theta < X.tf[j + 1]) { c1 = j; break; }
+        for (int j = 0; j < T.np; ++j) {
+            const double hi = (j < T.np - 1) ? X.pf[j + 1] : 2.0 * PI;
+            if (phi > X.pf[j] && phi < hi) { c2 = j; break; }
+        }
+    }
+    X.D(F_PX, s) = px; X.D(F_PY, s) = py; X.D(F_PZ, s) = pz; X.D(F_DX, s) = dx; X.D(F_DY, s) = dy; X.D(F_DZ, s) = dz;
+    X.D(F_S0, s) = 1.0; X.D(F_S1, s) = 0.0; X.D(F_S2, s) = 0.0; X.D(F_S3, s) = 0.0; X.D(F_TAU, s) = 0.0;
+    X.I(I_ND, s) = (int)nd;
+    X.I(I_HCELL, s) = pack_cell(c0, c1, c2) | (1 << 30);      // bit 30: the photon sits on the outer radial face
+    ray_setup(X, T, s, px, py, pz, dx, dy, dz, c0, c1, c2, T.nr, K_PRE, RAY_NONE);
+    return true;
+}
+
+// PRE: the tau pre-pass ended -> first optical depth :660-685
+template <class Sh>
+__device__ __forceinline__ bool ev_pre(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+    if (!valid) return false;
+    const LaunchArgs& L = A.L;
+    const int out = (X.I(I_INFO, s) >> 8) & 15;
+    const double tacc = X.D(F_ACC, s);
+    const bool hit_surface = (out == O_SURF);
+    if (tacc < 1.e-6 && !hit_surface) { X.I(I_INFO, s) = K_DEAD; return true; }
+    const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+    const unsigned nd = (unsigned)X.I(I_ND, s);
+    const Draws d(id, nd, L.seed, 1);
+    const double xi = d.get(0);
+    X.I(I_ND, s) = (int)(nd + 1u);
+    double arg = 1.0 - xi;
+    if (!(tacc < 1.e-6) && tacc < 50.0) {
+        const double f = 1.0 - exp(-tacc);
+        arg = 1.0 - xi * f;
+        X.D(F_S0, s) *= f; X.D(F_S1, s) *= f; X.D(F_S2, s) *= f; X.D(F_S3, s) *= f;
+    }
+    const double tau = -log(arg);
+    X.D(F_TAU, s) = tau;
+    const int hc = X.I(I_HCELL, s);
+    ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
+              hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, (hc >> 30) ? A.T.nr : -1, K_WALK, tau);
+    return true;
+}
+
+// H: the transport walk reached its optical depth.  Survival :791-813, peel-off weight and pixel (peel_photon
+// :4763-4951; the e^-tau factor is applied by DEP once the peel ray has been walked), scattering :819-845.
+template <class Sh>
+__device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+    if (!valid) return false;
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
+    const int cell = X.I(I_CELL, s);
+    const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+    const int ci = c0 + T.nr * (c1 + T.nt * c2);
+    double dx = X.D(F_DX, s), dy = X.D(F_DY, s), dz = X.D(F_DZ, s);
+    const double tpos = X.D(F_T, s) + (X.D(F_TAU, s) - X.D(F_ACC, s)) / __ldg(T.kext + ci);
+    const double px = X.D(F_PX, s) + tpos * dx, py = X.D(F_PY, s) + tpos * dy, pz = X.D(F_PZ, s) + tpos * dz;
+    double S[4] = {X.D(F_S0, s), X.D(F_S1, s), X.D(F_S2, s), X.D(F_S3, s)};
+    const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+    unsigned nd = (unsigned)X.I(I_ND, s);
+    const Draws dr(id, nd, L.seed, 5);
+    bool alive = L.photon_scattering != 0;
+    if (alive) { const double xi = dr.get(0); ++nd; if (xi < L.fstop) alive = false; }
+    if (alive) {
+        const double alb = __ldg(T.albedo + ci);
+        if (alb < 1.0 && alb > 0.0) { const double g = alb / (1.0 - L.fstop); S[0] *= g; S[1] *= g; S[2] *= g; S[3] *= g; }
+        if (S[0] <= L.photon_minimum) alive = false;
+    }
+    if (!alive) { X.I(I_ND, s) = (int)nd; X.I(I_INFO, s) = K_DEAD; return true; }
+    // ---- peel-off towards the detector: Stokes vector scattered into det, pixel
+    ++C.n_peel;
+    int pix = -1;
+    double W[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+        double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
+        if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
+        double F[16];
+        matrix_at_deg(T, ci, acos(mu) * (180.0 / PI), F);
+        if (!(fabs(dz) < 1.0)) err_count(A, 45);
+        else {
+            const double smu = sqrt(1.0 - mu * mu);
+            double nc = (L.det[2] - dz * mu) / (smu * sqrt(1.0 - dz * dz));
+            if (!(nc == nc)) err_count(A, 44);
+            else {
+                nc = fmin(fmax(nc, -1.0), 1.0);
+                const double cr = dy * L.det[0] - dx * L.det[1];
+                const bool flip = (cr > 0.0) || (cr == 0.0 && dx * L.det[0] + dy * L.det[1] > 0.0);
+                const double c2a = 2.0 * nc * nc - 1.0;
+                double s2a = 2.0 * nc * sqrt(fmax(1.0 - nc * nc, 0.0));
+                if (flip) s2a = -s2a;
+                const double nc2 = (dz - L.det[2] * mu) / (smu * sqrt(1.0 - L.det[2] * L.det[2]));
+                int soft = 0;
+                const int e = (fabs(L.det[2]) < 1.0) ? polrot_fast(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
+                if (e) err_count(A, e);
+                else if (!(W[0] > 0.0 && W[0] < 1.e100)) err_count(A, 53);
+                else {
+                    const double x_im = py * L.cos_dp - px * L.sin_dp;
+                    const double y_im = pz * L.sin_dt - py * L.cos_dt * L.sin_dp - px * L.cos_dt * L.cos_dp;
+                    const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
+                    const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
+                    if (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) err_count(A, 60);
+                    else pix = (ix - 1) + L.nx * (iy - 1);
+                }
+            }
+        }
+    }
+    // ---- scattering: new direction and Stokes vector (ev_scatter, fast branch)
+    ++C.n_sc;
+    double tau = -1.0;                      // < 0: the photon dies after its peel-off has been deposited
+    {
+        FastAngles g;
+        int e = sample_angles_fast_xi(A, dr.get(1), dr.get(2), dr.get(3), S, ci, g);
+        nd += (e == 6) ? 2u : 3u;
+        double e0 = 0, e1 = 0, e2 = 0;
+        if (!e) {
+            const double cto = dz / sqrt(dx * dx + dy * dy + dz * dz);
+            const double sto = sqrt(1.0 - cto * cto);
+            const double ctn = cto * g.alpha + sto * g.sT * g.cb;
+            const double stn = sqrt(1.0 - ctn * ctn);
+            double nc = (g.alpha - ctn * cto) / (stn * sto);
+            if (!(nc == nc)) e = 20;
+            else {
+                if (nc >= 1.0) nc = 1.0 - 1.e-10; else if (nc <= -1.0) nc = -1.0 + 1.e-10;
+                const double sD = sqrt(1.0 - nc * nc) * (g.flip ? -1.0 : 1.0);
+                const double rho = sqrt(dx * dx + dy * dy);
+                const double cph = rho > 0.0 ? dx / rho : 1.0, sph = rho > 0.0 ? dy / rho : 0.0;
+                e0 = stn * (cph * nc - sph * sD); e1 = stn * (sph * nc + cph * sD); e2 = ctn;
+                if (!(fabs(e2) < 1.0)) e = 16;
+            }
+        }
+        if (!e) {
+            double F[16], Sn[4];
+            matrix_at_deg(T, ci, g.deg, F);
+            const double nc2 = (dz - e2 * g.alpha) / (g.sT * sqrt(1.0 - e2 * e2));
+            int soft = 0;
+            e = polrot_fast(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
+            if (soft) err_count(A, soft);
+            if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
+        }
+        if (e) { err_count(A, e); ++C.n_err; }
+        else { const double xi = dr.get(4); ++nd; tau = -log(1.0 - xi); }
+    }
+    X.D(F_PX, s) = px; X.D(F_PY, s) = py; X.D(F_PZ, s) = pz; X.D(F_DX, s) = dx; X.D(F_DY, s) = dy; X.D(F_DZ, s) = dz;
+    X.D(F_S0, s) = S[0]; X.D(F_S1, s) = S[1]; X.D(F_S2, s) = S[2]; X.D(F_S3, s) = S[3]; X.D(F_TAU, s) = tau;
+    X.D(F_W0, s) = W[0]; X.D(F_W1, s) = W[1]; X.D(F_W2, s) = W[2]; X.D(F_W3, s) = W[3];
+#ifdef E2_DEBUG
+    if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, X.D(F_TAU, s), X.D(F_ACC, s), X.D(F_T, s));
+#endif
+    X.I(I_PIX, s) = pix; X.I(I_ND, s) = (int)nd; X.I(I_HCELL, s) = cell;
+    ray_setup(X, T, s, px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, RAY_NONE);
+    return true;
+}
+
+// DEP: the peel ray ended -> e^-tau, detector deposit :4955-4972; then the transport ray of the scattered photon
+template <class Sh>
+__device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+    if (!valid) return false;
+    const LaunchArgs& L = A.L;
+    const int out = (X.I(I_INFO, s) >> 8) & 15;
+    const double tacc = X.D(F_ACC, s);
+    const int pix = X.I(I_PIX, s);
+    if (out == O_EXIT && tacc < 50.0 && pix >= 0) {
+        const double w = exp(-tacc);
+        const double W0 = w * X.D(F_W0, s), W1 = -(w * X.D(F_W1, s)), W2 = w * X.D(F_W2, s), W3 = w * X.D(F_W3, s);
+        const size_t npx = (size_t)L.nx * L.ny;
+        double* d = A.O.det + pix;
+        atomicAdd(d, W0); atomicAdd(d + npx, W1); atomicAdd(d + 2 * npx, W2); atomicAdd(d + 3 * npx, W3);
+        atomicAdd(d + 4 * npx, W0 * W0); atomicAdd(d + 5 * npx, W1 * W1); atomicAdd(d + 6 * npx, W2 * W2); atomicAdd(d + 7 * npx, W3 * W3);
+        atomicAdd(d + 8 * npx, 1.0); atomicAdd(d + 9 * npx, 1.0);
+    }
+    const double tau = X.D(F_TAU, s);
+    if (tau < 0.0) { X.I(I_INFO, s) = K_DEAD; return true; }
+    const int hc = X.I(I_HCELL, s);
+    ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
+              hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, -1, K_WALK, tau);
+    return true;
+}
+
+// RES: a polar or azimuthal face was crossed at parameter t: step the cell index and re-solve that axis
+template <class Sh>
+__device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, bool valid, int s) {
+    if (!valid) return false;
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
+    int info = X.I(I_INFO, s);
+    const int out = (info >> 8) & 15, kind = info & 3;
+    const int cell = X.I(I_CELL, s);
+    int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+    const bool peel = (kind == K_PEEL);
+    const double n0 = peel ? L.det[0] : X.D(F_DX, s), n1 = peel ? L.det[1] : X.D(F_DY, s), n2 = peel ? L.det[2] : X.D(F_DZ, s);
+    RayK K;
+    double hbn, D0, iq;
+    ray_consts(T, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), n0, n1, n2, K, hbn, D0, iq);
+    const double t = X.D(F_T, s);
+    info &= 0xff;
+    if (out == O_REST) {
+        c1 += (info & B_TUPPER) ? 1 : -1;
+        int upper;
+        X.D(F_TT, s) = theta_next(X, T.nt, c1, t, K, upper);
+        info = (info & ~B_TUPPER) | (upper ? B_TUPPER : 0);
+    } else {
+        if (info & B_PUP) c2 = (c2 + 1 == T.np) ? 0 : c2 + 1; else c2 = (c2 == 0) ? T.np - 1 : c2 - 1;
+        int up;
+        X.D(F_TP, s) = phi_next(X, T.np, c2, t, K, up);
+    }
+#ifdef E2_DEBUG
+    if (c1 < 0 || c1 >= T.nt || c2 < 0 || c2 >= T.np) printf("E2 resolve: slot %d out %d cell %d %d %d info %x t %.17g\n", s, out, c0, c1, c2, info, t);
+#endif
+    X.I(I_CELL, s) = pack_cell(c0, c1, c2);
+    X.I(I_INFO, s) = info;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+template <int NT, int NP, int MINB>
+__global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_constant__ KernelArgs A) {
+    extern __shared__ double smraw[];
+    const DevTables& T = A.T;
+    const Lay lay(T.nr, T.nt, T.np, NP);
+    using Sh = ShT<NP>;
+    constexpr int RC = Sh::RC;
+    Sh X;
+    {
+        double* sm = smraw;
+        X.r = sm; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
+        X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
+        X.sd = sm + lay.o_sd;
+        X.si = reinterpret_cast<int*>(X.sd + NF_D * NP);
+        X.q = reinterpret_cast<short*>(X.si + NF_I * NP);
+        X.head = reinterpret_cast<int*>(X.q + N_LISTS * RC);
+        X.tail = X.head + 8; X.misc = X.head + 16;
+        const int tid = threadIdx.x;
+        for (int i = tid; i <= T.nr; i += NT) sm[i] = T.rfront[i];
+        for (int i = tid; i <= T.nt; i += NT) {
+            sm[lay.o_tf + i] = T.thetafront[i]; sm[lay.o_tt + i] = T.ttan[i];
+            reinterpret_cast<int*>(sm + lay.o_tp)[i] = T.tplane[i];
+        }
+        for (int i = tid; i < T.np; i += NT) { sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i]; }
+        for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; }
+        if (tid < 8) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
+        if (tid == 0) X.misc[0] = 0;
+    }
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 2;      // marcher trips per round
+    Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
+
+    // marcher state
+    int slot = -1, c0 = 0, cbase = 0, cell12 = 0, info = 0;
+    double t = 0, acc = 0, tr = 0, tt = 0, tp = 0, hbn = 0, D0 = 0, iq = 0, lim = 0, kap = 0;
+    volatile int* vhead = X.head;
+    volatile int* vtail = X.tail;
+
+    for (;;) {
+        // ================= marcher phase =================
+        for (int trip = 0; trip < trips; ++trip) {
+            // ---- free lanes claim ready rays
+            const unsigned fm = __ballot_sync(FULL, slot < 0);
+            if (fm && (vtail[L_RDY] - vhead[L_RDY]) > 0) {
+                int base = 0, n = 0;
+                if (lane == 0) {
+                    const int want = __popc(fm);
+                    int h = vhead[L_RDY];
+                    for (;;) {
+                        n = min(want, vtail[L_RDY] - h);
+                        if (n <= 0) { n = 0; break; }
+                        const int old = atomicCAS(X.head + L_RDY, h, h + n);
+                        if (old == h) { base = h; break; }
+                        h = old;
+                    }
+                }
+                base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
+                const int rank = __popc(fm & lt);
+                if (slot < 0 && rank < n) {
+                    slot = X.Q(L_RDY, base + rank);
+                    t = X.D(F_T, slot); acc = X.D(F_ACC, slot); tr = X.D(F_TR, slot); tt = X.D(F_TT, slot); tp = X.D(F_TP, slot);
+                    hbn = X.D(F_HBN, slot); D0 = X.D(F_D0, slot); iq = X.D(F_IQ, slot); lim = X.D(F_LIM, slot);
+                    const int cell = X.I(I_CELL, slot);
+                    info = X.I(I_INFO, slot);
+                    c0 = cell & 1023; cell12 = cell & ~1023;
+                    cbase = T.nr * (((cell >> 10) & 1023) + T.nt * ((cell >> 20) & 1023));
+                    kap = __ldg(T.kext + cbase + c0);
+                }
+            }
+            // ---- one trip
+            int lst = -1;
+            if (slot >= 0) {
+                const int kind = info & 3;
+                int out = O_NONE;
+                double tn = tr; int ax = 0;
+                if (tt < tn) { tn = tt; ax = 1; }
+                if (tp < tn) { tn = tp; ax = 2; }
+                if (kind == K_DEAD) out = O_DEAD;
+                else if (!(tn < RAY_NONE)) { ++C.n_cf; out = O_ERR; }
+                else {
+                    ++C.n_cf;
+                    const double dtau = (tn - t) * kap;
+#ifdef E2_DEBUG
+                    if (!(tn >= t) || !(kap >= 0.0)) printf("E2 marcher: slot %d kind %d ax %d t %.17g tn %.17g tr %.17g tt %.17g tp %.17g kap %g c0 %d cell12 %x info %x\n", slot, kind, ax, t, tn, tr, tt, tp, kap, c0, cell12, info);
+#endif
+                    if (kind == K_WALK && acc + dtau > lim) out = O_LIMIT;
+                    else {
+                        acc += dtau; t = tn;
+                        if (ax == 0) {
+                            const bool inward = (info & B_INWARD) != 0;
+                            const int f = inward ? c0 : c0 + 1;
+                            if (f == T.nr) out = O_EXIT;
+                            else if (f == T.cell_depth) out = O_SURF;
+                            else {
+                                c0 += inward ? -1 : 1;
+                                kap = __ldg(T.kext + cbase + c0);
+                                bool in2 = inward;
+                                if (inward) {
+                                    const double r = X.r[c0], disc = fma(r * r, iq, D0);
+                                    if (disc >= 0.0) tr = hbn - sqrt(disc); else in2 = false;
+                                }
+                                if (!in2) {
+                                    const double r = X.r[c0 + 1], disc = fma(r * r, iq, D0);
+                                    tr = (disc >= 0.0) ? hbn + sqrt(disc) : RAY_NONE;
+                                    info &= ~B_INWARD;
+                                }
+                            }
+                        } else out = (ax == 1) ? O_REST : O_RESP;
+                    }
+                }
+                if (out != O_NONE) {
+                    X.D(F_T, slot) = t; X.D(F_ACC, slot) = acc;
+                    if (out == O_REST || out == O_RESP) X.D(F_TR, slot) = tr;      // the ray goes on after the re-solve
+                    X.I(I_CELL, slot) = cell12 | c0;
+                    X.I(I_INFO, slot) = (info & 0xff) | (out << 8);
+                    if (out == O_REST || out == O_RESP) lst = L_RES;
+                    else if (out == O_DEAD) lst = L_EMIT;
+                    else if (out == O_ERR) {
+                        err_count(A, 31); ++C.n_err; lst = L_EMIT;
+                        err_count(A, kind == K_PRE ? 2 : (kind == K_WALK ? 3 : 43));
+                    } else if (kind == K_PRE) lst = L_PRE;
+                    else if (kind == K_PEEL) lst = L_DEP;
+                    else if (out == O_LIMIT) lst = L_H;
+                    else {   // the transport walk left the grid or was absorbed by the surface (:755-764: one draw)
+                        if (out == O_SURF) { ++C.n_surf; X.I(I_ND, slot) += 1; }
+                        lst = L_EMIT;
+                    }
+                }
+            }
+            // ---- push finished rays on their event lists (one shared-memory atomic per list present in the warp)
+            if (__any_sync(FULL, lst >= 0)) {
+                const unsigned g = __match_any_sync(FULL, lst);
+                const int leader = __ffs(g) - 1;
+                int base = 0;
+                if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
+                base = __shfl_sync(FULL, base, leader);
+                if (lst >= 0) { X.Q(lst, base + __popc(g & lt)) = (short)slot; slot = -1; }
+            }
+        }
+        __syncthreads();
+        // ================= event phase =================
+        {
+            int off[6], cnt[5], hd[5];
+            off[0] = 0;
+#pragma unroll
+            for (int l = 0; l < 5; ++l) { hd[l] = X.head[l]; cnt[l] = X.tail[l] - hd[l]; off[l + 1] = off[l] + ((cnt[l] + 31) & ~31); }
+            for (int v = tid; v < off[5]; v += NT) {
+                int l = 0;
+#pragma unroll
+                for (int k = 1; k < 5; ++k) if (v >= off[k]) l = k;
+                const int idx = v - off[l];
+                const bool valid = idx < cnt[l];
+                const int s = valid ? (int)X.Q(l, hd[l] + idx) : 0;
+                bool push;
+                if (l == L_H) push = ev_interact(X, A, valid, s, C);
+                else if (l == L_DEP) push = ev_deposit(X, A, valid, s, C);
+                else if (l == L_RES) push = ev_resolve(X, A, valid, s);
+                else if (l == L_PRE) push = ev_pre(X, A, valid, s, C);
+                else push = ev_emit(X, A, valid, s, C);
+                const unsigned pm = __ballot_sync(FULL, push);
+                if (pm) {
+                    const int leader = __ffs(pm) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(X.tail + L_RDY, __popc(pm));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (push) X.Q(L_RDY, base + __popc(pm & lt)) = (short)s;
+                }
+            }
+            __syncthreads();
+            if (tid < 5) X.head[tid] = hd[tid] + cnt[tid];
+        }
+        if (X.misc[0] >= NP) break;
+    }
+    // counters
+    {
+        unsigned long long v[7] = {C.n_emit, C.n_cf, C.n_sc, C.n_peel, C.n_surf, C.n_draw, C.n_err};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            unsigned long long x = v[k];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+            if (lane == 0 && x) atomicAdd(A.O.stats + k, x);
+        }
+    }
+}
+
+}  // namespace e2
