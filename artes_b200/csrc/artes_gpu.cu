@@ -34,6 +34,7 @@ cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cuda
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
 bool engine2_supports(const KernelArgs& a);
+size_t engine2_scratch_bytes(int sm_count);
 cudaError_t launch_transport2(const KernelArgs& a, int sm_count, cudaStream_t stream);
 }  // namespace fast
 cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
@@ -84,6 +85,7 @@ struct DeviceState {
     double* out_d = nullptr;               // [det 10*npx | flux 2 | flow4 4*cells | flow3 3*cells]
     size_t out_d_cap = 0;
     unsigned long long* out_u = nullptr;   // [err 64 | stats 8 | counter 1]
+    double* scratch = nullptr;             // ray/event engine: cold photon records (L2-resident working set)
     ncclComm_t comm = nullptr;
     unsigned long long n_photons = 0;
     int launches = 0;
@@ -265,6 +267,7 @@ int artes_gpu_destroy(artes_gpu_ctx* ctx) {
         free_pool(d.wl_allocs);
         if (d.out_d) cudaFree(d.out_d);
         if (d.out_u) cudaFree(d.out_u);
+        if (d.scratch) cudaFree(d.scratch);
         for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -468,7 +471,11 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
             static const int engine = env_int("ARTES_ENGINE", 2);
             cudaError_t e;
             if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, false, d.sm_count, d.stream);
-            else if (engine == 2 && fast::engine2_supports(a)) e = fast::launch_transport2(a, d.sm_count, d.stream);
+            else if (engine == 2 && fast::engine2_supports(a)) {
+                if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
+                a.O.scratch = d.scratch;
+                e = fast::launch_transport2(a, d.sm_count, d.stream);
+            }
             else e = fast::launch_transport(a, false, d.sm_count, d.stream);
             if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
             d.launches = 1;

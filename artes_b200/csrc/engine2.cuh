@@ -51,10 +51,15 @@ enum : int { O_NONE = 0, O_LIMIT, O_EXIT, O_SURF, O_REST, O_RESP, O_ERR, O_DEAD 
 // info word: bits 0-1 kind, 2 radial inward, 3 next theta face is the upper one, 4 phi increasing, 8-11 outcome
 enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16 };
 
-// slot fields (structure of arrays, [field][NP])
-enum : int { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_S0, F_S1, F_S2, F_S3, F_TAU, F_W0, F_W1, F_W2, F_W3,
-             F_T, F_ACC, F_TR, F_TT, F_TP, F_HBN, F_D0, F_IQ, F_LIM, NF_D };
-enum : int { I_CELL = 0, I_HCELL, I_INFO, I_PIX, I_ND, I_IDLO, I_IDHI, NF_I };
+// Slot fields.  COLD fields (touched by events only) live in a 160-byte record per slot in global memory
+// (L2-resident scratch, one region per block); HOT fields (the ray a marcher loads and stores) live in
+// shared memory as a structure of arrays [field][NP].  Keeping the cold part out of shared memory is what
+// lets a block hold several times more photons than lanes.
+enum : int { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_S0, F_S1, F_S2, F_S3, F_TAU, F_W0, F_W1, F_W2, F_W3, NF_COLD,
+             F_T = NF_COLD, F_ACC, F_TR, F_TT, F_TP, F_HBN, F_D0, F_IQ, F_LIM, NF_D };
+enum : int { I_CELL = 0, I_INFO, NI_HOT, I_HCELL = NI_HOT, I_PIX, I_ND, I_IDLO, I_IDHI, NF_I };
+constexpr int NF_HOT = NF_D - NF_COLD;
+constexpr int REC = 20;       // doubles per cold record: 15 doubles + 5 ints, padded to 160 bytes
 
 __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c < np_slots) c <<= 1; return c; }
 
@@ -64,7 +69,7 @@ struct Lay {
     __host__ __device__ Lay(int nr, int nt, int np, int NP) {
         o_tf = nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
         o_tp = o_pf + np; o_sd = o_tp + (nt + 2) / 2 + 1; n_tab = o_sd;
-        bytes = (size_t)(o_sd + NF_D * NP) * 8 + (size_t)NF_I * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
+        bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
     }
 };
 
@@ -72,10 +77,14 @@ template <int NP>
 struct ShT {                     // pointers into the block's shared memory
     const double* r; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
     const int* tplane;
-    double* sd; int* si; short* q; int* head; int* tail; int* misc;   // misc[0] = slots retired for good
+    double* sd; int* si; short* q; int* head; int* tail;
+    int* misc;                   // [0] slots retired for good, [1] event batch counter, [2] ready-list tail at the end of the last event phase
+    double* cold;                // this block's records in global memory
     static constexpr int RC = ring_cap(NP);
-    __device__ __forceinline__ double& D(int f, int s) const { return sd[f * NP + s]; }
-    __device__ __forceinline__ int& I(int f, int s) const { return si[f * NP + s]; }
+    __device__ __forceinline__ double& D(int f, int s) const { return (f >= NF_COLD) ? sd[(f - NF_COLD) * NP + s] : cold[(size_t)s * REC + f]; }
+    __device__ __forceinline__ int& I(int f, int s) const {
+        return (f < NI_HOT) ? si[f * NP + s] : reinterpret_cast<int*>(cold + (size_t)s * REC + NF_COLD)[f - NI_HOT];
+    }
     __device__ __forceinline__ short& Q(int l, int pos) const { return q[l * RC + (pos & (RC - 1))]; }
 };
 
@@ -397,20 +406,45 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
 // DEP: the peel ray ended -> e^-tau, detector deposit :4955-4972; then the transport ray of the scattered photon
 template <class Sh>
 __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
-    if (!valid) return false;
     const LaunchArgs& L = A.L;
-    const int out = (X.I(I_INFO, s) >> 8) & 15;
-    const double tacc = X.D(F_ACC, s);
-    const int pix = X.I(I_PIX, s);
-    if (out == O_EXIT && tacc < 50.0 && pix >= 0) {
-        const double w = exp(-tacc);
-        const double W0 = w * X.D(F_W0, s), W1 = -(w * X.D(F_W1, s)), W2 = w * X.D(F_W2, s), W3 = w * X.D(F_W3, s);
+    const int out = valid ? ((X.I(I_INFO, s) >> 8) & 15) : O_NONE;
+    const double tacc = valid ? X.D(F_ACC, s) : 0.0;
+    const int pix = valid ? X.I(I_PIX, s) : -1;
+    // Deposit.  When every depositing lane of the batch hits the same pixel (1x1 "photometry" detectors: phase
+    // curves, spectra) the ten sums are reduced across the warp first, so the L2 sees one atomic per plane and
+    // batch instead of 32 serialised ones on the same address.
+    const bool dep = valid && out == O_EXIT && tacc < 50.0 && pix >= 0;
+    const unsigned dm = __ballot_sync(FULL, dep);
+    if (dm) {
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (dep) {
+            const double w = exp(-tacc);
+            v[0] = w * X.D(F_W0, s); v[1] = -(w * X.D(F_W1, s)); v[2] = w * X.D(F_W2, s); v[3] = w * X.D(F_W3, s);
+            v[4] = v[0] * v[0]; v[5] = v[1] * v[1]; v[6] = v[2] * v[2]; v[7] = v[3] * v[3];
+        }
         const size_t npx = (size_t)L.nx * L.ny;
-        double* d = A.O.det + pix;
-        atomicAdd(d, W0); atomicAdd(d + npx, W1); atomicAdd(d + 2 * npx, W2); atomicAdd(d + 3 * npx, W3);
-        atomicAdd(d + 4 * npx, W0 * W0); atomicAdd(d + 5 * npx, W1 * W1); atomicAdd(d + 6 * npx, W2 * W2); atomicAdd(d + 7 * npx, W3 * W3);
-        atomicAdd(d + 8 * npx, 1.0); atomicAdd(d + 9 * npx, 1.0);
+        const int pix0 = __shfl_sync(FULL, pix, __ffs(dm) - 1);
+        const bool same = __all_sync(FULL, !dep || pix == pix0);
+        if (same && __popc(dm) > 2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+            const int lane = threadIdx.x & 31;
+            double* d = A.O.det + pix0;
+            if (lane < 8) {
+                double x = v[0];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) if (lane == k) x = v[k];
+                atomicAdd(d + (size_t)lane * npx, x);
+            } else if (lane < 10) atomicAdd(d + (size_t)lane * npx, (double)__popc(dm));
+        } else if (dep) {
+            double* d = A.O.det + pix;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(d + (size_t)k * npx, v[k]);
+            atomicAdd(d + 8 * npx, 1.0); atomicAdd(d + 9 * npx, 1.0);
+        }
     }
+    if (!valid) return false;
     const double tau = X.D(F_TAU, s);
     if (tau < 0.0) { X.I(I_INFO, s) = K_DEAD; return true; }
     const int hc = X.I(I_HCELL, s);
@@ -470,8 +504,9 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
         X.r = sm; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
         X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
         X.sd = sm + lay.o_sd;
-        X.si = reinterpret_cast<int*>(X.sd + NF_D * NP);
-        X.q = reinterpret_cast<short*>(X.si + NF_I * NP);
+        X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
+        X.q = reinterpret_cast<short*>(X.si + NI_HOT * NP);
+        X.cold = A.O.scratch + (size_t)blockIdx.x * NP * REC;
         X.head = reinterpret_cast<int*>(X.q + N_LISTS * RC);
         X.tail = X.head + 8; X.misc = X.head + 16;
         const int tid = threadIdx.x;
@@ -483,12 +518,12 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
         for (int i = tid; i < T.np; i += NT) { sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i]; }
         for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; }
         if (tid < 8) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
-        if (tid == 0) X.misc[0] = 0;
+        if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; }
     }
     __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 2;      // marcher trips per round
+    const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 16;      // marcher trips per round
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
 
     // marcher state
@@ -555,16 +590,13 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
                             else {
                                 c0 += inward ? -1 : 1;
                                 kap = __ldg(T.kext + cbase + c0);
+                                // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
                                 bool in2 = inward;
-                                if (inward) {
-                                    const double r = X.r[c0], disc = fma(r * r, iq, D0);
-                                    if (disc >= 0.0) tr = hbn - sqrt(disc); else in2 = false;
-                                }
-                                if (!in2) {
-                                    const double r = X.r[c0 + 1], disc = fma(r * r, iq, D0);
-                                    tr = (disc >= 0.0) ? hbn + sqrt(disc) : RAY_NONE;
-                                    info &= ~B_INWARD;
-                                }
+                                double r = X.r[in2 ? c0 : c0 + 1], disc = fma(r * r, iq, D0);
+                                if (in2 && disc < 0.0) { in2 = false; info &= ~B_INWARD; r = X.r[c0 + 1]; disc = fma(r * r, iq, D0); }
+                                const double sq = sqrt(fmax(disc, 0.0));
+                                tr = in2 ? hbn - sq : hbn + sq;
+                                if (disc < 0.0) tr = RAY_NONE;
                             }
                         } else out = (ax == 1) ? O_REST : O_RESP;
                     }
@@ -600,18 +632,29 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
         }
         __syncthreads();
         // ================= event phase =================
+        // Every warp claims 32-event batches of one type until none is left, heaviest type first.  Only full
+        // batches are served unless the marchers would run short of ready rays.
         {
-            int off[6], cnt[5], hd[5];
-            off[0] = 0;
+            const int order[5] = {L_H, L_DEP, L_RES, L_PRE, L_EMIT};
+            int hd[5], m[5], boff[6], full = 0;
 #pragma unroll
-            for (int l = 0; l < 5; ++l) { hd[l] = X.head[l]; cnt[l] = X.tail[l] - hd[l]; off[l + 1] = off[l] + ((cnt[l] + 31) & ~31); }
-            for (int v = tid; v < off[5]; v += NT) {
-                int l = 0;
+            for (int k = 0; k < 5; ++k) { hd[k] = X.head[order[k]]; m[k] = X.tail[order[k]] - hd[k]; full += m[k] >> 5; }
+            const bool partial = (X.misc[2] - X.head[L_RDY]) + 32 * full < NT + NT / 2;
+            boff[0] = 0;
 #pragma unroll
-                for (int k = 1; k < 5; ++k) if (v >= off[k]) l = k;
-                const int idx = v - off[l];
-                const bool valid = idx < cnt[l];
-                const int s = valid ? (int)X.Q(l, hd[l] + idx) : 0;
+            for (int k = 0; k < 5; ++k) { if (!partial) m[k] &= ~31; boff[k + 1] = boff[k] + ((m[k] + 31) >> 5); }
+            for (;;) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(X.misc + 1, 1);
+                b = __shfl_sync(FULL, b, 0);
+                if (b >= boff[5]) break;
+                int k = 0;
+#pragma unroll
+                for (int j = 1; j < 5; ++j) if (b >= boff[j]) k = j;
+                const int idx = ((b - boff[k]) << 5) + lane;
+                const bool valid = idx < m[k];
+                const int l = order[k];
+                const int s = valid ? (int)X.Q(l, hd[k] + idx) : 0;
                 bool push;
                 if (l == L_H) push = ev_interact(X, A, valid, s, C);
                 else if (l == L_DEP) push = ev_deposit(X, A, valid, s, C);
@@ -628,7 +671,11 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
                 }
             }
             __syncthreads();
-            if (tid < 5) X.head[tid] = hd[tid] + cnt[tid];
+            if (tid == 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) X.head[order[k]] = hd[k] + m[k];
+                X.misc[1] = 0; X.misc[2] = X.tail[L_RDY];
+            }
         }
         if (X.misc[0] >= NP) break;
     }

@@ -56,6 +56,7 @@ struct DevOutputs {
     unsigned long long* err;         // [64]
     unsigned long long* stats;       // [8]: emit, cell_face, scatter, peel, surface, draws, error, -
     unsigned long long* counter;     // work counter (photon ids handed out)
+    double* scratch;                 // ray/event engine: cold photon records, blocks x slots x 160 B
 };
 
 // Injected-stream walk trace (test hook).

@@ -39,3 +39,24 @@ flt = sys.argv[3] if len(sys.argv) > 3 else ""
 for (f, ln), (ns, ni, nt, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:nlines]:
     if flt and flt not in f: continue
     print(f"{ni / tot[1] * 100:5.1f}% inst {ns / tot[0] * 100:5.1f}% smp lanes {nt / max(ni, 1):5.1f} | {f}:{ln}: {s}")
+
+# region split for engine2.cuh: marcher loop vs event phase (line ranges read from the source file itself)
+import os
+src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "artes_b200", "csrc", "engine2.cuh")
+if os.path.exists(src):
+    L = open(src).read().split("\n")
+    def find(s):
+        return next((i + 1 for i, x in enumerate(L) if s in x), None)
+    m0, m1, e1 = find("// ================= marcher phase"), find("// ================= event phase"), find("// counters")
+    if m0 and m1 and e1:
+        reg = {"marcher": [0, 0, 0], "event-dispatch": [0, 0, 0], "events": [0, 0, 0], "other files": [0, 0, 0]}
+        for (f, ln), (ns, ni, nt, s) in agg.items():
+            if f != "engine2.cuh":
+                k = "other files"
+            elif m0 <= ln < m1: k = "marcher"
+            elif m1 <= ln < e1: k = "event-dispatch"
+            elif ln < m0 - 40: k = "events"
+            else: k = "marcher"
+            reg[k][0] += ns; reg[k][1] += ni; reg[k][2] += nt
+        for k, (ns, ni, nt) in reg.items():
+            print(f"region {k:16s} {ni / tot[1] * 100:5.1f}% inst {ns / tot[0] * 100:5.1f}% smp lanes {nt / max(ni, 1):5.1f}")
