@@ -163,7 +163,7 @@ void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
     // warp regrouping thresholds; tunable for experiments through the environment
     static const int defer_events = env_int("ARTES_DEFER_EVENTS", 12), defer_refill = env_int("ARTES_DEFER_REFILL", 4);
     a.defer_events = defer_events; a.defer_refill = defer_refill;
-    static const int e2_trips = env_int("ARTES_E2_TRIPS", 2);
+    static const int e2_trips = env_int("ARTES_E2_TRIPS", 0);
     static const int e2_cfg = env_int("ARTES_E2_CFG", 32) & 31;      // block shape, see launch_transport2
     a.e2_trips = e2_trips; a.e2_pad = e2_cfg;
     a.fstop = L.fstop; a.photon_minimum = L.photon_minimum; a.photon_bias = L.photon_bias;
@@ -310,6 +310,7 @@ int artes_gpu_set_grid(artes_gpu_ctx* ctx, int nr, int ntheta, int nphi, const d
         free_pool(d.grid_allocs);
         DevTables& T = d.T;
         T.nr = nr; T.nt = ntheta; T.np = nphi; T.cells = ctx->cells; T.ox = ox; T.oy = oy; T.oz = oz;
+        T.inv_ox = 1.0 / ox; T.inv_oy = 1.0 / oy; T.inv_oz = 1.0 / oz;
         int rc = 0;
         rc |= upload(ctx, d, d.grid_allocs, rfront, (size_t)nr + 1, &T.rfront);
         rc |= upload(ctx, d, d.grid_allocs, thetafront, (size_t)ntheta + 1, &T.thetafront);

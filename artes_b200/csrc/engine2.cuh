@@ -113,12 +113,12 @@ struct RayK { double A1, A2, B1, B2, C1, C2, g0, g1, Xx, Xy, Nx, Ny, z0, n2; };
 
 __device__ __forceinline__ void ray_consts(const DevTables& T, double x, double y, double z, double n0, double n1, double n2,
                                            RayK& K, double& hbn, double& D0, double& iq) {
-    const double a = 1.0 / T.ox, b = 1.0 / T.oy, c = 1.0 / T.oz;
-    K.A1 = a * a * n0 * n0 + b * b * n1 * n1; K.A2 = c * c * n2 * n2;
-    K.B1 = a * a * x * n0 + b * b * y * n1;   K.B2 = c * c * z * n2;
-    K.C1 = a * a * x * x + b * b * y * y;     K.C2 = c * c * z * z;
+    const double a = T.inv_ox, b = T.inv_oy, a2 = a * a, b2 = b * b, c2 = T.inv_oz * T.inv_oz;
+    K.A1 = a2 * n0 * n0 + b2 * n1 * n1; K.A2 = c2 * n2 * n2;
+    K.B1 = a2 * x * n0 + b2 * y * n1;   K.B2 = c2 * z * n2;
+    K.C1 = a2 * x * x + b2 * y * y;     K.C2 = c2 * z * z;
     const double qa = K.A1 + K.A2, hb = K.B1 + K.B2, Cs = K.C1 + K.C2;
-    iq = 1.0 / qa; hbn = -hb * iq; D0 = fma(hbn, hbn, -(Cs * iq));
+    iq = frcp(qa); hbn = -hb * iq; D0 = fma(hbn, hbn, -(Cs * iq));
     K.g0 = n2 * Cs - z * hb; K.g1 = n2 * hb - z * qa;      // sign of d(cos theta)/dt = sign(g0 + g1 t)
     K.Xx = a * x; K.Xy = b * y; K.Nx = a * n0; K.Ny = b * n1; K.z0 = z; K.n2 = n2;
 }
@@ -129,15 +129,27 @@ __device__ __forceinline__ double radial_first(const Sh& X, int c0, int sface, d
     inward = hbn > 0.0;
     if (inward) {
         const double r = X.r[c0], disc = fma(r * r, iq, D0);
-        if (disc >= 0.0) { const double t = hbn - sqrt(disc); if (t > 1.e-15) return t; }
+        if (disc >= 0.0) { const double t = hbn - fsqrt(disc); if (t > 1.e-15) return t; }
         inward = 0;
     }
     const double r = X.r[c0 + 1], disc = fma(r * r, iq, D0);
     if (disc >= 0.0) {
-        const double t = hbn + sqrt(disc);
+        const double t = hbn + fsqrt(disc);
         if (t > ((sface == c0 + 1) ? 1.e-3 : 1.e-15)) return t;     // same-face threshold :2944
     }
     return RAY_NONE;
+}
+
+// smallest root > lim of qa t^2 + 2 hb t + qc = 0 on the right nappe (ray.cuh quadric_next with the fast operations)
+__device__ __forceinline__ double quadric_next_f(double qa, double hb, double qc, int hs, double lim, double z0, double n2) {
+    const double disc = hb * hb - qa * qc;
+    if (!(disc >= 0.0)) return RAY_NONE;
+    const double q = -(hb + copysign(fsqrt(disc), hb));
+    double t1 = (fabs(qa) > 1.e-100) ? fdiv(q, qa) : RAY_NONE;
+    double t2 = (fabs(q) > 1.e-100) ? fdiv(qc, q) : RAY_NONE;
+    if (!(t1 > lim) || (z0 + t1 * n2) * (double)hs < 0.0) t1 = RAY_NONE;
+    if (!(t2 > lim) || (z0 + t2 * n2) * (double)hs < 0.0) t2 = RAY_NONE;
+    return fmin(t1, t2);
 }
 
 template <class Sh>
@@ -145,12 +157,12 @@ __device__ __forceinline__ double cone_root(const Sh& X, int k, double t, const 
     const int tp = X.tplane[k];
     if (tp != 1) {   // equatorial plane :3068 / :3118
         if (tp != 2 || K.n2 == 0.0) return RAY_NONE;
-        const double r = -K.z0 / K.n2;
+        const double r = fdiv(-K.z0, K.n2);
         return (r > t) ? r : RAY_NONE;
     }
     const double tn = X.ttan[k], T2 = tn * tn, tf = X.tf[k];
     const int hs = (tf < PI / 2.0) ? 1 : ((tf > PI / 2.0) ? -1 : 0);
-    return quadric_next(K.A1 - K.A2 * T2, K.B1 - K.B2 * T2, K.C1 - K.C2 * T2, hs, t, K.z0, K.n2);
+    return quadric_next_f(K.A1 - K.A2 * T2, K.B1 - K.B2 * T2, K.C1 - K.C2 * T2, hs, t, K.z0, K.n2);
 }
 
 // next polar crossing after parameter t from cell c1: face in the direction of motion first, then the other
@@ -178,7 +190,7 @@ __device__ __forceinline__ double phi_next(const Sh& X, int np, int c2, double t
     const double ps = X.ps[k], pc = X.pc[k];
     const double den = K.Ny * pc - K.Nx * ps;
     if (den == 0.0) return RAY_NONE;
-    const double r = (K.Xx * ps - K.Xy * pc) / den;
+    const double r = fdiv(K.Xx * ps - K.Xy * pc, den);
     return (r > t) ? r : RAY_NONE;
 }
 
@@ -197,6 +209,73 @@ __device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s
     X.D(F_HBN, s) = hbn; X.D(F_D0, s) = D0; X.D(F_IQ, s) = iq; X.D(F_LIM, s) = lim;
     X.I(I_CELL, s) = pack_cell(c0, c1, c2);
     X.I(I_INFO, s) = kind | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
+}
+
+// polrot_fast (transport.cuh) with the fast division / square root
+__device__ __forceinline__ int polrot_f(double c2a, double s2a, bool flip, double nc2, const double Sin[4],
+                                        const double F[16], double Sout[4], bool peeling, int& soft) {
+    if (!(fabs(nc2) < 1.00001)) return 11;
+    nc2 = fmin(fmax(nc2, -1.0), 1.0);
+    const double r0 = Sin[0], r1 = c2a * Sin[1] + s2a * Sin[2], r2 = c2a * Sin[2] - s2a * Sin[1], r3 = Sin[3];
+    double s[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s[r] = F[4 * r] * r0 + F[4 * r + 1] * r1 + F[4 * r + 2] * r2 + F[4 * r + 3] * r3;
+    if (!peeling) {
+        if (s[0] > 0.0) { const double nrm = fdiv(r0, s[0]); s[0] = r0; s[1] *= nrm; s[2] *= nrm; s[3] *= nrm; }
+        else soft = 12;
+    }
+    const double c2 = 2.0 * nc2 * nc2 - 1.0;
+    double s2 = 2.0 * nc2 * fsqrt(fmax(1.0 - nc2 * nc2, 0.0));
+    if (flip) s2 = -s2;
+    Sout[0] = s[0];
+    Sout[1] = c2 * s[1] + s2 * s[2];
+    Sout[2] = c2 * s[2] - s2 * s[1];
+    Sout[3] = s[3];
+    return 0;
+}
+
+// sample_angles_fast with the three random numbers supplied by the caller (engine2: stateless Philox draws)
+__device__ __forceinline__ int sample_angles_f(const KernelArgs& A, double xi1, double xi2, double xi3, const double S[4],
+                                                     int cellidx, FastAngles& g) {
+    const DevTables& T = A.T;
+    const int u = __ldg(T.c2u + cellidx);
+    const double p11 = __ldg(T.p1k + 4 * u), p12 = __ldg(T.p1k + 4 * u + 1), p13 = __ldg(T.p1k + 4 * u + 2), p14 = __ldg(T.p1k + 4 * u + 3);
+    const double Ac = p11 * S[0] + p14 * S[3], Bc = p12 * S[1] + p13 * S[2], Cc = p12 * S[2] - p13 * S[1];
+    const double* pc2 = T.cdfA;
+    const double* ps2 = T.cdfA + 181;
+    auto cumA = [&](int i) { return Ac * (double)i + Bc * __ldg(pc2 + i) + Cc * __ldg(ps2 + i); };
+    double samp = xi1 * cumA(180);
+    int lo = 0, hi = 180;  // smallest i in 1..180 with cum(i) >= samp
+    double ylo = 0.0, yhi = cumA(180);
+#pragma unroll 1
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; double y = cumA(mid); if (y >= samp) { hi = mid; yhi = y; } else { lo = mid; ylo = y; } }
+    double fr = fdiv(samp - ylo, yhi - ylo);
+    if (!(fr == fr)) return 6;
+    fr = fmin(fmax(fr, 0.0), 1.0);
+    const double beta = (fr + (double)lo) * (PI / 180.0);
+    sincos(beta, &g.sb, &g.cb);
+    g.flip = xi2 > 0.5;                       // beta + pi  (:1589-1590)
+    if (g.flip) { g.sb = -g.sb; g.cb = -g.cb; }
+    const double c2b = g.cb * g.cb - g.sb * g.sb, s2b = 2.0 * g.sb * g.cb;
+    const double w1 = S[0], w2 = c2b * S[1] + s2b * S[2], w3 = c2b * S[2] - s2b * S[1], w4 = S[3];
+    const double2* tab = reinterpret_cast<const double2*>(T.cdfP + (size_t)u * (181 * 4));
+    auto cumP = [&](int i) {
+        double2 q01 = __ldg(tab + 2 * i), q23 = __ldg(tab + 2 * i + 1);
+        return w1 * q01.x + w2 * q01.y + w3 * q23.x + w4 * q23.y;
+    };
+    yhi = cumP(180); ylo = 0.0;
+    samp = xi3 * yhi;
+    lo = 0; hi = 180;
+#pragma unroll 1
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; double y = cumP(mid); if (y >= samp) { hi = mid; yhi = y; } else { lo = mid; ylo = y; } }
+    fr = fdiv(samp - ylo, yhi - ylo);
+    if (!(fr == fr)) return 7;
+    fr = fmin(fmax(fr, 0.0), 1.0);
+    g.deg = fr + (double)lo;
+    sincos(g.deg * (PI / 180.0), &g.sT, &g.alpha);
+    if (g.alpha >= 1.0) { g.alpha = 1.0 - 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
+    if (g.alpha <= -1.0) { g.alpha = -1.0 + 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
+    return 0;
 }
 
 struct Cnt {
@@ -305,7 +384,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     const int ci = c0 + T.nr * (c1 + T.nt * c2);
     double dx = X.D(F_DX, s), dy = X.D(F_DY, s), dz = X.D(F_DZ, s);
-    const double tpos = X.D(F_T, s) + (X.D(F_TAU, s) - X.D(F_ACC, s)) / __ldg(T.kext + ci);
+    const double tpos = X.D(F_T, s) + fdiv(X.D(F_TAU, s) - X.D(F_ACC, s), __ldg(T.kext + ci));
     const double px = X.D(F_PX, s) + tpos * dx, py = X.D(F_PY, s) + tpos * dy, pz = X.D(F_PZ, s) + tpos * dz;
     double S[4] = {X.D(F_S0, s), X.D(F_S1, s), X.D(F_S2, s), X.D(F_S3, s)};
     const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
@@ -315,7 +394,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     if (alive) { const double xi = dr.get(0); ++nd; if (xi < L.fstop) alive = false; }
     if (alive) {
         const double alb = __ldg(T.albedo + ci);
-        if (alb < 1.0 && alb > 0.0) { const double g = alb / (1.0 - L.fstop); S[0] *= g; S[1] *= g; S[2] *= g; S[3] *= g; }
+        if (alb < 1.0 && alb > 0.0) { const double g = fdiv(alb, 1.0 - L.fstop); S[0] *= g; S[1] *= g; S[2] *= g; S[3] *= g; }
         if (S[0] <= L.photon_minimum) alive = false;
     }
     if (!alive) { X.I(I_ND, s) = (int)nd; X.I(I_INFO, s) = K_DEAD; return true; }
@@ -330,26 +409,26 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
         matrix_at_deg(T, ci, acos(mu) * (180.0 / PI), F);
         if (!(fabs(dz) < 1.0)) err_count(A, 45);
         else {
-            const double smu = sqrt(1.0 - mu * mu);
-            double nc = (L.det[2] - dz * mu) / (smu * sqrt(1.0 - dz * dz));
+            const double smu = fsqrt(1.0 - mu * mu);
+            double nc = fdiv(L.det[2] - dz * mu, smu * fsqrt(1.0 - dz * dz));
             if (!(nc == nc)) err_count(A, 44);
             else {
                 nc = fmin(fmax(nc, -1.0), 1.0);
                 const double cr = dy * L.det[0] - dx * L.det[1];
                 const bool flip = (cr > 0.0) || (cr == 0.0 && dx * L.det[0] + dy * L.det[1] > 0.0);
                 const double c2a = 2.0 * nc * nc - 1.0;
-                double s2a = 2.0 * nc * sqrt(fmax(1.0 - nc * nc, 0.0));
+                double s2a = 2.0 * nc * fsqrt(fmax(1.0 - nc * nc, 0.0));
                 if (flip) s2a = -s2a;
-                const double nc2 = (dz - L.det[2] * mu) / (smu * sqrt(1.0 - L.det[2] * L.det[2]));
+                const double nc2 = fdiv(dz - L.det[2] * mu, smu * fsqrt(1.0 - L.det[2] * L.det[2]));
                 int soft = 0;
-                const int e = (fabs(L.det[2]) < 1.0) ? polrot_fast(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
+                const int e = (fabs(L.det[2]) < 1.0) ? polrot_f(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
                 if (e) err_count(A, e);
                 else if (!(W[0] > 0.0 && W[0] < 1.e100)) err_count(A, 53);
                 else {
                     const double x_im = py * L.cos_dp - px * L.sin_dp;
                     const double y_im = pz * L.sin_dt - py * L.cos_dt * L.sin_dp - px * L.cos_dt * L.cos_dp;
-                    const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
-                    const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
+                    const int ix = (int)fdiv(L.nx * (x_im + L.x_max), 2.0 * L.x_max) + 1;
+                    const int iy = (int)fdiv(L.ny * (y_im + L.y_max), 2.0 * L.y_max) + 1;
                     if (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) err_count(A, 60);
                     else pix = (ix - 1) + L.nx * (iy - 1);
                 }
@@ -361,21 +440,22 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     double tau = -1.0;                      // < 0: the photon dies after its peel-off has been deposited
     {
         FastAngles g;
-        int e = sample_angles_fast_xi(A, dr.get(1), dr.get(2), dr.get(3), S, ci, g);
+        int e = sample_angles_f(A, dr.get(1), dr.get(2), dr.get(3), S, ci, g);
         nd += (e == 6) ? 2u : 3u;
         double e0 = 0, e1 = 0, e2 = 0;
         if (!e) {
-            const double cto = dz / sqrt(dx * dx + dy * dy + dz * dz);
-            const double sto = sqrt(1.0 - cto * cto);
+            const double cto = fdiv(dz, fsqrt(dx * dx + dy * dy + dz * dz));
+            const double sto = fsqrt(1.0 - cto * cto);
             const double ctn = cto * g.alpha + sto * g.sT * g.cb;
-            const double stn = sqrt(1.0 - ctn * ctn);
-            double nc = (g.alpha - ctn * cto) / (stn * sto);
+            const double stn = fsqrt(1.0 - ctn * ctn);
+            double nc = fdiv(g.alpha - ctn * cto, stn * sto);
             if (!(nc == nc)) e = 20;
             else {
                 if (nc >= 1.0) nc = 1.0 - 1.e-10; else if (nc <= -1.0) nc = -1.0 + 1.e-10;
-                const double sD = sqrt(1.0 - nc * nc) * (g.flip ? -1.0 : 1.0);
-                const double rho = sqrt(dx * dx + dy * dy);
-                const double cph = rho > 0.0 ? dx / rho : 1.0, sph = rho > 0.0 ? dy / rho : 0.0;
+                const double sD = fsqrt(1.0 - nc * nc) * (g.flip ? -1.0 : 1.0);
+                const double rho = fsqrt(dx * dx + dy * dy);
+                const double irho = frcp(rho);
+                const double cph = rho > 0.0 ? dx * irho : 1.0, sph = rho > 0.0 ? dy * irho : 0.0;
                 e0 = stn * (cph * nc - sph * sD); e1 = stn * (sph * nc + cph * sD); e2 = ctn;
                 if (!(fabs(e2) < 1.0)) e = 16;
             }
@@ -383,9 +463,9 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
         if (!e) {
             double F[16], Sn[4];
             matrix_at_deg(T, ci, g.deg, F);
-            const double nc2 = (dz - e2 * g.alpha) / (g.sT * sqrt(1.0 - e2 * e2));
+            const double nc2 = fdiv(dz - e2 * g.alpha, g.sT * fsqrt(1.0 - e2 * e2));
             int soft = 0;
-            e = polrot_fast(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
+            e = polrot_f(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
             if (soft) err_count(A, soft);
             if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
         }
@@ -489,46 +569,156 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the kernel
+// block set-up and the marcher
+// ---------------------------------------------------------------------------------------------------
+template <int NT, int NP>
+__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP>& X, bool mark_empty) {
+    const DevTables& T = A.T;
+    const Lay lay(T.nr, T.nt, T.np, NP);
+    constexpr int RC = ShT<NP>::RC;
+    X.r = sm; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
+    X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
+    X.sd = sm + lay.o_sd;
+    X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
+    X.q = reinterpret_cast<short*>(X.si + NI_HOT * NP);
+    X.cold = A.O.scratch + (size_t)blockIdx.x * NP * REC;
+    X.head = reinterpret_cast<int*>(X.q + N_LISTS * RC);
+    X.tail = X.head + 8; X.misc = X.head + 16;
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= T.nr; i += NT) sm[i] = T.rfront[i];
+    for (int i = tid; i <= T.nt; i += NT) {
+        sm[lay.o_tf + i] = T.thetafront[i]; sm[lay.o_tt + i] = T.ttan[i];
+        reinterpret_cast<int*>(sm + lay.o_tp)[i] = T.tplane[i];
+    }
+    for (int i = tid; i < T.np; i += NT) { sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i]; }
+    if (mark_empty) for (int i = tid; i < N_LISTS * RC; i += NT) X.q[i] = (short)-1;
+    __syncthreads();
+    for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; }   // every slot starts by asking for a photon
+    if (tid < 8) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
+    if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; }
+    __syncthreads();
+}
+
+// list a ray goes on when it ends, by [kind][outcome]  (-1: it does not end)
+__constant__ signed char c_list[4][8] = {
+    //  NONE  LIMIT   EXIT    SURF    REST   RESP   ERR     DEAD
+    {-1, L_PRE, L_PRE, L_PRE, L_RES, L_RES, L_EMIT, L_EMIT},     // K_PRE
+    {-1, L_H, L_EMIT, L_EMIT, L_RES, L_RES, L_EMIT, L_EMIT},     // K_WALK
+    {-1, L_DEP, L_DEP, L_DEP, L_RES, L_RES, L_EMIT, L_EMIT},     // K_PEEL
+    {-1, L_EMIT, L_EMIT, L_EMIT, L_EMIT, L_EMIT, L_EMIT, L_EMIT} // K_DEAD
+};
+
+// A marcher lane: the ray it is stepping (24 registers) and one trip of it.
+struct Marcher {
+    int slot, c0, cbase, cell12, info;
+    double t, acc, tr, tt, tp, hbn, D0, iq, lim, kap;
+    int nr, nt, depth;           // launch invariants kept in registers (the kernel parameters live in constant memory)
+    const double* kext;
+
+    __device__ __forceinline__ void init(const DevTables& T) {
+        slot = -1; c0 = cbase = cell12 = info = 0;
+        t = acc = tr = tt = tp = hbn = D0 = iq = lim = kap = 0.0;
+        nr = T.nr; nt = T.nt; depth = T.cell_depth; kext = T.kext;
+    }
+
+    template <class Sh>
+    __device__ __forceinline__ void load(const Sh& X, int s) {
+        slot = s;
+        t = X.D(F_T, s); acc = X.D(F_ACC, s); tr = X.D(F_TR, s); tt = X.D(F_TT, s); tp = X.D(F_TP, s);
+        hbn = X.D(F_HBN, s); D0 = X.D(F_D0, s); iq = X.D(F_IQ, s); lim = X.D(F_LIM, s);
+        const int cell = X.I(I_CELL, s);
+        info = X.I(I_INFO, s);
+        c0 = cell & 1023; cell12 = cell & ~1023;
+        cbase = nr * (((cell >> 10) & 1023) + nt * ((cell >> 20) & 1023));
+        kap = __ldg(kext + cbase + c0);
+    }
+
+    // One trip: advance to the next crossing.  Returns the event list the slot has to go on if the ray ended
+    // (its state is then written back to the slot), else -1.
+    template <class Sh>
+    __device__ __forceinline__ int trip(const Sh& X, const KernelArgs& A, Cnt& C) {
+        const int kind = info & 3;
+        int out = O_NONE;
+        double tn = tr; int ax = 0;
+        if (tt < tn) { tn = tt; ax = 1; }
+        if (tp < tn) { tn = tp; ax = 2; }
+        if (kind == K_DEAD) out = O_DEAD;
+        else {
+            ++C.n_cf;
+            const double dtau = (tn - t) * kap;
+#ifdef E2_DEBUG
+            if (!(tn >= t) || !(kap >= 0.0)) printf("E2 marcher: slot %d kind %d ax %d t %.17g tn %.17g tr %.17g tt %.17g tp %.17g kap %g c0 %d cell12 %x info %x\n", slot, kind, ax, t, tn, tr, tt, tp, kap, c0, cell12, info);
+#endif
+            if (!(tn < RAY_NONE)) out = O_ERR;
+            else if (kind == K_WALK && acc + dtau > lim) out = O_LIMIT;
+            else {
+                acc += dtau; t = tn;
+                if (ax == 0) {
+                    const bool inward = (info & B_INWARD) != 0;
+                    const int f = inward ? c0 : c0 + 1;
+                    if (f == nr) out = O_EXIT;
+                    else if (f == depth) out = O_SURF;
+                    else {
+                        c0 += inward ? -1 : 1;
+                        kap = __ldg(kext + cbase + c0);
+                        // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
+                        bool in2 = inward;
+                        double r = X.r[in2 ? c0 : c0 + 1], disc = fma(r * r, iq, D0);
+                        if (in2 && disc < 0.0) { in2 = false; info &= ~B_INWARD; r = X.r[c0 + 1]; disc = fma(r * r, iq, D0); }
+                        const double sq = fsqrt(fmax(disc, 0.0));
+                        tr = in2 ? hbn - sq : hbn + sq;
+                        if (disc < 0.0) tr = RAY_NONE;
+                    }
+                } else out = (ax == 1) ? O_REST : O_RESP;
+            }
+        }
+        if (out == O_NONE) return -1;
+        X.D(F_T, slot) = t; X.D(F_ACC, slot) = acc; X.D(F_TR, slot) = tr;   // (tr: a re-solved ray goes on)
+        X.I(I_CELL, slot) = cell12 | c0;
+        X.I(I_INFO, slot) = (info & 0xff) | (out << 8);
+        if (out == O_ERR) {
+            err_count(A, 31); ++C.n_err;
+            err_count(A, kind == K_PRE ? 2 : (kind == K_WALK ? 3 : 43));
+        } else if (out == O_SURF && kind == K_WALK) { ++C.n_surf; X.I(I_ND, slot) += 1; }   // absorbed (:755-764: one draw)
+        return c_list[kind][out];
+    }
+};
+
+template <class Sh>
+__device__ __forceinline__ bool run_event(const Sh& X, const KernelArgs& A, int l, bool valid, int s, Cnt& C) {
+    if (l == L_H) return ev_interact(X, A, valid, s, C);
+    if (l == L_DEP) return ev_deposit(X, A, valid, s, C);
+    if (l == L_RES) return ev_resolve(X, A, valid, s);
+    if (l == L_PRE) return ev_pre(X, A, valid, s, C);
+    return ev_emit(X, A, valid, s, C);
+}
+
+__device__ __forceinline__ void flush_counters(const KernelArgs& A, const Cnt& C) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long v[7] = {C.n_emit, C.n_cf, C.n_sc, C.n_peel, C.n_surf, C.n_draw, C.n_err};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+        if (lane == 0 && x) atomicAdd(A.O.stats + k, x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel A: bulk-synchronous rounds (marcher phase of `trips` trips | barrier | event phase | barrier)
 // ---------------------------------------------------------------------------------------------------
 template <int NT, int NP, int MINB>
 __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
-    const Lay lay(T.nr, T.nt, T.np, NP);
     using Sh = ShT<NP>;
-    constexpr int RC = Sh::RC;
     Sh X;
-    {
-        double* sm = smraw;
-        X.r = sm; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
-        X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
-        X.sd = sm + lay.o_sd;
-        X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
-        X.q = reinterpret_cast<short*>(X.si + NI_HOT * NP);
-        X.cold = A.O.scratch + (size_t)blockIdx.x * NP * REC;
-        X.head = reinterpret_cast<int*>(X.q + N_LISTS * RC);
-        X.tail = X.head + 8; X.misc = X.head + 16;
-        const int tid = threadIdx.x;
-        for (int i = tid; i <= T.nr; i += NT) sm[i] = T.rfront[i];
-        for (int i = tid; i <= T.nt; i += NT) {
-            sm[lay.o_tf + i] = T.thetafront[i]; sm[lay.o_tt + i] = T.ttan[i];
-            reinterpret_cast<int*>(sm + lay.o_tp)[i] = T.tplane[i];
-        }
-        for (int i = tid; i < T.np; i += NT) { sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i]; }
-        for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; }
-        if (tid < 8) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
-        if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; }
-    }
-    __syncthreads();
+    block_setup<NT, NP>(A, smraw, X, false);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 16;      // marcher trips per round
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
-
-    // marcher state
-    int slot = -1, c0 = 0, cbase = 0, cell12 = 0, info = 0;
-    double t = 0, acc = 0, tr = 0, tt = 0, tp = 0, hbn = 0, D0 = 0, iq = 0, lim = 0, kap = 0;
+    Marcher M; M.init(T);
     volatile int* vhead = X.head;
     volatile int* vtail = X.tail;
 
@@ -536,7 +726,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
         // ================= marcher phase =================
         for (int trip = 0; trip < trips; ++trip) {
             // ---- free lanes claim ready rays
-            const unsigned fm = __ballot_sync(FULL, slot < 0);
+            const unsigned fm = __ballot_sync(FULL, M.slot < 0);
             if (fm && (vtail[L_RDY] - vhead[L_RDY]) > 0) {
                 int base = 0, n = 0;
                 if (lane == 0) {
@@ -552,74 +742,11 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
                 }
                 base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
                 const int rank = __popc(fm & lt);
-                if (slot < 0 && rank < n) {
-                    slot = X.Q(L_RDY, base + rank);
-                    t = X.D(F_T, slot); acc = X.D(F_ACC, slot); tr = X.D(F_TR, slot); tt = X.D(F_TT, slot); tp = X.D(F_TP, slot);
-                    hbn = X.D(F_HBN, slot); D0 = X.D(F_D0, slot); iq = X.D(F_IQ, slot); lim = X.D(F_LIM, slot);
-                    const int cell = X.I(I_CELL, slot);
-                    info = X.I(I_INFO, slot);
-                    c0 = cell & 1023; cell12 = cell & ~1023;
-                    cbase = T.nr * (((cell >> 10) & 1023) + T.nt * ((cell >> 20) & 1023));
-                    kap = __ldg(T.kext + cbase + c0);
-                }
+                if (M.slot < 0 && rank < n) M.load(X, X.Q(L_RDY, base + rank));
             }
             // ---- one trip
             int lst = -1;
-            if (slot >= 0) {
-                const int kind = info & 3;
-                int out = O_NONE;
-                double tn = tr; int ax = 0;
-                if (tt < tn) { tn = tt; ax = 1; }
-                if (tp < tn) { tn = tp; ax = 2; }
-                if (kind == K_DEAD) out = O_DEAD;
-                else if (!(tn < RAY_NONE)) { ++C.n_cf; out = O_ERR; }
-                else {
-                    ++C.n_cf;
-                    const double dtau = (tn - t) * kap;
-#ifdef E2_DEBUG
-                    if (!(tn >= t) || !(kap >= 0.0)) printf("E2 marcher: slot %d kind %d ax %d t %.17g tn %.17g tr %.17g tt %.17g tp %.17g kap %g c0 %d cell12 %x info %x\n", slot, kind, ax, t, tn, tr, tt, tp, kap, c0, cell12, info);
-#endif
-                    if (kind == K_WALK && acc + dtau > lim) out = O_LIMIT;
-                    else {
-                        acc += dtau; t = tn;
-                        if (ax == 0) {
-                            const bool inward = (info & B_INWARD) != 0;
-                            const int f = inward ? c0 : c0 + 1;
-                            if (f == T.nr) out = O_EXIT;
-                            else if (f == T.cell_depth) out = O_SURF;
-                            else {
-                                c0 += inward ? -1 : 1;
-                                kap = __ldg(T.kext + cbase + c0);
-                                // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
-                                bool in2 = inward;
-                                double r = X.r[in2 ? c0 : c0 + 1], disc = fma(r * r, iq, D0);
-                                if (in2 && disc < 0.0) { in2 = false; info &= ~B_INWARD; r = X.r[c0 + 1]; disc = fma(r * r, iq, D0); }
-                                const double sq = sqrt(fmax(disc, 0.0));
-                                tr = in2 ? hbn - sq : hbn + sq;
-                                if (disc < 0.0) tr = RAY_NONE;
-                            }
-                        } else out = (ax == 1) ? O_REST : O_RESP;
-                    }
-                }
-                if (out != O_NONE) {
-                    X.D(F_T, slot) = t; X.D(F_ACC, slot) = acc;
-                    if (out == O_REST || out == O_RESP) X.D(F_TR, slot) = tr;      // the ray goes on after the re-solve
-                    X.I(I_CELL, slot) = cell12 | c0;
-                    X.I(I_INFO, slot) = (info & 0xff) | (out << 8);
-                    if (out == O_REST || out == O_RESP) lst = L_RES;
-                    else if (out == O_DEAD) lst = L_EMIT;
-                    else if (out == O_ERR) {
-                        err_count(A, 31); ++C.n_err; lst = L_EMIT;
-                        err_count(A, kind == K_PRE ? 2 : (kind == K_WALK ? 3 : 43));
-                    } else if (kind == K_PRE) lst = L_PRE;
-                    else if (kind == K_PEEL) lst = L_DEP;
-                    else if (out == O_LIMIT) lst = L_H;
-                    else {   // the transport walk left the grid or was absorbed by the surface (:755-764: one draw)
-                        if (out == O_SURF) { ++C.n_surf; X.I(I_ND, slot) += 1; }
-                        lst = L_EMIT;
-                    }
-                }
-            }
+            if (M.slot >= 0) lst = M.trip(X, A, C);
             // ---- push finished rays on their event lists (one shared-memory atomic per list present in the warp)
             if (__any_sync(FULL, lst >= 0)) {
                 const unsigned g = __match_any_sync(FULL, lst);
@@ -627,7 +754,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
                 int base = 0;
                 if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
                 base = __shfl_sync(FULL, base, leader);
-                if (lst >= 0) { X.Q(lst, base + __popc(g & lt)) = (short)slot; slot = -1; }
+                if (lst >= 0) { X.Q(lst, base + __popc(g & lt)) = (short)M.slot; M.slot = -1; }
             }
         }
         __syncthreads();
@@ -655,12 +782,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
                 const bool valid = idx < m[k];
                 const int l = order[k];
                 const int s = valid ? (int)X.Q(l, hd[k] + idx) : 0;
-                bool push;
-                if (l == L_H) push = ev_interact(X, A, valid, s, C);
-                else if (l == L_DEP) push = ev_deposit(X, A, valid, s, C);
-                else if (l == L_RES) push = ev_resolve(X, A, valid, s);
-                else if (l == L_PRE) push = ev_pre(X, A, valid, s, C);
-                else push = ev_emit(X, A, valid, s, C);
+                const bool push = run_event(X, A, l, valid, s, C);
                 const unsigned pm = __ballot_sync(FULL, push);
                 if (pm) {
                     const int leader = __ffs(pm) - 1;
@@ -679,16 +801,124 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
         }
         if (X.misc[0] >= NP) break;
     }
-    // counters
-    {
-        unsigned long long v[7] = {C.n_emit, C.n_cf, C.n_sc, C.n_peel, C.n_surf, C.n_draw, C.n_err};
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            unsigned long long x = v[k];
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-            if (lane == 0 && x) atomicAdd(A.O.stats + k, x);
+    flush_counters(A, C);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel B: asynchronous.  No block barrier after set-up: every warp loops  claim rays -> one trip -> push
+// ended rays -> if some event list holds a full batch, take it and run it.  List entries are published
+// through the ring cell itself (-1 = empty): a producer reserves a position with an atomic on `tail`, fences
+// its slot writes and stores the slot id; a consumer reserves positions with a CAS on `head`, waits for the
+// id to appear, clears the cell and fences before touching the slot.  A warp with (almost) nothing to march
+// and no ready ray to claim also takes partial batches, which is what drains the lists at the end.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ring_take(volatile short* e) {
+    short v;
+    do { v = *e; } while (v < 0);
+    *e = (short)-1;
+    return (int)v;
+}
+__device__ __forceinline__ void ring_put(volatile short* e, int s) {
+    while (*e >= 0) { }
+    *e = (short)s;
+}
+
+template <int NT, int NP, int MINB>
+__global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_constant__ KernelArgs A) {
+    extern __shared__ double smraw[];
+    const DevTables& T = A.T;
+    using Sh = ShT<NP>;
+    Sh X;
+    block_setup<NT, NP>(A, smraw, X, true);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
+    Marcher M; M.init(T);
+    volatile int* vhead = X.head;
+    volatile int* vtail = X.tail;
+    volatile int* vmisc = X.misc;
+    const int starve = A.L.e2_trips > 0 ? A.L.e2_trips : 8;     // take partial batches when fewer lanes than this march
+
+    for (;;) {
+        if (vmisc[0] >= NP) break;
+        // ---- free lanes claim ready rays
+        const unsigned fm = __ballot_sync(FULL, M.slot < 0);
+        bool rdy_empty = false;
+        if (fm) {
+            int base = 0, n = 0;
+            if (lane == 0) {
+                const int want = __popc(fm);
+                int h = vhead[L_RDY];
+                for (;;) {
+                    n = min(want, vtail[L_RDY] - h);
+                    if (n <= 0) { n = 0; break; }
+                    const int old = atomicCAS(X.head + L_RDY, h, h + n);
+                    if (old == h) { base = h; break; }
+                    h = old;
+                }
+            }
+            base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
+            rdy_empty = n < __popc(fm);
+            const int rank = __popc(fm & lt);
+            if (M.slot < 0 && rank < n) {
+                const int s = ring_take(&X.Q(L_RDY, base + rank));
+                __threadfence_block();
+                M.load(X, s);
+            }
+        }
+        // ---- one trip
+        int lst = -1;
+        if (M.slot >= 0) lst = M.trip(X, A, C);
+        // ---- push ended rays on their event lists
+        if (__any_sync(FULL, lst >= 0)) {
+            __threadfence_block();
+            const unsigned g = __match_any_sync(FULL, lst);
+            const int leader = __ffs(g) - 1;
+            int base = 0;
+            if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
+            base = __shfl_sync(FULL, base, leader);
+            if (lst >= 0) { ring_put(&X.Q(lst, base + __popc(g & lt)), M.slot); M.slot = -1; }
+        }
+        // ---- events: a full batch if there is one; a partial one if this warp has little else to do
+        int av = 0;
+        if (lane < 5) av = vtail[lane] - vhead[lane];
+        const unsigned fullm = __ballot_sync(FULL, av >= 32);
+        const unsigned anym = __ballot_sync(FULL, av > 0);
+        const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
+        int l = -1;
+        // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
+        if (fullm) l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
+                       : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
+        else if (anym && rdy_empty && nactive < starve)
+            l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_DEP)) ? L_DEP : (anym & (1u << L_H)) ? L_H
+                : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
+        if (l >= 0) {
+            int base = 0, n = 0;
+            if (lane == 0) {
+                const int h = vhead[l];
+                n = min(32, vtail[l] - h);
+                if (n > 0 && atomicCAS(X.head + l, h, h + n) == h) base = h; else n = 0;
+            }
+            base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
+            if (n > 0) {
+                const bool valid = lane < n;
+                int s = 0;
+                if (valid) s = ring_take(&X.Q(l, base + lane));
+                __threadfence_block();
+                const bool push = run_event(X, A, l, valid, s, C);
+                __threadfence_block();
+                const unsigned pm = __ballot_sync(FULL, push);
+                if (pm) {
+                    const int leader = __ffs(pm) - 1;
+                    int pb = 0;
+                    if (lane == leader) pb = atomicAdd(X.tail + L_RDY, __popc(pm));
+                    pb = __shfl_sync(FULL, pb, leader);
+                    if (push) ring_put(&X.Q(L_RDY, pb + __popc(pm & lt)), s);
+                }
+            }
         }
     }
+    flush_counters(A, C);
 }
 
 }  // namespace e2

@@ -9,6 +9,7 @@ namespace artes {
 struct DevTables {
     int nr, nt, np, cells, cell_depth, n_uniq;
     double ox, oy, oz;               // oblate_x/y/z (:42)
+    double inv_ox, inv_oy, inv_oz;   // their reciprocals (a, b, c of :2838-2840)
     const double* rfront;            // [nr+1]           (:58)
     const double* thetafront;        // [nt+1] rad       (:59)
     const double* ttan;              // [nt+1] theta_grid_tan (:77)

@@ -520,6 +520,39 @@ __device__ __forceinline__ int sample_angles(const double* __restrict__ sm, cons
 
 #if !ARTES_FAITHFUL
 // ---------------------------------------------------------------------------------------------
+// Fast-mode reciprocal, division and square root: MUFU seed (20 bits) + two Newton / Goldschmidt steps,
+// without the IEEE special-case paths of div.rn.f64 / sqrt.rn.f64 (~25 / ~21 instructions each).  Results are
+// within an ulp or two for normal operands; a zero or infinite operand gives NaN where IEEE gives inf/0, so
+// callers guard those cases exactly where the reference's logic depends on them.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double frcp(double b) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(b));
+    double e = fma(-b, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-b, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ __forceinline__ double fdiv(double a, double b) {
+    const double x = frcp(b);
+    const double q = a * x;
+    return fma(fma(-b, q, a), x, q);
+}
+__device__ __forceinline__ double fsqrt(double a) {   // a >= 0
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    g = fma(fma(-g, g, a), h, g);
+    return (a > 0.0) ? g : 0.0;
+}
+#endif
+
+#if !ARTES_FAITHFUL
+// ---------------------------------------------------------------------------------------------
 // Fast-mode event math.  Same formulas as the reference's spherical trigonometry, with every
 // acos/cos/atan2 round trip replaced by its algebraic identity:
 //   mueller(psi) == (cos 2psi, sin 2psi)                       (src/ARTES.f90:1942-1953 is the sign of sin 2psi)
@@ -614,52 +647,6 @@ __device__ __forceinline__ int sample_angles_fast(const KernelArgs& A, Rng& rng,
     xi = rng_next<TRACE>(rng, A);
     yhi = cumP(180); ylo = 0.0;
     samp = xi * yhi;
-    lo = 0; hi = 180;
-#pragma unroll 1
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; double y = cumP(mid); if (y >= samp) { hi = mid; yhi = y; } else { lo = mid; ylo = y; } }
-    fr = (samp - ylo) / (yhi - ylo);
-    if (!(fr == fr)) return 7;
-    fr = fmin(fmax(fr, 0.0), 1.0);
-    g.deg = fr + (double)lo;
-    sincos(g.deg * (PI / 180.0), &g.sT, &g.alpha);
-    if (g.alpha >= 1.0) { g.alpha = 1.0 - 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
-    if (g.alpha <= -1.0) { g.alpha = -1.0 + 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
-    return 0;
-}
-#endif
-
-#if !ARTES_FAITHFUL
-// sample_angles_fast with the three random numbers supplied by the caller (engine2: stateless Philox draws)
-__device__ __forceinline__ int sample_angles_fast_xi(const KernelArgs& A, double xi1, double xi2, double xi3, const double S[4],
-                                                     int cellidx, FastAngles& g) {
-    const DevTables& T = A.T;
-    const int u = __ldg(T.c2u + cellidx);
-    const double p11 = __ldg(T.p1k + 4 * u), p12 = __ldg(T.p1k + 4 * u + 1), p13 = __ldg(T.p1k + 4 * u + 2), p14 = __ldg(T.p1k + 4 * u + 3);
-    const double Ac = p11 * S[0] + p14 * S[3], Bc = p12 * S[1] + p13 * S[2], Cc = p12 * S[2] - p13 * S[1];
-    const double* pc2 = T.cdfA;
-    const double* ps2 = T.cdfA + 181;
-    auto cumA = [&](int i) { return Ac * (double)i + Bc * __ldg(pc2 + i) + Cc * __ldg(ps2 + i); };
-    double samp = xi1 * cumA(180);
-    int lo = 0, hi = 180;  // smallest i in 1..180 with cum(i) >= samp
-    double ylo = 0.0, yhi = cumA(180);
-#pragma unroll 1
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; double y = cumA(mid); if (y >= samp) { hi = mid; yhi = y; } else { lo = mid; ylo = y; } }
-    double fr = (samp - ylo) / (yhi - ylo);
-    if (!(fr == fr)) return 6;
-    fr = fmin(fmax(fr, 0.0), 1.0);
-    const double beta = (fr + (double)lo) * (PI / 180.0);
-    sincos(beta, &g.sb, &g.cb);
-    g.flip = xi2 > 0.5;                       // beta + pi  (:1589-1590)
-    if (g.flip) { g.sb = -g.sb; g.cb = -g.cb; }
-    const double c2b = g.cb * g.cb - g.sb * g.sb, s2b = 2.0 * g.sb * g.cb;
-    const double w1 = S[0], w2 = c2b * S[1] + s2b * S[2], w3 = c2b * S[2] - s2b * S[1], w4 = S[3];
-    const double2* tab = reinterpret_cast<const double2*>(T.cdfP + (size_t)u * (181 * 4));
-    auto cumP = [&](int i) {
-        double2 q01 = __ldg(tab + 2 * i), q23 = __ldg(tab + 2 * i + 1);
-        return w1 * q01.x + w2 * q01.y + w3 * q23.x + w4 * q23.y;
-    };
-    yhi = cumP(180); ylo = 0.0;
-    samp = xi3 * yhi;
     lo = 0; hi = 180;
 #pragma unroll 1
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; double y = cumP(mid); if (y >= samp) { hi = mid; yhi = y; } else { lo = mid; ylo = y; } }
