@@ -79,10 +79,45 @@ std::string card(const char* key, const std::string& value, bool quoted = false)
 }  // namespace
 
 bool fits_read(const std::string& path, std::vector<FitsImage>& hdus, std::string& err) {
+    return fits_read_upto(path, 1 << 30, hdus, err);
+}
+
+FitsSlab::~FitsSlab() { if (file_) std::fclose(static_cast<FILE*>(file_)); }
+
+bool FitsSlab::open(const std::string& path, int hdu_index, std::string& err) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) { err = "cannot open " + path; return false; }
+    for (int i = 0;; ++i) {
+        Header h;
+        if (!read_header(f, h)) { err = "HDU not found in " + path; std::fclose(f); return false; }
+        size_t n = h.naxes.empty() ? 0 : 1;
+        for (long a : h.naxes) n *= (size_t)a;
+        const size_t bytes = n * elem_bytes(h.bitpix);
+        if (i == hdu_index) {
+            file_ = f; data_start_ = ftello(f); bitpix_ = h.bitpix; elems = n; naxes = h.naxes;
+            return true;
+        }
+        if (fseeko(f, (off_t)(bytes + (BLOCK - bytes % BLOCK) % BLOCK), SEEK_CUR) != 0) { err = "seek failed"; std::fclose(f); return false; }
+    }
+}
+
+bool FitsSlab::read(size_t elem_offset, size_t n, double* out, std::string& err) {
+    FILE* f = static_cast<FILE*>(file_);
+    const size_t eb = elem_bytes(bitpix_);
+    if (!f || elem_offset + n > elems) { err = "FitsSlab::read out of range"; return false; }
+    if (fseeko(f, (off_t)(data_start_ + (long long)(elem_offset * eb)), SEEK_SET) != 0) { err = "seek failed"; return false; }
+    raw_.resize(n * eb);
+    if (fread(raw_.data(), eb, n, f) != n) { err = "truncated FITS data"; return false; }
+    convert(raw_.data(), n, bitpix_, out);
+    return true;
+}
+
+bool fits_read_upto(const std::string& path, int n_hdus, std::vector<FitsImage>& hdus, std::string& err) {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) { err = "cannot open " + path; return false; }
     hdus.clear();
     for (;;) {
+        if ((int)hdus.size() >= n_hdus) break;
         Header h;
         if (!read_header(f, h)) break;
         FitsImage im;

@@ -23,6 +23,24 @@ struct FitsImage {
 // header but their pixels are not converted (used to look at the dense matrix HDU without loading it).
 bool fits_read(const std::string& path, std::vector<FitsImage>& hdus, std::string& err);
 
+// Same, but only the first `n_hdus` HDUs (atmosphere.fits: HDUs 0-7 are small, HDU 8 is the dense matrix array).
+bool fits_read_upto(const std::string& path, int n_hdus, std::vector<FitsImage>& hdus, std::string& err);
+
+// Random access to the elements of one image HDU (element offsets in FITS / Fortran order), for the matrix HDU:
+// a wavelength's slice is 2880 runs of `cells` contiguous values.
+struct FitsSlab {
+    ~FitsSlab();
+    bool open(const std::string& path, int hdu_index, std::string& err);
+    bool read(size_t elem_offset, size_t n, double* out, std::string& err);
+    size_t elems = 0;
+    std::vector<long> naxes;
+  private:
+    void* file_ = nullptr;
+    long long data_start_ = 0;
+    int bitpix_ = 0;
+    std::vector<unsigned char> raw_;
+};
+
 // Streams one HDU's pixels in chunks through a callback (for the 16.6 GB/wavelength matrix HDU).
 bool fits_read_hdu_chunked(const std::string& path, int hdu_index, size_t chunk_elems,
                            bool (*cb)(void* user, size_t offset, const double* vals, size_t n), void* user, std::string& err);

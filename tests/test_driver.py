@@ -1,0 +1,129 @@
+"""The C++ host driver bin/ARTES (src/host): same CLI / artes.in grammar / input tree / output files as the
+reference's `program artes` (src/ARTES.f90:4232-4517, :3472-3772).  CPU part: argument handling, keyword
+grammar, atmosphere.fits ingest (dry run, no GPU touched).  GPU part: a real run compared with the Python host
+mirror driving the same library."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from artes_b200 import abi, fitsio, host
+from tools import atmospheres as A
+from tools.make_input import write_input
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin", "ARTES")
+
+
+@pytest.fixture(scope="module")
+def driver():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "artes_b200", "csrc"), "-j4"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "src", "host")], stdout=subprocess.DEVNULL)
+    assert os.path.exists(BIN)
+    return BIN
+
+
+def run(driver, cwd, *args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([driver, *args], cwd=cwd, env=e, capture_output=True, text=True, timeout=600)
+
+
+def test_usage_and_missing_input(driver, tmp_path):
+    r = run(driver, tmp_path)                         # :4242-4246: fewer than two arguments -> usage, exit(0)
+    assert r.returncode == 0 and "./bin/ARTES [inputDirectory] [photons] -o [outputDirectory] -k [keyWord]=[value]" in r.stdout
+    r = run(driver, tmp_path, "nothing", "1e3", "-o", "x")
+    assert r.returncode == 0 and "Input file does not exist!" in r.stdout     # :374-378
+
+
+def test_keyword_grammar_and_overrides(driver, tmp_path, atmospheres):
+    atm = atmospheres("c1_template_rayleigh")
+    write_input(atm, "tmpl", root=str(tmp_path))
+    dry = {"ARTES_DRYRUN": "1"}
+    r = run(driver, tmp_path, "tmpl", "1e6", "-o", "o1", env=dry)
+    assert r.returncode == 0, r.stderr
+    assert "photons=1000000" in r.stdout and "grid nr=2 ntheta=7 nphi=1 nlambda=1" in r.stdout
+    assert "type=imaging_mono" in r.stdout and "pixels=25" in r.stdout and "fstop=1e-05" in r.stdout     # 1d-5 (Fortran exponent)
+    # -k overrides artes.in (:4297-4303); detector angles are degrees in the file, radians inside (:4467-4474)
+    r = run(driver, tmp_path, "tmpl", "2.5e4", "-o", "o1", "-k", "detector:phi=45", "-k", "detector:pixel=64", "-k", "gpu:seed=7", env=dry)
+    assert "photons=25000" in r.stdout and "pixels=64" in r.stdout and "seed=7" in r.stdout
+    assert f"phi={math.radians(45.0):.6f}" in r.stdout
+    # phase curves force a 1x1 detector in the equatorial plane (:455-463)
+    r = run(driver, tmp_path, "tmpl", "1e4", "-o", "o1", "-k", "detector:type=phase", env=dry)
+    assert "pixels=1" in r.stdout
+    # unknown keyword: message and exit(0) like the reference (:4494-4496)
+    r = run(driver, tmp_path, "tmpl", "1e4", "-o", "o1", "-k", "photon:colour=blue", env=dry)
+    assert r.returncode == 0 and "Wrong keyword found in input file" in r.stdout
+    # comment lines (* - =) and blank lines are skipped (:390)
+    with open(tmp_path / "input" / "tmpl" / "artes.in", "a") as f:
+        f.write("\n* a comment\n----\n====\nplanet:oblateness=0.05\n")
+    r = run(driver, tmp_path, "tmpl", "1e4", "-o", "o1", env=dry)
+    assert "oblateness=0.05" in r.stdout
+
+
+def test_driver_fails_loudly_without_gpu(driver, tmp_path, atmospheres):
+    import ctypes
+    try:
+        has_gpu = ctypes.CDLL("libcuda.so.1").cuInit(0) == 0
+    except OSError:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    write_input(atmospheres("c1_template_rayleigh"), "tmpl", root=str(tmp_path))
+    r = run(driver, tmp_path, "tmpl", "1e3", "-o", "o1")
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def _read_table(path):
+    rows = [l.split() for l in open(path) if l.strip() and not l.lstrip().startswith("#")]
+    return np.array(rows, dtype=float)
+
+
+@pytest.mark.gpu
+def test_driver_imaging_mono_matches_python_host(driver, tmp_path, atmospheres):
+    atm = atmospheres("c1_template_rayleigh")
+    write_input(atm, "c1", root=str(tmp_path))
+    n = 200000
+    r = run(driver, tmp_path, "c1", str(n), "-o", "run1", "-k", "detector:phi=60", "-k", "gpu:seed=5")
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = tmp_path / "output" / "run1"
+    for f in ("input/artes.in", "input/atmosphere.fits", "plot.dat", "error.log", "output/stokes.fits", "output/error.fits",
+              "output/photometry.dat", "output/normalization.dat", "output/cell_depth.dat"):
+        assert (out / f).exists(), f
+    assert "detector:phi=60" in open(out / "input" / "artes.in").read()      # -k appended to the copied artes.in
+    stokes = fitsio.read_hdus(str(out / "output" / "stokes.fits"))[0][1]
+    err = fitsio.read_hdus(str(out / "output" / "error.fits"))[0][1]
+    assert stokes.shape == (4, 25, 25) and err.shape == (5, 25, 25)
+    p = host.Params(det_phi=math.radians(60.0))
+    t = host.Transport(atm, p, mode=abi.MODE_FAST)
+    det, phot, _ = t.radiative_transfer(n, seed=5)
+    x_fov = 2.0 * math.atan(t.x_max / p.distance_planet) * 3600.0 * 180.0 / math.pi * 1000.0
+    img = det[0] * 1e-6 / (x_fov / 25) ** 2
+    np.testing.assert_allclose(stokes, img, rtol=1e-9, atol=1e-12 * np.abs(img).max())
+    np.testing.assert_allclose(err, host.stokes_error(det), rtol=1e-6, atol=1e-9 * np.abs(err).max())
+    tab = _read_table(out / "output" / "photometry.dat")
+    np.testing.assert_allclose(tab[0, 0], atm.wavelengths[0], rtol=1e-12)
+    np.testing.assert_allclose(tab[0, 1:9], 1e-6 * phot[:8], rtol=1e-9, atol=1e-30)
+    t.close()
+
+
+@pytest.mark.gpu
+def test_driver_phase_curve_and_spectrum(driver, tmp_path, atmospheres):
+    write_input(atmospheres("c2_hg_deck"), "c2", root=str(tmp_path))
+    r = run(driver, tmp_path, "c2", "20000", "-o", "ph", "-k", "detector:type=phase")
+    assert r.returncode == 0, r.stdout + r.stderr
+    ph = _read_table(tmp_path / "output" / "ph" / "output" / "phase.dat")
+    assert ph.shape == (73, 9) and ph[0, 0] == 0.0 and ph[-1, 0] == 180.0 and abs(ph[1, 0] - 2.5) < 1e-9     # :215-245
+    assert (ph[:, 1] > 0).all() and ph[0, 1] > 5 * ph[-1, 1]          # bright at full phase, faint near new phase
+    assert len(_read_table(tmp_path / "output" / "ph" / "output" / "normalization.dat")) == 1                # only at phase 0 (:3631)
+    atm3 = A.c3_molecular(nr=30, nl=4)
+    write_input(atm3, "c3", root=str(tmp_path))
+    r = run(driver, tmp_path, "c3", "20000", "-o", "sp", "-k", "detector:type=spectrum")
+    assert r.returncode == 0, r.stdout + r.stderr
+    sp = _read_table(tmp_path / "output" / "sp" / "output" / "spectrum.dat")
+    assert sp.shape == (4, 5)
+    np.testing.assert_allclose(sp[:, 0], atm3.wavelengths, rtol=1e-12)
+    assert (sp[:, 1] > 0).all()
+    assert _read_table(tmp_path / "output" / "sp" / "output" / "optical_depth.dat").shape == (4, 4)

@@ -184,6 +184,50 @@ def test_same_stream_images_agree(atmospheres, oracle_factory, gpu_factory, name
     np.testing.assert_allclose(b["flow3"], a["flow3"], rtol=1e-6, atol=1e-3 * np.abs(a["flow3"]).max())
 
 
+# The fast mode's production path is the ray/event engine (artes_b200/csrc/engine2.cuh): star source, black
+# surface, no flow counters.  Same Philox stream and draw order as the oracle, so the trajectories agree to
+# rounding: identical event counts up to the odd threshold decision that falls within an ulp, images to ~1e-5.
+E2_CASES = [
+    ("c1_template_rayleigh", dict(), 60000),
+    ("c2_hg_deck", dict(nx=1, ny=1, det_phi=math.radians(140.0)), 60000),
+    ("c2_hg_deck", dict(nx=8, ny=8, limb_emission=1, det_phi=math.radians(175.0)), 30000),
+    ("c3_molecular", dict(nx=1, ny=1), 20000),
+    ("c4_mie_patches", dict(nx=64, ny=64, det_phi=math.radians(60.0)), 60000),
+    ("c4_mie_patches", dict(nx=16, ny=16, stellar_direction=1, theta_star=math.radians(70.0), phi_star=math.radians(33.0)), 30000),
+    ("c5_scale", dict(nx=64, ny=64, det_phi=math.radians(60.0)), 8000),
+]
+
+
+@pytest.mark.parametrize("name,kw,n", E2_CASES)
+def test_ray_event_engine_same_stream_vs_oracle(atmospheres, oracle_factory, gpu_factory, name, kw, n):
+    atm = atmospheres(name)
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(mode=abi.MODE_FAST, n_photons=n, x_max=xm, y_max=xm, seed=33, **kw)
+    a, b = o.run(L), g.run(L)
+    for k in ("n_emit", "n_cell_face", "n_scatter", "n_peel", "n_surface", "n_draws"):
+        assert abs(a["stats"][k] - b["stats"][k]) <= max(2, 2e-5 * a["stats"][k]), (k, a["stats"][k], b["stats"][k])
+    assert b["stats"]["n_error"] <= a["stats"]["n_error"] + 2
+    assert np.abs(a["det"][2] - b["det"][2]).sum() <= max(4, 2e-5 * a["det"][2].sum())
+    scale = np.abs(a["det"][0]).max()
+    same = a["det"][2] == b["det"][2]
+    np.testing.assert_allclose(b["det"][0][same], a["det"][0][same], rtol=2e-4, atol=1e-6 * scale)
+    np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=2e-5, atol=1e-7 * scale)
+    np.testing.assert_allclose(b["det"][1].sum(axis=(1, 2)), a["det"][1].sum(axis=(1, 2)), rtol=2e-4, atol=1e-9 * scale * scale)
+
+
+def test_ray_event_engine_oblate_planet(atmospheres):
+    atm = atmospheres("c4_mie_patches")
+    o, g = oblate_pair(atm, 0.06)
+    xm = 1.06 * 1.3 * atm.rfront[-1]
+    L = make_launch(mode=abi.MODE_FAST, n_photons=40000, x_max=xm, y_max=xm, seed=9, nx=32, ny=32, det_phi=math.radians(100.0))
+    a, b = o.run(L), g.run(L)
+    assert abs(a["stats"]["n_cell_face"] - b["stats"]["n_cell_face"]) <= max(2, 2e-5 * a["stats"]["n_cell_face"])
+    assert a["stats"]["n_scatter"] == b["stats"]["n_scatter"] or abs(a["stats"]["n_scatter"] - b["stats"]["n_scatter"]) <= 3
+    np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=2e-5, atol=1e-9)
+
+
 def batch_z(batches_a, batches_b, min_count=30):
     """Per-pixel z score of two sets of independent batches.  The noise is the variance ACROSS batches:
     the reference's own error estimate (src/ARTES.f90:3490-3493, variance of the deposits about their mean)
