@@ -102,7 +102,8 @@ def test_driver_imaging_mono_matches_python_host(driver, tmp_path, atmospheres):
     x_fov = 2.0 * math.atan(t.x_max / p.distance_planet) * 3600.0 * 180.0 / math.pi * 1000.0
     img = det[0] * 1e-6 / (x_fov / 25) ** 2
     np.testing.assert_allclose(stokes, img, rtol=1e-9, atol=1e-12 * np.abs(img).max())
-    np.testing.assert_allclose(err, host.stokes_error(det), rtol=1e-6, atol=1e-9 * np.abs(err).max())
+    # (single-deposit pixels: the variance is a rounding-level difference of two equal numbers)
+    np.testing.assert_allclose(err, host.stokes_error(det), rtol=1e-6, atol=1e-6 * np.abs(err).max())
     tab = _read_table(out / "output" / "photometry.dat")
     np.testing.assert_allclose(tab[0, 0], atm.wavelengths[0], rtol=1e-12)
     np.testing.assert_allclose(tab[0, 1:9], 1e-6 * phot[:8], rtol=1e-9, atol=1e-30)

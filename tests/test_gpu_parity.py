@@ -217,7 +217,8 @@ def test_ray_event_engine_same_stream_vs_oracle(atmospheres, oracle_factory, gpu
     np.testing.assert_allclose(b["det"][1].sum(axis=(1, 2)), a["det"][1].sum(axis=(1, 2)), rtol=2e-4, atol=1e-9 * scale * scale)
 
 
-def test_ray_event_engine_oblate_planet(atmospheres):
+def test_fast_mode_oblate_planet_same_stream(atmospheres):
+    """Oblate launches are outside the ray/event engine's scope (launchers.inc) and run on the persistent-lane engine."""
     atm = atmospheres("c4_mie_patches")
     o, g = oblate_pair(atm, 0.06)
     xm = 1.06 * 1.3 * atm.rfront[-1]
