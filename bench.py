@@ -165,7 +165,7 @@ def main():
     # ------------------------------------------------------------------ our arm (GPU)
     import torch
     import torch.distributed as dist
-    from artes_b200 import abi, host, lib
+    from artes_b200 import abi, host, dist as adist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
@@ -178,9 +178,7 @@ def main():
     params = host.Params(nx=wl_kw["nx"], ny=wl_kw["ny"], det_phi=math.radians(wl_kw["det_phi"]))
     t = host.Transport(atm, params, devices=(local_rank,), mode=mode)
     if world > 1:  # NCCL communicator of the library itself: the id travels through torch.distributed
-        obj = [lib.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        t.gpu.nccl_init_rank(world, rank, obj[0])
+        adist.init_library_comm(t.gpu, dist, rank, world)
     t.set_wavelength(0)
     peaks = t.gpu.fma_peak()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -191,7 +189,7 @@ def main():
         torch.cuda.synchronize()
 
     def step(i):
-        base = (i * world + rank) * P          # disjoint photon ids for every step and rank
+        base = adist.step_base(i, world, rank, P)   # disjoint photon ids for every step and rank
         L = t.launch_struct(P, seed=4, photon_id_base=base)
         return t.gpu.run(L)
 
@@ -255,7 +253,8 @@ def main():
         hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            traffic = tr["dram_bytes_per_launch"] * P / tr["photons_per_launch"] if tr else None   # scaled to this launch size
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -266,9 +265,11 @@ def main():
                 "clocks": clocks,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
                              "frac": achieved / peaks["fp64_tflops"], "traffic": traffic,
-                             "note": "dominant kernel transport_kernel; algorithmic FP64 flop = exact event counters x "
-                                     "SURVEY 8d per-event figures; peak = FP64 FMA rate measured in this run by "
-                                     "artes_gpu_fma_peak (MEASURED_PEAKS.json holds no FP64 figure)",
+                             "note": "dominant kernel transport2_kernel (ray/event engine); this path is FP64-issue / latency bound, "
+                                     "not HBM or tensor bound: algorithmic FP64 flop = exact event counters x SURVEY 8d "
+                                     "per-event figures; peak = FP64 FMA rate measured in this run by artes_gpu_fma_peak "
+                                     "(MEASURED_PEAKS.json holds no FP64 figure); traffic = ncu dram bytes per launch of "
+                                     "the same workload (profiles/traffic.json)",
                              "flop_per_packet": fl / (world * args.steps * P), "fp32_peak_tflops": peaks["fp32_tflops"]},
                 "roofline_hbm": {"bound": "hbm", "achieved": per_launch_by / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": per_launch_by / k_s / 1e9 / hbm_peak,
