@@ -165,7 +165,8 @@ void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
     a.defer_events = defer_events; a.defer_refill = defer_refill;
     static const int e2_trips = env_int("ARTES_E2_TRIPS", 0);
     static const int e2_cfg = env_int("ARTES_E2_CFG", 32) & 31;      // block shape, see launch_transport2
-    a.e2_trips = e2_trips; a.e2_pad = e2_cfg;
+    static const int e2_inner = env_int("ARTES_E2_INNER", 0);
+    a.e2_trips = e2_trips; a.e2_pad = e2_cfg; a.e2_inner = e2_inner; a.e2_pad2 = 0;
     a.fstop = L.fstop; a.photon_minimum = L.photon_minimum; a.photon_bias = L.photon_bias;
     a.surface_albedo = L.surface_albedo; a.theta_star = L.theta_star; a.phi_star = L.phi_star;
     a.x_max = L.x_max; a.y_max = L.y_max;

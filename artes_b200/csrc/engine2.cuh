@@ -64,10 +64,10 @@ constexpr int REC = 20;       // doubles per cold record: 15 doubles + 5 ints, p
 __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c < np_slots) c <<= 1; return c; }
 
 struct Lay {
-    int o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_sd, n_tab;   // offsets in doubles
+    int o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_sd, n_tab;   // offsets in doubles
     size_t bytes;
     __host__ __device__ Lay(int nr, int nt, int np, int NP) {
-        o_tf = nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
+        o_r2 = nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
         o_tp = o_pf + np; o_sd = o_tp + (nt + 2) / 2 + 1; n_tab = o_sd;
         bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
     }
@@ -75,7 +75,7 @@ struct Lay {
 
 template <int NP>
 struct ShT {                     // pointers into the block's shared memory
-    const double* r; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
+    const double* r; const double* r2; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
     const int* tplane;
     double* sd; int* si; short* q; int* head; int* tail;
     int* misc;                   // [0] slots retired for good, [1] event batch counter, [2] ready-list tail at the end of the last event phase
@@ -358,7 +358,7 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
     X.D(F_S0, s) = 1.0; X.D(F_S1, s) = 0.0; X.D(F_S2, s) = 0.0; X.D(F_S3, s) = 0.0; X.D(F_TAU, s) = 0.0;
     X.I(I_ND, s) = (int)nd;
     X.I(I_HCELL, s) = pack_cell(c0, c1, c2) | (1 << 30);      // bit 30: the photon sits on the outer radial face
-    ray_setup(X, T, s, px, py, pz, dx, dy, dz, c0, c1, c2, T.nr, K_PRE, RAY_NONE);
+    ray_setup(X, T, s, px, py, pz, dx, dy, dz, c0, c1, c2, T.nr, K_PRE, CUDART_INF);
     return true;
 }
 
@@ -401,7 +401,8 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     const int ci = c0 + T.nr * (c1 + T.nt * c2);
     double dx = X.D(F_DX, s), dy = X.D(F_DY, s), dz = X.D(F_DZ, s);
-    const double tpos = X.D(F_T, s) + fdiv(X.D(F_TAU, s) - X.D(F_ACC, s), __ldg(T.kext + ci));
+    // the marcher stopped after adding the crossing that overshoots tau: step back by the overshoot (:705-720)
+    const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - X.D(F_TAU, s), __ldg(T.kext + ci));
     const double px = X.D(F_PX, s) + tpos * dx, py = X.D(F_PY, s) + tpos * dy, pz = X.D(F_PZ, s) + tpos * dz;
     double S[4] = {X.D(F_S0, s), X.D(F_S1, s), X.D(F_S2, s), X.D(F_S3, s)};
     const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
@@ -496,7 +497,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, X.D(F_TAU, s), X.D(F_ACC, s), X.D(F_T, s));
 #endif
     X.I(I_PIX, s) = pix; X.I(I_ND, s) = (int)nd; X.I(I_HCELL, s) = cell;
-    ray_setup(X, T, s, px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, RAY_NONE);
+    ray_setup(X, T, s, px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF);
     return true;
 }
 
@@ -593,7 +594,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     const DevTables& T = A.T;
     const Lay lay(T.nr, T.nt, T.np, NP);
     constexpr int RC = ShT<NP>::RC;
-    X.r = sm; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
+    X.r = sm; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
     X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
     X.sd = sm + lay.o_sd;
     X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
@@ -602,7 +603,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     X.head = reinterpret_cast<int*>(X.q + N_LISTS * RC);
     X.tail = X.head + 8; X.misc = X.head + 16;
     const int tid = threadIdx.x;
-    for (int i = tid; i <= T.nr; i += NT) sm[i] = T.rfront[i];
+    for (int i = tid; i <= T.nr; i += NT) { const double r = T.rfront[i]; sm[i] = r; sm[lay.o_r2 + i] = r * r; }
     for (int i = tid; i <= T.nt; i += NT) {
         sm[lay.o_tf + i] = T.thetafront[i]; sm[lay.o_tt + i] = T.ttan[i];
         reinterpret_cast<int*>(sm + lay.o_tp)[i] = T.tplane[i];
@@ -625,17 +626,21 @@ __constant__ signed char c_list[4][8] = {
     {-1, L_EMIT, L_EMIT, L_EMIT, L_EMIT, L_EMIT, L_EMIT, L_EMIT} // K_DEAD
 };
 
-// A marcher lane: the ray it is stepping (24 registers) and one trip of it.
+// A marcher lane: the ray it is stepping and one step of it.  The step is written for a short instruction stream:
+// every update is committed unconditionally (an interaction inside the cell is recognised by acc > lim AFTER the
+// crossing was added, and the event subtracts the overshoot), the radial direction is a +-1 register, the opacity
+// row pointer is kept, and the sphere radii come squared from shared memory.
 struct Marcher {
-    int slot, c0, cbase, cell12, info;
-    double t, acc, tr, tt, tp, hbn, D0, iq, lim, kap;
+    int slot, c0, dr, cell12, info;
+    double t, acc, tr, tt, tp, hbn, D0, iq, lim, kap, ds;
+    const double* kb;            // kext + nr*(c1 + nt*c2): the opacity row of the ray's (theta, phi) column
     int nr, nt, depth;           // launch invariants kept in registers (the kernel parameters live in constant memory)
     const double* kext;
 
     __device__ __forceinline__ void init(const DevTables& T) {
-        slot = -1; c0 = cbase = cell12 = info = 0;
-        t = acc = tr = tt = tp = hbn = D0 = iq = lim = kap = 0.0;
-        nr = T.nr; nt = T.nt; depth = T.cell_depth; kext = T.kext;
+        slot = -1; c0 = cell12 = info = 0; dr = 1;
+        t = acc = tr = tt = tp = hbn = D0 = iq = lim = kap = 0.0; ds = 1.0;
+        nr = T.nr; nt = T.nt; depth = T.cell_depth; kext = T.kext; kb = T.kext;
     }
 
     template <class Sh>
@@ -646,58 +651,61 @@ struct Marcher {
         const int cell = X.I(I_CELL, s);
         info = X.I(I_INFO, s);
         c0 = cell & 1023; cell12 = cell & ~1023;
-        cbase = nr * (((cell >> 10) & 1023) + nt * ((cell >> 20) & 1023));
-        kap = __ldg(kext + cbase + c0);
+        dr = (info & B_INWARD) ? -1 : 1; ds = (info & B_INWARD) ? -1.0 : 1.0;
+        kb = kext + nr * (((cell >> 10) & 1023) + nt * ((cell >> 20) & 1023));
+        kap = __ldg(kb + c0);
     }
 
-    // One trip: advance to the next crossing.  Returns the event list the slot has to go on if the ray ended
-    // (its state is then written back to the slot), else -1.
+    // One step: advance to the next crossing.  Returns the outcome (O_NONE: the ray goes on).
     template <class Sh>
-    __device__ __forceinline__ int trip(const Sh& X, const KernelArgs& A, Cnt& C) {
-        const int kind = info & 3;
-        int out = O_NONE;
-        double tn = tr; int ax = 0;
-        if (tt < tn) { tn = tt; ax = 1; }
-        if (tp < tn) { tn = tp; ax = 2; }
-        if (kind == K_DEAD) out = O_DEAD;
-        else {
-            ++C.n_cf;
-            const double dtau = (tn - t) * kap;
-#ifdef E2_DEBUG
-            if (!(tn >= t) || !(kap >= 0.0)) printf("E2 marcher: slot %d kind %d ax %d t %.17g tn %.17g tr %.17g tt %.17g tp %.17g kap %g c0 %d cell12 %x info %x\n", slot, kind, ax, t, tn, tr, tt, tp, kap, c0, cell12, info);
-#endif
-            if (!(tn < RAY_NONE)) out = O_ERR;
-            else if (kind == K_WALK && acc + dtau > lim) out = O_LIMIT;
-            else {
-                acc += dtau; t = tn;
-                if (ax == 0) {
-                    const bool inward = (info & B_INWARD) != 0;
-                    const int f = inward ? c0 : c0 + 1;
-                    if (f == nr) out = O_EXIT;
-                    else if (f == depth) out = O_SURF;
-                    else {
-                        c0 += inward ? -1 : 1;
-                        kap = __ldg(kext + cbase + c0);
-                        // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
-                        bool in2 = inward;
-                        double r = X.r[in2 ? c0 : c0 + 1], disc = fma(r * r, iq, D0);
-                        if (in2 && disc < 0.0) { in2 = false; info &= ~B_INWARD; r = X.r[c0 + 1]; disc = fma(r * r, iq, D0); }
-                        const double sq = fsqrt(fmax(disc, 0.0));
-                        tr = in2 ? hbn - sq : hbn + sq;
-                        if (disc < 0.0) tr = RAY_NONE;
-                    }
-                } else out = (ax == 1) ? O_REST : O_RESP;
-            }
+    __device__ __forceinline__ int step(const Sh& X, unsigned& n_cf) {
+        double tn = tr;
+        if (tt < tn) tn = tt;
+        if (tp < tn) tn = tp;
+        ++n_cf;
+        if (!(tn < RAY_NONE)) return O_ERR;
+        acc = fma(tn - t, kap, acc);
+        const bool radial = (tn == tr);
+        t = tn;
+        if (acc > lim) return O_LIMIT;          // lim = +inf for the probe walks
+        if (!radial) return (tn == tt) ? O_REST : O_RESP;
+        const int up = (dr > 0) ? 1 : 0;
+        const int f = c0 + up;
+        if (f == nr) return O_EXIT;
+        if (f == depth) return O_SURF;
+        c0 += dr;
+        kap = __ldg(kb + c0);
+        // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
+        double disc = fma(X.r2[c0 + up], iq, D0);
+        if (disc < 0.0) {
+            if (dr < 0) { dr = 1; ds = 1.0; disc = fma(X.r2[c0 + 1], iq, D0); }
+            if (disc < 0.0) { tr = RAY_NONE; return O_NONE; }
         }
-        if (out == O_NONE) return -1;
+        tr = fma(ds, fsqrt(disc), hbn);
+        return O_NONE;
+    }
+
+    // The ray ended with outcome `out`: write its state back to the slot; returns the event list the slot goes on.
+    template <class Sh>
+    __device__ __forceinline__ int finish(const Sh& X, const KernelArgs& A, Cnt& C, int out) {
+        const int kind = info & 3;
         X.D(F_T, slot) = t; X.D(F_ACC, slot) = acc; X.D(F_TR, slot) = tr;   // (tr: a re-solved ray goes on)
         X.I(I_CELL, slot) = cell12 | c0;
-        X.I(I_INFO, slot) = (info & 0xff) | (out << 8);
+        X.I(I_INFO, slot) = (info & 0xff & ~B_INWARD) | (dr < 0 ? B_INWARD : 0) | (out << 8);
         if (out == O_ERR) {
             err_count(A, 31); ++C.n_err;
             err_count(A, kind == K_PRE ? 2 : (kind == K_WALK ? 3 : 43));
         } else if (out == O_SURF && kind == K_WALK) { ++C.n_surf; X.I(I_ND, slot) += 1; }   // absorbed (:755-764: one draw)
         return c_list[kind][out];
+    }
+
+    template <class Sh>
+    __device__ __forceinline__ int trip(const Sh& X, const KernelArgs& A, Cnt& C) {
+        if ((info & 3) == K_DEAD) return finish(X, A, C, O_DEAD);
+        unsigned n = 0;
+        const int out = step(X, n);
+        C.n_cf += n;
+        return (out == O_NONE) ? -1 : finish(X, A, C, out);
     }
 };
 
@@ -724,7 +732,7 @@ __device__ __forceinline__ void flush_counters(const KernelArgs& A, const Cnt& C
 // ---------------------------------------------------------------------------------------------------
 // kernel A: bulk-synchronous rounds (marcher phase of `trips` trips | barrier | event phase | barrier)
 // ---------------------------------------------------------------------------------------------------
-template <int NT, int NP, int MINB>
+template <int NT, int NP, int MINB, int NRAY>
 __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
@@ -733,45 +741,67 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
     block_setup<NT, NP>(A, smraw, X, false);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 16;      // marcher trips per round
+    const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 32;      // marcher steps per round
+    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : 4;       // steps per bookkeeping pass
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
-    Marcher M; M.init(T);
+    Marcher M[NRAY];              // NRAY independent rays per lane: their dependency chains interleave (ILP)
+#pragma unroll
+    for (int j = 0; j < NRAY; ++j) M[j].init(T);
     volatile int* vhead = X.head;
     volatile int* vtail = X.tail;
 
     for (;;) {
         // ================= marcher phase =================
-        for (int trip = 0; trip < trips; ++trip) {
+        // `trips` steps per round in passes of `inner`: claim rays for the free lanes, step every lane `inner` times
+        // in a tight loop (a lane whose ray ends inside the pass waits for its end), write back and push what ended.
+        for (int trip = 0; trip < trips; trip += inner) {
             // ---- free lanes claim ready rays
-            const unsigned fm = __ballot_sync(FULL, M.slot < 0);
-            if (fm && (vtail[L_RDY] - vhead[L_RDY]) > 0) {
-                int base = 0, n = 0;
-                if (lane == 0) {
-                    const int want = __popc(fm);
-                    int h = vhead[L_RDY];
-                    for (;;) {
-                        n = min(want, vtail[L_RDY] - h);
-                        if (n <= 0) { n = 0; break; }
-                        const int old = atomicCAS(X.head + L_RDY, h, h + n);
-                        if (old == h) { base = h; break; }
-                        h = old;
+#pragma unroll
+            for (int j = 0; j < NRAY; ++j) {
+                const unsigned fm = __ballot_sync(FULL, M[j].slot < 0);
+                if (fm && (vtail[L_RDY] - vhead[L_RDY]) > 0) {
+                    int base = 0, n = 0;
+                    if (lane == 0) {
+                        const int want = __popc(fm);
+                        int h = vhead[L_RDY];
+                        for (;;) {
+                            n = min(want, vtail[L_RDY] - h);
+                            if (n <= 0) { n = 0; break; }
+                            const int old = atomicCAS(X.head + L_RDY, h, h + n);
+                            if (old == h) { base = h; break; }
+                            h = old;
+                        }
                     }
+                    base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
+                    const int rank = __popc(fm & lt);
+                    if (M[j].slot < 0 && rank < n) M[j].load(X, X.Q(L_RDY, base + rank));
                 }
-                base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
-                const int rank = __popc(fm & lt);
-                if (M.slot < 0 && rank < n) M.load(X, X.Q(L_RDY, base + rank));
             }
-            // ---- one trip
-            int lst = -1;
-            if (M.slot >= 0) lst = M.trip(X, A, C);
-            // ---- push finished rays on their event lists (one shared-memory atomic per list present in the warp)
-            if (__any_sync(FULL, lst >= 0)) {
-                const unsigned g = __match_any_sync(FULL, lst);
-                const int leader = __ffs(g) - 1;
-                int base = 0;
-                if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
-                base = __shfl_sync(FULL, base, leader);
-                if (lst >= 0) { X.Q(lst, base + __popc(g & lt)) = (short)M.slot; M.slot = -1; }
+            // ---- `inner` steps of every ray
+            int out[NRAY];
+            unsigned n_step = 0;
+#pragma unroll
+            for (int j = 0; j < NRAY; ++j) out[j] = (M[j].slot >= 0 && (M[j].info & 3) == K_DEAD) ? O_DEAD : O_NONE;
+#pragma unroll 1
+            for (int k = 0; k < inner; ++k) {
+#pragma unroll
+                for (int j = 0; j < NRAY; ++j)
+                    if (M[j].slot >= 0 && out[j] == O_NONE) out[j] = M[j].step(X, n_step);
+            }
+            C.n_cf += n_step;
+            // ---- write back and push ended rays on their event lists (one shared-memory atomic per list present in the warp)
+#pragma unroll
+            for (int j = 0; j < NRAY; ++j) {
+                int lst = -1;
+                if (M[j].slot >= 0 && out[j] != O_NONE) lst = M[j].finish(X, A, C, out[j]);
+                if (__any_sync(FULL, lst >= 0)) {
+                    const unsigned g = __match_any_sync(FULL, lst);
+                    const int leader = __ffs(g) - 1;
+                    int base = 0;
+                    if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (lst >= 0) { X.Q(lst, base + __popc(g & lt)) = (short)M[j].slot; M[j].slot = -1; }
+                }
             }
         }
         __syncthreads();
@@ -783,7 +813,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
             int hd[5], m[5], boff[6], full = 0;
 #pragma unroll
             for (int k = 0; k < 5; ++k) { hd[k] = X.head[order[k]]; m[k] = X.tail[order[k]] - hd[k]; full += m[k] >> 5; }
-            const bool partial = (X.misc[2] - X.head[L_RDY]) + 32 * full < NT + NT / 2;
+            const bool partial = (X.misc[2] - X.head[L_RDY]) + 32 * full < NRAY * (NT + NT / 2);
             boff[0] = 0;
 #pragma unroll
             for (int k = 0; k < 5; ++k) { if (!partial) m[k] &= ~31; boff[k + 1] = boff[k] + ((m[k] + 31) >> 5); }

@@ -37,7 +37,8 @@ struct LaunchArgs {
     int photon_source, photon_scattering, photon_emission, stellar_direction, limb_emission;
     int flow_global, flow_theta, nx, ny;
     int defer_events, defer_refill;   // ballot-regrouping thresholds (lanes), persistent-lane engine
-    int e2_trips, e2_pad;             // ray/event engine: marcher trips per round
+    int e2_trips, e2_pad;             // ray/event engine: marcher steps per round, block shape
+    int e2_inner, e2_pad2;            // steps per bookkeeping pass
     double fstop, photon_minimum, photon_bias, surface_albedo, theta_star, phi_star;
     double x_max, y_max;
     double det[3];                   // det_dir(1:3)
