@@ -151,7 +151,7 @@ int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     if (!v || !*v) return dflt;
     int x = std::atoi(v);
-    return x < 1 ? 1 : (x > 32 ? 32 : x);
+    return x < 1 ? 1 : (x > 4096 ? 4096 : x);
 }
 
 // LaunchArgs from the ABI struct: host-evaluated detector / star geometry (src/ARTES.f90:495-502, 1080-1109, 4628, 4871)

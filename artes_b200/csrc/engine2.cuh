@@ -884,7 +884,8 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     volatile int* vhead = X.head;
     volatile int* vtail = X.tail;
     volatile int* vmisc = X.misc;
-    const int starve = A.L.e2_trips > 0 ? A.L.e2_trips : 8;     // take partial batches when fewer lanes than this march
+    const int starve = 8;                                        // take partial batches when fewer lanes than this march
+    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : 8;       // steps per bookkeeping pass
 
     for (;;) {
         if (vmisc[0] >= NP) break;
@@ -913,9 +914,17 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
                 M.load(X, s);
             }
         }
-        // ---- one trip
+        // ---- `inner` steps in a tight loop, then the write-back of what ended
         int lst = -1;
-        if (M.slot >= 0) lst = M.trip(X, A, C);
+        {
+            int out = (M.slot >= 0 && (M.info & 3) == K_DEAD) ? O_DEAD : O_NONE;
+            unsigned n_step = 0;
+#pragma unroll 1
+            for (int k = 0; k < inner; ++k)
+                if (M.slot >= 0 && out == O_NONE) out = M.step(X, n_step);
+            C.n_cf += n_step;
+            if (M.slot >= 0 && out != O_NONE) lst = M.finish(X, A, C, out);
+        }
         // ---- push ended rays on their event lists
         if (__any_sync(FULL, lst >= 0)) {
             __threadfence_block();
