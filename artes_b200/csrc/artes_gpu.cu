@@ -36,6 +36,7 @@ cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const dou
 bool engine2_supports(const KernelArgs& a);
 size_t engine2_scratch_bytes(int sm_count);
 cudaError_t launch_transport2(const KernelArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_transport2_trace(const KernelArgs& a, int sm_count, cudaStream_t stream);
 }  // namespace fast
 cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
 }  // namespace artes
@@ -108,6 +109,7 @@ struct artes_gpu_ctx {
     artes_launch_t pending_launch{};
     size_t n_out_d = 0;
     double last_h2d_ms = 0.0;
+    int last_engine = 0;
 };
 
 namespace {
@@ -472,8 +474,10 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
             // fast mode: the ray/event engine wherever it applies (ARTES_ENGINE=1 forces the persistent-lane engine)
             static const int engine = env_int("ARTES_ENGINE", 2);
             cudaError_t e;
+            ctx->last_engine = 1;
             if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, false, d.sm_count, d.stream);
             else if (engine == 2 && fast::engine2_supports(a)) {
+                ctx->last_engine = 2;
                 if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
                 a.O.scratch = d.scratch;
                 e = fast::launch_transport2(a, d.sm_count, d.stream);
@@ -617,8 +621,17 @@ int artes_gpu_trace(artes_gpu_ctx* ctx, const artes_launch_t* L, const double* x
     a.O.err = d.out_u; a.O.stats = d.out_u + ARTES_ERR_SLOTS; a.O.counter = d.out_u + ARTES_ERR_SLOTS + 8;
     a.R.xi = d_xi; a.R.max_draws = max_draws; a.R.max_rec = d_head ? max_rec : 0;
     a.R.seq_len = d_len; a.R.seq_hash = d_hash; a.R.seq_head = d_head; a.R.fstate = d_f;
-    cudaError_t e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport(a, true, d.sm_count, d.stream)
-                                                     : fast::launch_transport(a, true, d.sm_count, d.stream);
+    // fast mode: the ray/event engine wherever it applies, so that the trace hook walks the production path
+    static const int engine = env_int("ARTES_ENGINE", 2);
+    cudaError_t e;
+    ctx->last_engine = 1;
+    if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, true, d.sm_count, d.stream);
+    else if (engine == 2 && fast::engine2_supports(a)) {
+        ctx->last_engine = 2;
+        if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
+        a.O.scratch = d.scratch;
+        e = fast::launch_transport2_trace(a, d.sm_count, d.stream);
+    } else e = fast::launch_transport(a, true, d.sm_count, d.stream);
     if (e != cudaSuccess) return fail(ctx, -2, std::string("trace launch: ") + cudaGetErrorString(e));
     CU(cudaMemcpyAsync(seq_len, d_len, n * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
     CU(cudaMemcpyAsync(seq_hash, d_hash, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
@@ -653,6 +666,8 @@ int artes_gpu_cell_face(artes_gpu_ctx* ctx, int mode, uint64_t n, const double* 
     cudaFree(dp); cudaFree(dd); cudaFree(dod); cudaFree(df); cudaFree(dc); cudaFree(doi);
     return 0;
 }
+
+int artes_gpu_last_engine(const artes_gpu_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
 
 int artes_gpu_fma_peak(artes_gpu_ctx* ctx, double* fp64_tflops, double* fp32_tflops) {
     if (!ctx) return fail(nullptr, -1, "null context");

@@ -57,9 +57,10 @@ enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16 };
 // lets a block hold several times more photons than lanes.
 enum : int { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_S0, F_S1, F_S2, F_S3, F_TAU, F_W0, F_W1, F_W2, F_W3, NF_COLD,
              F_T = NF_COLD, F_ACC, F_TR, F_TT, F_TP, F_HBN, F_D0, F_IQ, F_LIM, NF_D };
-enum : int { I_CELL = 0, I_INFO, NI_HOT, I_HCELL = NI_HOT, I_PIX, I_ND, I_IDLO, I_IDHI, NF_I };
+enum : int { I_CELL = 0, I_INFO, NI_HOT, I_HCELL = NI_HOT, I_PIX, I_ND, I_IDLO, I_IDHI,
+             I_TLEN, I_TNSC, I_THLO, I_THHI, I_FLAG, NF_I };     // I_T*: walk recorder of the trace hook; I_FLAG bit 0: injected stream used up
 constexpr int NF_HOT = NF_D - NF_COLD;
-constexpr int REC = 20;       // doubles per cold record: 15 doubles + 5 ints, padded to 160 bytes
+constexpr int REC = 20;       // doubles per cold record: 15 doubles + 10 ints = 160 bytes
 
 __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c < np_slots) c <<= 1; return c; }
 
@@ -73,8 +74,9 @@ struct Lay {
     }
 };
 
-template <int NP>
+template <int NP, bool TR = false>
 struct ShT {                     // pointers into the block's shared memory
+    static constexpr bool TRACE = TR;   // the injected-stream walk recorder (test hook) is compiled in
     const double* r; const double* r2; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
     const int* tplane;
     double* sd; int* si; short* q; int* head; int* tail;
@@ -107,6 +109,34 @@ struct Draws {
         return ((double)x + 0.5) * (1.0 / 4294967296.0);
     }
 };
+
+// `count` (<= 5) consecutive draws of slot s starting at draw index nd: the Philox stream, or -- trace hook -- the
+// injected stream xi[photon][max_draws] (a draw past its end returns 0.5 and marks the stream as used up,
+// like rng_next<true> of transport.cuh)
+template <class Sh>
+__device__ __forceinline__ void draws(const Sh& X, const KernelArgs& A, int s, unsigned long long id, unsigned nd, int count, double* xi) {
+    if (Sh::TRACE) {
+        for (int i = 0; i < count; ++i) {
+            if ((int)(nd + i) >= A.R.max_draws) { xi[i] = 0.5; X.I(I_FLAG, s) |= 1; }
+            else xi[i] = A.R.xi[(size_t)(id - A.L.id_base) * A.R.max_draws + nd + i];
+        }
+    } else {
+        const Draws d(id, nd, A.L.seed, count);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) if (i < count) xi[i] = d.get(i);
+    }
+}
+
+// walk recorder of the trace hook: one (a,b,c,d,e) tuple per cell_face outcome / detector deposit
+__device__ __forceinline__ void trace_tuple(const KernelArgs& A, unsigned long long id, int& tlen, unsigned long long& thash,
+                                            int a, int b, int c, int d, int e) {
+    if (A.R.seq_head && tlen < A.R.max_rec) {
+        int* p = A.R.seq_head + ((size_t)(id - A.L.id_base) * A.R.max_rec + tlen) * 5;
+        p[0] = a; p[1] = b; p[2] = c; p[3] = d; p[4] = e;
+    }
+    tuple_hash(thash, a); tuple_hash(thash, b); tuple_hash(thash, c); tuple_hash(thash, d); tuple_hash(thash, e);
+    ++tlen;
+}
 
 // quadric constants of a ray, event side
 struct RayK { double A1, A2, B1, B2, C1, C2, g0, g1, Xx, Xy, Nx, Ny, z0, n2; };
@@ -317,18 +347,36 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
     base = __shfl_sync(FULL, base, leader < 0 ? 0 : leader);
     if (!valid) return false;
     C.n_draw += (unsigned)X.I(I_ND, s);          // draws of the photon that lived in this slot before
+    if (Sh::TRACE && X.I(I_ND, s) > 0) {         // ... and its walk record
+        const unsigned long long pid = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+        const size_t kk = (size_t)(pid - L.id_base);
+        A.R.seq_len[kk] = X.I(I_TLEN, s);
+        A.R.seq_hash[kk] = (unsigned long long)(unsigned)X.I(I_THLO, s) | ((unsigned long long)(unsigned)X.I(I_THHI, s) << 32);
+        if (A.R.fstate) {
+            const int pinfo = X.I(I_INFO, s);
+            const int pout = (pinfo >> 8) & 15;
+            const double tw = ((pinfo & 3) == K_WALK && (pout == O_EXIT || pout == O_SURF || pout == O_ERR)) ? X.D(F_T, s) : 0.0;
+            double* f = A.R.fstate + kk * 8;
+            f[0] = X.D(F_PX, s) + tw * X.D(F_DX, s); f[1] = X.D(F_PY, s) + tw * X.D(F_DY, s); f[2] = X.D(F_PZ, s) + tw * X.D(F_DZ, s);
+            f[3] = X.D(F_S0, s); f[4] = X.D(F_S1, s); f[5] = X.D(F_S2, s); f[6] = X.D(F_S3, s); f[7] = (double)X.I(I_TNSC, s);
+        }
+    }
     X.I(I_ND, s) = 0;
     const unsigned long long k = base + (unsigned long long)__popc(vm & ((1u << lane) - 1u));
     if (k >= L.n_photons) { atomicAdd(X.misc, 1); return false; }
     ++C.n_emit;
     const unsigned long long id = L.id_base + k;
     X.I(I_IDLO, s) = (int)(unsigned)id; X.I(I_IDHI, s) = (int)(unsigned)(id >> 32);
+    if (Sh::TRACE) {
+        X.I(I_TLEN, s) = 0; X.I(I_TNSC, s) = 0; X.I(I_FLAG, s) = 0;
+        X.I(I_THLO, s) = (int)(unsigned)1469598103934665603ull; X.I(I_THHI, s) = (int)(unsigned)(1469598103934665603ull >> 32);
+    }
     unsigned nd = 0;
     double xi, r_disk;
     if (L.limb_emission) {
-        for (;;) { Draws d(id, nd, L.seed, 1); xi = d.get(0); ++nd; r_disk = sqrt(xi); if (r_disk > 0.9) break; }
-    } else { Draws d(id, nd, L.seed, 1); xi = d.get(0); ++nd; r_disk = sqrt(xi); }
-    { Draws d(id, nd, L.seed, 1); xi = d.get(0); ++nd; }
+        for (;;) { draws(X, A, s, id, nd, 1, &xi); ++nd; r_disk = sqrt(xi); if (r_disk > 0.9 || (Sh::TRACE && (X.I(I_FLAG, s) & 1))) break; }
+    } else { draws(X, A, s, id, nd, 1, &xi); ++nd; r_disk = sqrt(xi); }
+    draws(X, A, s, id, nd, 1, &xi); ++nd;
     const double phi_disk = 2.0 * PI * xi;
     const double R = X.r[T.nr];
     double sphi, cphi;
@@ -373,8 +421,8 @@ __device__ __forceinline__ bool ev_pre(const Sh& X, const KernelArgs& A, bool va
     if (tacc < 1.e-6 && !hit_surface) { X.I(I_INFO, s) = K_DEAD; return true; }
     const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
     const unsigned nd = (unsigned)X.I(I_ND, s);
-    const Draws d(id, nd, L.seed, 1);
-    const double xi = d.get(0);
+    double xi;
+    draws(X, A, s, id, nd, 1, &xi);
     X.I(I_ND, s) = (int)(nd + 1u);
     double arg = 1.0 - xi;
     if (!(tacc < 1.e-6) && tacc < 50.0) {
@@ -407,15 +455,25 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     double S[4] = {X.D(F_S0, s), X.D(F_S1, s), X.D(F_S2, s), X.D(F_S3, s)};
     const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
     unsigned nd = (unsigned)X.I(I_ND, s);
-    const Draws dr(id, nd, L.seed, 5);
     bool alive = L.photon_scattering != 0;
-    if (alive) { const double xi = dr.get(0); ++nd; if (xi < L.fstop) alive = false; }
+    if (Sh::TRACE && (X.I(I_FLAG, s) & 1)) alive = false;       // injected stream used up (test hook only)
+    double xr[5];
+    if (alive) draws(X, A, s, id, nd, 5, xr);
+    if (Sh::TRACE && alive) X.I(I_FLAG, s) &= ~1;                // (only the draws actually consumed below may exhaust it)
+    if (alive) { const double xi = xr[0]; ++nd; if (Sh::TRACE && (int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; if (xi < L.fstop) alive = false; }
     if (alive) {
         const double alb = __ldg(T.albedo + ci);
         if (alb < 1.0 && alb > 0.0) { const double g = fdiv(alb, 1.0 - L.fstop); S[0] *= g; S[1] *= g; S[2] *= g; S[3] *= g; }
         if (S[0] <= L.photon_minimum) alive = false;
     }
-    if (!alive) { X.I(I_ND, s) = (int)nd; X.I(I_INFO, s) = K_DEAD; return true; }
+    if (!alive) {
+        X.I(I_ND, s) = (int)nd; X.I(I_INFO, s) = K_DEAD;
+        if (Sh::TRACE) {   // final state of the photon for the trace hook
+            X.D(F_PX, s) = px; X.D(F_PY, s) = py; X.D(F_PZ, s) = pz;
+            X.D(F_S0, s) = S[0]; X.D(F_S1, s) = S[1]; X.D(F_S2, s) = S[2]; X.D(F_S3, s) = S[3];
+        }
+        return true;
+    }
     // ---- peel-off towards the detector: Stokes vector scattered into det, pixel
     ++C.n_peel;
     int pix = -1;
@@ -458,8 +516,9 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     double tau = -1.0;                      // < 0: the photon dies after its peel-off has been deposited
     {
         FastAngles g;
-        int e = sample_angles_f(A, dr.get(1), dr.get(2), dr.get(3), S, ci, g);
+        int e = sample_angles_f(A, xr[1], xr[2], xr[3], S, ci, g);
         nd += (e == 6) ? 2u : 3u;
+        if (Sh::TRACE) { X.I(I_TNSC, s) += 1; if ((int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; }
         double e0 = 0, e1 = 0, e2 = 0;
         if (!e) {
             const double cto = fdiv(dz, fsqrt(dx * dx + dy * dy + dz * dz));
@@ -488,7 +547,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
             if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
         }
         if (e) { err_count(A, e); ++C.n_err; }
-        else { const double xi = dr.get(4); ++nd; tau = -log(1.0 - xi); }
+        else { const double xi = xr[4]; ++nd; if (Sh::TRACE && (int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; tau = -log(1.0 - xi); }
     }
     X.D(F_PX, s) = px; X.D(F_PY, s) = py; X.D(F_PZ, s) = pz; X.D(F_DX, s) = dx; X.D(F_DY, s) = dy; X.D(F_DZ, s) = dz;
     X.D(F_S0, s) = S[0]; X.D(F_S1, s) = S[1]; X.D(F_S2, s) = S[2]; X.D(F_S3, s) = S[3]; X.D(F_TAU, s) = tau;
@@ -512,6 +571,13 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     // curves, spectra) the ten sums are reduced across the warp first, so the L2 sees one atomic per plane and
     // batch instead of 32 serialised ones on the same address.
     const bool dep = valid && out == O_EXIT && tacc < 50.0 && pix >= 0;
+    if (Sh::TRACE && dep) {   // the reference's deposit point in the walk record: (100, ix, iy, 0, 0)
+        const unsigned long long pid = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+        int tl = X.I(I_TLEN, s);
+        unsigned long long th = (unsigned long long)(unsigned)X.I(I_THLO, s) | ((unsigned long long)(unsigned)X.I(I_THHI, s) << 32);
+        trace_tuple(A, pid, tl, th, 100, pix % L.nx + 1, pix / L.nx + 1, 0, 0);
+        X.I(I_TLEN, s) = tl; X.I(I_THLO, s) = (int)(unsigned)th; X.I(I_THHI, s) = (int)(unsigned)(th >> 32);
+    }
     const unsigned dm = __ballot_sync(FULL, dep);
     if (dm) {
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -589,11 +655,11 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
 // ---------------------------------------------------------------------------------------------------
 // block set-up and the marcher
 // ---------------------------------------------------------------------------------------------------
-template <int NT, int NP>
-__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP>& X, bool mark_empty) {
+template <int NT, int NP, bool TR>
+__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP, TR>& X, bool mark_empty) {
     const DevTables& T = A.T;
     const Lay lay(T.nr, T.nt, T.np, NP);
-    constexpr int RC = ShT<NP>::RC;
+    constexpr int RC = ShT<NP, TR>::RC;
     X.r = sm; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
     X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
     X.sd = sm + lay.o_sd;
@@ -611,7 +677,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     for (int i = tid; i < T.np; i += NT) { sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i]; }
     if (mark_empty) for (int i = tid; i < N_LISTS * RC; i += NT) X.q[i] = (short)-1;
     __syncthreads();
-    for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; }   // every slot starts by asking for a photon
+    for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; X.I(I_INFO, i) = 0; }   // every slot starts by asking for a photon
     if (tid < 8) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
     if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; }
     __syncthreads();
@@ -636,6 +702,7 @@ struct Marcher {
     const double* kb;            // kext + nr*(c1 + nt*c2): the opacity row of the ray's (theta, phi) column
     int nr, nt, depth;           // launch invariants kept in registers (the kernel parameters live in constant memory)
     const double* kext;
+    int tl; unsigned long long th, pid;   // walk recorder (trace hook only; dead code otherwise)
 
     __device__ __forceinline__ void init(const DevTables& T) {
         slot = -1; c0 = cell12 = info = 0; dr = 1;
@@ -654,15 +721,30 @@ struct Marcher {
         dr = (info & B_INWARD) ? -1 : 1; ds = (info & B_INWARD) ? -1.0 : 1.0;
         kb = kext + nr * (((cell >> 10) & 1023) + nt * ((cell >> 20) & 1023));
         kap = __ldg(kb + c0);
+        if (Sh::TRACE) {
+            tl = X.I(I_TLEN, s);
+            th = (unsigned long long)(unsigned)X.I(I_THLO, s) | ((unsigned long long)(unsigned)X.I(I_THHI, s) << 32);
+            pid = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+        }
     }
 
     // One step: advance to the next crossing.  Returns the outcome (O_NONE: the ray goes on).
     template <class Sh>
-    __device__ __forceinline__ int step(const Sh& X, unsigned& n_cf) {
+    __device__ __forceinline__ int step(const Sh& X, const KernelArgs& A, unsigned& n_cf) {
         double tn = tr;
         if (tt < tn) tn = tt;
         if (tp < tn) tn = tp;
         ++n_cf;
+        if (Sh::TRACE) {   // the cell_face outcome the reference would record here: (next_face(2), cell_out(3))
+            const int c1 = (cell12 >> 10) & 1023, c2 = (cell12 >> 20) & 1023, np = A.T.np;
+            if (!(tn < RAY_NONE)) trace_tuple(A, pid, tl, th, 0, 0, 0, 0, 0);
+            else if (tn == tr) trace_tuple(A, pid, tl, th, 1, c0 + (dr > 0 ? 1 : 0), c0 + dr, c1, c2);
+            else if (tn == tt) trace_tuple(A, pid, tl, th, 2, (info & B_TUPPER) ? c1 + 1 : c1, c0, (info & B_TUPPER) ? c1 + 1 : c1 - 1, c2);
+            else {
+                const int up2 = (c2 + 1 == np) ? 0 : c2 + 1, dn2 = (c2 == 0) ? np - 1 : c2 - 1;
+                trace_tuple(A, pid, tl, th, 3, (info & B_PUP) ? up2 : c2, c0, c1, (info & B_PUP) ? up2 : dn2);
+            }
+        }
         if (!(tn < RAY_NONE)) return O_ERR;
         acc = fma(tn - t, kap, acc);
         const bool radial = (tn == tr);
@@ -692,6 +774,7 @@ struct Marcher {
         X.D(F_T, slot) = t; X.D(F_ACC, slot) = acc; X.D(F_TR, slot) = tr;   // (tr: a re-solved ray goes on)
         X.I(I_CELL, slot) = cell12 | c0;
         X.I(I_INFO, slot) = (info & 0xff & ~B_INWARD) | (dr < 0 ? B_INWARD : 0) | (out << 8);
+        if (Sh::TRACE) { X.I(I_TLEN, slot) = tl; X.I(I_THLO, slot) = (int)(unsigned)th; X.I(I_THHI, slot) = (int)(unsigned)(th >> 32); }
         if (out == O_ERR) {
             err_count(A, 31); ++C.n_err;
             err_count(A, kind == K_PRE ? 2 : (kind == K_WALK ? 3 : 43));
@@ -703,7 +786,7 @@ struct Marcher {
     __device__ __forceinline__ int trip(const Sh& X, const KernelArgs& A, Cnt& C) {
         if ((info & 3) == K_DEAD) return finish(X, A, C, O_DEAD);
         unsigned n = 0;
-        const int out = step(X, n);
+        const int out = step(X, A, n);
         C.n_cf += n;
         return (out == O_NONE) ? -1 : finish(X, A, C, out);
     }
@@ -736,9 +819,9 @@ template <int NT, int NP, int MINB, int NRAY>
 __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
-    using Sh = ShT<NP>;
+    using Sh = ShT<NP, false>;
     Sh X;
-    block_setup<NT, NP>(A, smraw, X, false);
+    block_setup<NT, NP, false>(A, smraw, X, false);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 32;      // marcher steps per round
@@ -786,7 +869,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
             for (int k = 0; k < inner; ++k) {
 #pragma unroll
                 for (int j = 0; j < NRAY; ++j)
-                    if (M[j].slot >= 0 && out[j] == O_NONE) out[j] = M[j].step(X, n_step);
+                    if (M[j].slot >= 0 && out[j] == O_NONE) out[j] = M[j].step(X, A, n_step);
             }
             C.n_cf += n_step;
             // ---- write back and push ended rays on their event lists (one shared-memory atomic per list present in the warp)
@@ -870,13 +953,13 @@ __device__ __forceinline__ void ring_put(volatile short* e, int s) {
     *e = (short)s;
 }
 
-template <int NT, int NP, int MINB>
+template <int NT, int NP, int MINB, bool TR>
 __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
-    using Sh = ShT<NP>;
+    using Sh = ShT<NP, TR>;
     Sh X;
-    block_setup<NT, NP>(A, smraw, X, true);
+    block_setup<NT, NP, TR>(A, smraw, X, true);
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
@@ -921,7 +1004,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             unsigned n_step = 0;
 #pragma unroll 1
             for (int k = 0; k < inner; ++k)
-                if (M.slot >= 0 && out == O_NONE) out = M.step(X, n_step);
+                if (M.slot >= 0 && out == O_NONE) out = M.step(X, A, n_step);
             C.n_cf += n_step;
             if (M.slot >= 0 && out != O_NONE) lst = M.finish(X, A, C, out);
         }

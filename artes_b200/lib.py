@@ -25,7 +25,7 @@ SYMBOLS = [
     "artes_gpu_set_grid", "artes_gpu_set_wavelength", "artes_gpu_set_wavelength_dense",
     "artes_gpu_run", "artes_gpu_run_async", "artes_gpu_wait", "artes_gpu_nccl_unique_id",
     "artes_gpu_nccl_init_rank", "artes_gpu_trace", "artes_gpu_cell_face", "artes_gpu_device_info",
-    "artes_gpu_fma_peak",
+    "artes_gpu_fma_peak", "artes_gpu_last_engine",
 ]
 
 
@@ -64,6 +64,7 @@ def load():
     lib.artes_gpu_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.c_char_p, C.c_int]
     lib.artes_gpu_fma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.artes_gpu_last_engine.argtypes = [C.c_void_p]
     if lib.artes_gpu_abi_version() != ABI_VERSION:
         raise ArtesGpuError("libartes_gpu.so ABI version mismatch")
     _LIB = lib
@@ -220,6 +221,10 @@ class GpuTransport:
         self._check(self.lib.artes_gpu_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), name, 256),
                     "artes_gpu_device_info")
         return dict(sm_count=sm.value, cc=(ma.value, mi.value), name=name.value.decode())
+
+    def last_engine(self):
+        """1 = persistent-lane engine, 2 = ray/event engine (the last run / trace of this context)."""
+        return int(self.lib.artes_gpu_last_engine(self.h))
 
     def fma_peak(self):
         a, b = C.c_double(), C.c_double()

@@ -94,6 +94,7 @@ CASES_LIVE = [
     ("c4_mie_patches", dict(stellar_direction=1, theta_star=math.radians(70.0), phi_star=math.radians(33.0)), 20000),
     ("c2_hg_deck", dict(limb_emission=1, nx=1, ny=1, det_phi=math.radians(175.0)), 20000),
     ("c3_molecular", dict(nx=1, ny=1), 20000),
+    ("c5_scale", dict(nx=16, ny=16, det_phi=math.radians(60.0)), 6000),
 ]
 
 
@@ -110,6 +111,10 @@ def test_crossing_sequences_bit_exact_vs_oracle(atmospheres, oracle_factory, gpu
     L = make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, fstop=0.03, **kw)
     ro = o.trace(L, xi, max_rec=4)
     rg = g.trace(L, xi, max_rec=4)
+    # fast mode walks the ray/event engine (the production path) wherever it applies; everything else, and the
+    # faithful mode, the persistent-lane engine
+    plain = not kw.get("surface_albedo")
+    assert g.last_engine() == (2 if (mode == abi.MODE_FAST and plain) else 1)
     same = (ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])
     assert same.all(), f"{(~same).sum()} of {n} sequences differ"
     np.testing.assert_array_equal(ro["head"], rg["head"])
@@ -206,6 +211,7 @@ def test_ray_event_engine_same_stream_vs_oracle(atmospheres, oracle_factory, gpu
     xm = 1.3 * atm.rfront[-1]
     L = make_launch(mode=abi.MODE_FAST, n_photons=n, x_max=xm, y_max=xm, seed=33, **kw)
     a, b = o.run(L), g.run(L)
+    assert g.last_engine() == 2
     for k in ("n_emit", "n_cell_face", "n_scatter", "n_peel", "n_surface", "n_draws"):
         assert abs(a["stats"][k] - b["stats"][k]) <= max(2, 2e-5 * a["stats"][k]), (k, a["stats"][k], b["stats"][k])
     assert b["stats"]["n_error"] <= a["stats"]["n_error"] + 2
@@ -224,6 +230,7 @@ def test_fast_mode_oblate_planet_same_stream(atmospheres):
     xm = 1.06 * 1.3 * atm.rfront[-1]
     L = make_launch(mode=abi.MODE_FAST, n_photons=40000, x_max=xm, y_max=xm, seed=9, nx=32, ny=32, det_phi=math.radians(100.0))
     a, b = o.run(L), g.run(L)
+    assert g.last_engine() == 1
     assert abs(a["stats"]["n_cell_face"] - b["stats"]["n_cell_face"]) <= max(2, 2e-5 * a["stats"]["n_cell_face"])
     assert a["stats"]["n_scatter"] == b["stats"]["n_scatter"] or abs(a["stats"]["n_scatter"] - b["stats"]["n_scatter"]) <= 3
     np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=2e-5, atol=1e-9)
