@@ -9,12 +9,13 @@
 //
 //   ray     a straight segment through the r-theta-phi grid (tau pre-pass :633-656, transport walk
 //           :691-778 / :850-941, peel-off walk :4739-4761).  A lane ("marcher") owns one ray at a time and
-//           does nothing but step it radially; its whole state is ~24 registers.
-//   event   everything else.  A photon lives in a shared-memory SLOT.  When its ray ends the marcher
-//           writes (t, tau) back to the slot and pushes the slot on the list of the event it needs;
-//           after every few trips the block synchronises and ALL threads of the block work through
-//           the lists, 32 same-type events per warp, fully converged.  Each event ends by setting up
-//           the slot's next ray and pushing the slot on the ready list, from which free marchers claim.
+//           does nothing but step it radially in a tight loop; its whole state is ~30 registers.
+//   event   everything else.  A photon lives in a SLOT: the hot ray state in shared memory, the cold state
+//           (position, direction, Stokes vector, pending peel-off weights, stream position) in a 160-byte
+//           L2-resident record.  When its ray ends the marcher writes (t, tau) back to the slot and pushes
+//           the slot on the list of the event it needs; whenever a list holds 32 entries some warp takes
+//           them and runs the event fully converged.  Each event ends by setting up the slot's next ray
+//           and pushing the slot on the ready list, from which free marcher lanes claim.
 //
 //   EMIT  emit_photon :1008-1115 (star)                     -> pre-pass ray
 //   PRE   first optical depth :660-685                      -> transport ray
@@ -36,8 +37,12 @@
 // The draw order of the random stream and every physical formula are those of the oracle, so for the
 // same Philox stream the trajectories agree with the oracle's to rounding.
 //
-// Scope: star source, black surface, no flow counters, no trace (the configurations the benchmark and
-// the reference's default artes.in use).  Anything else runs on the persistent-lane engine.
+// Two kernels schedule the same marcher and events: transport3_kernel (asynchronous, no block barrier; the
+// default) and transport2_kernel (bulk-synchronous rounds; kept for comparison, a few per cent slower).
+//
+// Scope: star source, black surface, no flow counters, spherical planet (the configurations the benchmark and
+// the reference's default artes.in use), with or without the trace hook.  Anything else runs on the
+// persistent-lane engine.
 
 namespace e2 {
 
@@ -968,7 +973,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     volatile int* vtail = X.tail;
     volatile int* vmisc = X.misc;
     const int starve = 8;                                        // take partial batches when fewer lanes than this march
-    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : 8;       // steps per bookkeeping pass
+    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : 12;      // steps per bookkeeping pass (measured best of 4..16 on C4/C5)
 
     for (;;) {
         if (vmisc[0] >= NP) break;
