@@ -45,18 +45,15 @@ def cell_depth(rfront, k_sca, k_abs, nr, ntheta, nphi, photon_source=1, ring=Fal
     kap = kap.reshape(nphi, ntheta, nr)
     limit = 30.0 if photon_source == 1 else 5.0
     grid_out = 2 if (photon_source == 2 and ring) else 0
-    cell_max = 1000000
-    depth = 0
-    for j in range(ntheta):
-        for k in range(nphi):
-            tot = 0.0
-            for i in range(grid_out, nr):
-                tot = tot + kap[k, j, nr - i - 1] * (rfront[nr - i] - rfront[nr - i - 1])
-                depth = nr - i - 1
-                if tot > limit:
-                    break
-            cell_max = min(cell_max, depth)
-    return cell_max
+    rf = np.asarray(rfront, dtype=np.float64)
+    # top-down running optical depth of every (theta, phi) column, summed in the reference's order (:2345-2375);
+    # the depth of a column is the layer in which it first exceeds the limit, else the bottom layer
+    layers = np.arange(nr - 1 - grid_out, -1, -1)                       # nr-i-1 for i = grid_out .. nr-1
+    dtau = kap[:, :, layers] * (rf[layers + 1] - rf[layers])
+    tot = np.cumsum(dtau, axis=2)
+    over = tot > limit
+    first = np.where(over.any(axis=2), over.argmax(axis=2), len(layers) - 1)
+    return int(min(1000000, layers[first].min())) if len(layers) else 1000000
 
 
 def cell_volume(rfront, thetafront, phifront, oblate=(1.0, 1.0, 1.0)):
