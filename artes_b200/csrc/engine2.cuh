@@ -458,6 +458,9 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - X.D(F_TAU, s), __ldg(T.kext + ci));
     const double px = X.D(F_PX, s) + tpos * dx, py = X.D(F_PY, s) + tpos * dy, pz = X.D(F_PZ, s) + tpos * dz;
     double S[4] = {X.D(F_S0, s), X.D(F_S1, s), X.D(F_S2, s), X.D(F_S3, s)};
+    double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
+    if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
+    const double peel_deg = acos(mu) * (180.0 / PI);
     const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
     unsigned nd = (unsigned)X.I(I_ND, s);
     bool alive = L.photon_scattering != 0;
@@ -484,10 +487,8 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     int pix = -1;
     double W[4] = {0.0, 0.0, 0.0, 0.0};
     {
-        double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
-        if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
         double F[16];
-        matrix_at_deg(T, ci, acos(mu) * (180.0 / PI), F);
+        matrix_at_deg(T, ci, peel_deg, F);
         if (!(fabs(dz) < 1.0)) err_count(A, 45);
         else {
             const double smu = fsqrt(1.0 - mu * mu);
@@ -973,13 +974,21 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     volatile int* vtail = X.tail;
     volatile int* vmisc = X.misc;
     const int starve = 8;                                        // take partial batches when fewer lanes than this march
-    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : 12;      // steps per bookkeeping pass (measured best of 4..16 on C4/C5)
+    // Soft warp specialisation: the last `we` warps of the block only run events (they never claim rays), the others
+    // only march and leave full batches to them (they still take batches when they have nothing to march).  Every
+    // warp then loops over a small part of the kernel's code -- the instruction cache, not the register file, is
+    // what the roles are for.  we = 0: every warp does both.
+    const int we = A.L.e2_trips > 0 ? min(A.L.e2_trips, NT / 32 - 1) : 0;
+    const bool event_warp = (int)(threadIdx.x >> 5) >= NT / 32 - we;
+    int idle = 0;
+    // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100)
+    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / 2 + 2));
 
     for (;;) {
         if (vmisc[0] >= NP) break;
         // ---- free lanes claim ready rays
-        const unsigned fm = __ballot_sync(FULL, M.slot < 0);
-        bool rdy_empty = false;
+        const unsigned fm = event_warp ? 0u : __ballot_sync(FULL, M.slot < 0);
+        bool rdy_empty = event_warp;
         if (fm) {
             int base = 0, n = 0;
             if (lane == 0) {
@@ -1031,9 +1040,10 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
         int l = -1;
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
-        if (fullm) l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
-                       : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
-        else if (anym && rdy_empty && nactive < starve)
+        if (fullm && (we == 0 || event_warp || nactive == 0))
+            l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
+                : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
+        else if (anym && rdy_empty && nactive < starve && (!event_warp || ++idle > 8))
             l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_DEP)) ? L_DEP : (anym & (1u << L_H)) ? L_H
                 : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
         if (l >= 0) {
@@ -1045,6 +1055,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             }
             base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
             if (n > 0) {
+                idle = 0;
                 const bool valid = lane < n;
                 int s = 0;
                 if (valid) s = ring_take(&X.Q(l, base + lane));
