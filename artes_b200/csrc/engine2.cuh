@@ -40,9 +40,9 @@
 // Two kernels schedule the same marcher and events: transport3_kernel (asynchronous, no block barrier; the
 // default) and transport2_kernel (bulk-synchronous rounds; kept for comparison, a few per cent slower).
 //
-// Scope: star source, black surface, no flow counters, spherical planet (the configurations the benchmark and
-// the reference's default artes.in use), with or without the trace hook.  Anything else runs on the
-// persistent-lane engine.
+// Scope: everything except flow_global and oblate planets (those run on the persistent-lane engine).  The GEN
+// instantiation compiles in the thermal source, the reflecting surface (SURF event) and the latitudinal flow
+// counters; the TRACE instantiation the injected-stream walk recorder.
 
 namespace e2 {
 
@@ -51,10 +51,11 @@ namespace e2 {
 // the event phase.  RC = ring capacity of the lists (power of two >= NP).
 
 enum : int { K_PRE = 0, K_WALK = 1, K_PEEL = 2, K_DEAD = 3 };
-enum : int { L_EMIT = 0, L_PRE, L_H, L_DEP, L_RES, L_RDY, N_LISTS };
+enum : int { L_EMIT = 0, L_PRE, L_H, L_DEP, L_RES, L_SURF, L_RDY, N_LISTS };   // event lists, then the ready list
+constexpr int N_EVENT_LISTS = L_RDY;
 enum : int { O_NONE = 0, O_LIMIT, O_EXIT, O_SURF, O_REST, O_RESP, O_ERR, O_DEAD };
 // info word: bits 0-1 kind, 2 radial inward, 3 next theta face is the upper one, 4 phi increasing, 8-11 outcome
-enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16 };
+enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16, PK_SHIFT = 5 };   // bits 5-6: peel kind of a K_PEEL ray (PK_SCATTER/SURFACE/THERMAL)
 
 // Slot fields.  COLD fields (touched by events only) live in a 160-byte record per slot in global memory
 // (L2-resident scratch, one region per block); HOT fields (the ray a marcher loads and stores) live in
@@ -79,9 +80,10 @@ struct Lay {
     }
 };
 
-template <int NP, bool TR = false>
+template <int NP, bool TR = false, bool GN = false>
 struct ShT {                     // pointers into the block's shared memory
     static constexpr bool TRACE = TR;   // the injected-stream walk recorder (test hook) is compiled in
+    static constexpr bool GEN = GN;     // thermal source, reflecting surface and latitudinal flow counters are compiled in
     const double* r; const double* r2; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
     const int* tplane;
     double* sd; int* si; short* q; int* head; int* tail;
@@ -232,7 +234,8 @@ __device__ __forceinline__ double phi_next(const Sh& X, int np, int c2, double t
 // set up the next ray of slot s: origin (x,y,z) in cell (c0,c1,c2), direction n
 template <class Sh>
 __device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s, double x, double y, double z,
-                                          double n0, double n1, double n2, int c0, int c1, int c2, int sface, int kind, double lim) {
+                                          double n0, double n1, double n2, int c0, int c1, int c2, int sface, int kind, double lim,
+                                          double acc0 = 0.0, int pk = 0) {
     RayK K;
     double hbn, D0, iq;
     ray_consts(T, x, y, z, n0, n1, n2, K, hbn, D0, iq);
@@ -240,10 +243,10 @@ __device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s
     const double tr = radial_first(X, c0, sface, hbn, D0, iq, inward);
     const double tt = (T.nt > 1) ? theta_next(X, T.nt, c1, 0.0, K, upper) : RAY_NONE;
     const double tp = phi_next(X, T.np, c2, 0.0, K, up);
-    X.D(F_T, s) = 0.0; X.D(F_ACC, s) = 0.0; X.D(F_TR, s) = tr; X.D(F_TT, s) = tt; X.D(F_TP, s) = tp;
+    X.D(F_T, s) = 0.0; X.D(F_ACC, s) = acc0; X.D(F_TR, s) = tr; X.D(F_TT, s) = tt; X.D(F_TP, s) = tp;
     X.D(F_HBN, s) = hbn; X.D(F_D0, s) = D0; X.D(F_IQ, s) = iq; X.D(F_LIM, s) = lim;
     X.I(I_CELL, s) = pack_cell(c0, c1, c2);
-    X.I(I_INFO, s) = kind | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
+    X.I(I_INFO, s) = kind | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0) | (pk << PK_SHIFT);
 }
 
 // polrot_fast (transport.cuh) with the fast division / square root
@@ -339,6 +342,124 @@ struct Cnt {
 // events (called warp-converged: every lane of the warp handles one slot of the same list; !valid lanes idle)
 // ---------------------------------------------------------------------------------------------------
 
+// EMIT, planet source: emit_photon :1117-1266 + the thermal weight and the start of peel_thermal :599-621.
+// The cell comes from a binary search on the emissivity CDF (the reference scans it linearly, :1132-1155).
+template <class Sh>
+__device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A, int s, unsigned long long id, Cnt& C) {
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
+    double xr[5], xq;
+    unsigned nd = 0;
+    draws(X, A, s, id, nd, 4, xr); nd += 4;
+    const int ncdf = (T.nr - T.cell_depth) * T.nt * T.np;
+    const double samp = xr[0] * __ldg(T.emis_cdf + ncdf - 1);
+    int lo = -1, hi = ncdf - 1;      // first p with cdf[p] >= samp
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(T.emis_cdf + mid) >= samp) hi = mid; else lo = mid; }
+    const int c2 = hi % T.np, c1 = (hi / T.np) % T.nt, c0 = T.cell_depth + hi / (T.np * T.nt);
+    double rs = xr[1] * (X.r[c0 + 1] - X.r[c0]); rs = X.r[c0] + rs;
+    const double tc0 = __ldg(T.tcos + c1), tc1 = __ldg(T.tcos + c1 + 1);
+    double ct = xr[2] * (tc1 - tc0); ct = tc0 + ct;
+    const double st = sqrt(1.0 - ct * ct);
+    double phs;
+    if (T.np == 1) phs = 2.0 * PI * xr[3];
+    else if (c2 < T.np - 1) { phs = xr[3] * (X.pf[c2 + 1] - X.pf[c2]); phs = X.pf[c2] + phs; }
+    else { phs = xr[3] * (2.0 * PI - X.pf[c2]); phs = X.pf[c2] + phs; }
+    const double cp = cos(phs);
+    double sp = sqrt(1.0 - cp * cp);
+    if (phs > PI) sp = -sp;
+    double px = rs * st * cp, py = rs * st * sp, pz = rs * ct;
+    px = T.ox * px; py = T.oy * py; pz = T.oz * pz;
+    double dx, dy, dz, bias_weight = 1.0;
+    int e = 0;
+    if (L.photon_emission == 1) {
+        draws(X, A, s, id, nd, 2, xr); nd += 2;
+        const double al = 2.0 * xr[0] - 1.0, be = 2.0 * PI * xr[1];
+        const double cb = cos(be);
+        double sb = sqrt(1.0 - cb * cb);
+        if (be > PI) sb = -sb;
+        dx = sqrt(1.0 - al * al) * cb; dy = sqrt(1.0 - al * al) * sb; dz = al;
+    } else {
+        draws(X, A, s, id, nd, 2, xr); nd += 2;
+        const double yb = (1.0 + L.photon_bias) * tan(PI * xr[0] / 2.0) / sqrt(1.0 - L.photon_bias * L.photon_bias);
+        const double ths = acos((1.0 - yb * yb) / (1.0 + yb * yb));
+        const double be = 2.0 * PI * xr[1];
+        double r0 = px / (T.ox * T.ox), r1 = py / (T.oy * T.oy), r2 = pz / (T.oz * T.oz);
+        const double nrm = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+        r0 = r0 / nrm; r1 = r1 / nrm; r2 = r2 / nrm;
+        e = direction_cosine(cos(PI - ths), be, r0, r1, r2, dx, dy, dz);
+        bias_weight = (PI * sin(ths) * (1.0 + L.photon_bias * cos(ths))) / (2.0 * sqrt(1.0 - L.photon_bias * L.photon_bias));
+    }
+    (void)xq;
+    X.I(I_ND, s) = (int)nd;
+    X.I(I_HCELL, s) = pack_cell(c0, c1, c2);
+    X.D(F_PX, s) = px; X.D(F_PY, s) = py; X.D(F_PZ, s) = pz;
+    X.D(F_S1, s) = 0.0; X.D(F_S2, s) = 0.0; X.D(F_S3, s) = 0.0; X.D(F_TAU, s) = 0.0;
+    if (e) { err_count(A, e); ++C.n_err; X.D(F_S0, s) = 1.0; X.I(I_INFO, s) = K_DEAD; return true; }
+    if (fabs(dz) >= 1.0) err_count(A, 54);
+    X.D(F_DX, s) = dx; X.D(F_DY, s) = dy; X.D(F_DZ, s) = dz;
+    const double S0 = 1.0 * bias_weight / __ldg(T.cell_weight + c0 + T.nr * (c1 + T.nt * c2));
+    X.D(F_S0, s) = S0;
+    atomicAdd(A.O.flux, S0);
+    // peel_thermal :4519-4598: walk to the detector, deposit e^-tau / 4 pi x I (weight applied by DEP)
+    ++C.n_peel;
+    X.D(F_W0, s) = S0;
+    {
+        const double x_im = py * L.cos_dp - px * L.sin_dp;
+        const double y_im = pz * L.sin_dt - py * L.cos_dt * L.sin_dp - px * L.cos_dt * L.cos_dp;
+        const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
+        const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
+        X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1);
+    }
+    ray_setup(X, T, s, px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF, 0.0, PK_THERMAL);
+    return true;
+}
+
+// SURF (reflecting surface only): the transport walk reached the surface :755-774 -> absorbed, or Lambert reflection
+// (lambertian :1369-1402) followed by the start of peel_surface :4600-4650.  The optical depth of the walk is NOT
+// resampled: the reflected photon goes on with the same tau and the running sum (:766-776).
+template <class Sh>
+__device__ __forceinline__ bool ev_surface(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+    if (!valid) return false;
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
+    const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+    unsigned nd = (unsigned)X.I(I_ND, s);
+    double xr[5];
+    draws(X, A, s, id, nd, 1, xr); ++nd;
+    const double tw = X.D(F_T, s);
+    const double wx = X.D(F_PX, s) + tw * X.D(F_DX, s), wy = X.D(F_PY, s) + tw * X.D(F_DY, s), wz = X.D(F_PZ, s) + tw * X.D(F_DZ, s);
+    X.D(F_PX, s) = wx; X.D(F_PY, s) = wy; X.D(F_PZ, s) = wz;      // the photon now sits on the surface
+    if (xr[0] > L.surface_albedo) { X.I(I_ND, s) = (int)nd; X.I(I_INFO, s) = K_DEAD; return true; }
+    double s0 = wx / (T.ox * T.ox), s1 = wy / (T.oy * T.oy), s2 = wz / (T.oz * T.oz);
+    const double nrm = sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+    s0 = s0 / nrm; s1 = s1 / nrm; s2 = s2 / nrm;
+    draws(X, A, s, id, nd, 2, xr); nd += 2;
+    X.I(I_ND, s) = (int)nd;
+    const double al = sqrt(xr[0]), be = 2.0 * PI * xr[1];
+    double e0, e1, e2;
+    const int e = direction_cosine(al, be, s0, s1, s2, e0, e1, e2);
+    if (e) { err_count(A, e); ++C.n_err; X.I(I_INFO, s) = K_DEAD; return true; }
+    X.D(F_DX, s) = e0; X.D(F_DY, s) = e1; X.D(F_DZ, s) = e2;
+    X.D(F_S1, s) = 0.0; X.D(F_S2, s) = 0.0; X.D(F_S3, s) = 0.0;      // fully depolarised :1397-1400
+    const int cell = X.I(I_CELL, s);                                 // the cell above the surface face
+    const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+    X.I(I_HCELL, s) = cell;
+    const double tau = X.D(F_TAU, s), acc = X.D(F_ACC, s);
+    const double cos_angle = surface_cos_angle(A, wx, wy, wz);
+    if (cos_angle > 0.0) {
+        ++C.n_peel;
+        X.D(F_W0, s) = X.D(F_S0, s); X.D(F_W1, s) = acc; X.D(F_W2, s) = cos_angle;
+        const double x_im = wy * L.cos_dp - wx * L.sin_dp;
+        const double y_im = wz * L.sin_dt - wy * L.cos_dt * L.sin_dp - wx * L.cos_dt * L.cos_dp;
+        const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
+        const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
+        X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1);
+        ray_setup(X, T, s, wx, wy, wz, L.det[0], L.det[1], L.det[2], c0, c1, c2, T.cell_depth, K_PEEL, CUDART_INF, 0.0, PK_SURFACE);
+    } else
+        ray_setup(X, T, s, wx, wy, wz, e0, e1, e2, c0, c1, c2, T.cell_depth, K_WALK, tau, acc);
+    return true;
+}
+
 // EMIT: star emission (emit_photon :1008-1115 + initial_cell).  Returns true if a ray was set up.
 template <class Sh>
 __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
@@ -366,6 +487,10 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
             f[3] = X.D(F_S0, s); f[4] = X.D(F_S1, s); f[5] = X.D(F_S2, s); f[6] = X.D(F_S3, s); f[7] = (double)X.I(I_TNSC, s);
         }
     }
+    if (Sh::GEN && L.photon_source == 2 && X.I(I_ND, s) > 0) {   // emergent flux of a thermal photon that left the grid (:780, :953)
+        const int pinfo = X.I(I_INFO, s);
+        if ((pinfo & 3) == K_WALK && ((pinfo >> 8) & 15) == O_EXIT) atomicAdd(A.O.flux + 1, X.D(F_S0, s));
+    }
     X.I(I_ND, s) = 0;
     const unsigned long long k = base + (unsigned long long)__popc(vm & ((1u << lane) - 1u));
     if (k >= L.n_photons) { atomicAdd(X.misc, 1); return false; }
@@ -377,6 +502,7 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
         X.I(I_THLO, s) = (int)(unsigned)1469598103934665603ull; X.I(I_THHI, s) = (int)(unsigned)(1469598103934665603ull >> 32);
     }
     unsigned nd = 0;
+    if (Sh::GEN && L.photon_source == 2) return ev_emit_thermal(X, A, s, id, C);
     double xi, r_disk;
     if (L.limb_emission) {
         for (;;) { draws(X, A, s, id, nd, 1, &xi); ++nd; r_disk = sqrt(xi); if (r_disk > 0.9 || (Sh::TRACE && (X.I(I_FLAG, s) & 1))) break; }
@@ -576,7 +702,19 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     // Deposit.  When every depositing lane of the batch hits the same pixel (1x1 "photometry" detectors: phase
     // curves, spectra) the ten sums are reduced across the warp first, so the L2 sees one atomic per plane and
     // batch instead of 32 serialised ones on the same address.
-    const bool dep = valid && out == O_EXIT && tacc < 50.0 && pix >= 0;
+    const int pk = (Sh::GEN && valid) ? ((X.I(I_INFO, s) >> PK_SHIFT) & 3) : PK_SCATTER;
+    bool dep = valid && out == O_EXIT && tacc < 50.0 && pix >= 0;
+    double w_i = 0.0;            // surface / thermal peel: the only deposited quantity
+    if (Sh::GEN && pk != PK_SCATTER) {
+        dep = false;
+        if (valid && out == O_EXIT && tacc < 50.0) {
+            const double w = (pk == PK_THERMAL) ? exp(-tacc) / (4.0 * PI) : exp(-tacc) * X.D(F_W2, s) / PI;
+            w_i = w * X.D(F_W0, s);
+            if (!(w_i > 0.0 && w_i < 1.e100)) err_count(A, pk == PK_THERMAL ? 51 : 52);
+            else if (pix == -2) err_count(A, 60);
+            else dep = true;
+        }
+    }
     if (Sh::TRACE && dep) {   // the reference's deposit point in the walk record: (100, ix, iy, 0, 0)
         const unsigned long long pid = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
         int tl = X.I(I_TLEN, s);
@@ -594,8 +732,11 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
         }
         const size_t npx = (size_t)L.nx * L.ny;
         const int pix0 = __shfl_sync(FULL, pix, __ffs(dm) - 1);
-        const bool same = __all_sync(FULL, !dep || pix == pix0);
-        if (same && __popc(dm) > 2) {
+        const bool same = __all_sync(FULL, !dep || (pix == pix0 && pk == PK_SCATTER));
+        if (Sh::GEN && dep && pk != PK_SCATTER) {   // :4583-4585 / :4691-4693: Stokes I only
+            double* d = A.O.det + pix;
+            atomicAdd(d, w_i); atomicAdd(d + 4 * npx, w_i * w_i); atomicAdd(d + 8 * npx, 1.0);
+        } else if (same && __popc(dm) > 2) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
@@ -616,8 +757,18 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     }
     if (!valid) return false;
     const double tau = X.D(F_TAU, s);
-    if (tau < 0.0) { X.I(I_INFO, s) = K_DEAD; return true; }
     const int hc = X.I(I_HCELL, s);
+    if (Sh::GEN && pk == PK_THERMAL) {          // after peel_thermal the photon starts its tau pre-pass (:621-656)
+        ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
+                  hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, -1, K_PRE, CUDART_INF);
+        return true;
+    }
+    if (Sh::GEN && pk == PK_SURFACE) {          // the reflected photon goes on with its old tau and running sum (:766-776)
+        ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
+                  hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, A.T.cell_depth, K_WALK, tau, X.D(F_W1, s));
+        return true;
+    }
+    if (tau < 0.0) { X.I(I_INFO, s) = K_DEAD; return true; }
     ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
               hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, -1, K_WALK, tau);
     return true;
@@ -641,6 +792,8 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
     const double t = X.D(F_T, s);
     info &= 0xff;
     if (out == O_REST) {
+        if (Sh::GEN && L.flow_theta && kind == K_WALK)      // add_flow :5016-5047, polar crossings (:736-742)
+            atomicAdd(A.O.flow4 + (size_t)4 * (c0 + T.nr * (c1 + T.nt * c2)) + ((info & B_TUPPER) ? 2 : 3), X.D(F_S0, s));
         c1 += (info & B_TUPPER) ? 1 : -1;
         int upper;
         X.D(F_TT, s) = theta_next(X, T.nt, c1, t, K, upper);
@@ -661,11 +814,11 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
 // ---------------------------------------------------------------------------------------------------
 // block set-up and the marcher
 // ---------------------------------------------------------------------------------------------------
-template <int NT, int NP, bool TR>
-__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP, TR>& X, bool mark_empty) {
+template <int NT, int NP, bool TR, bool GN>
+__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP, TR, GN>& X, bool mark_empty) {
     const DevTables& T = A.T;
     const Lay lay(T.nr, T.nt, T.np, NP);
-    constexpr int RC = ShT<NP, TR>::RC;
+    constexpr int RC = ShT<NP, TR, GN>::RC;
     X.r = sm; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
     X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
     X.sd = sm + lay.o_sd;
@@ -709,6 +862,7 @@ struct Marcher {
     int nr, nt, depth;           // launch invariants kept in registers (the kernel parameters live in constant memory)
     const double* kext;
     int tl; unsigned long long th, pid;   // walk recorder (trace hook only; dead code otherwise)
+    double s0w;                           // Stokes I of the photon (latitudinal flow counters only)
 
     __device__ __forceinline__ void init(const DevTables& T) {
         slot = -1; c0 = cell12 = info = 0; dr = 1;
@@ -717,8 +871,9 @@ struct Marcher {
     }
 
     template <class Sh>
-    __device__ __forceinline__ void load(const Sh& X, int s) {
+    __device__ __forceinline__ void load(const Sh& X, const KernelArgs& A, int s) {
         slot = s;
+        if (Sh::GEN && A.L.flow_theta) s0w = X.D(F_S0, s);
         t = X.D(F_T, s); acc = X.D(F_ACC, s); tr = X.D(F_TR, s); tt = X.D(F_TT, s); tp = X.D(F_TP, s);
         hbn = X.D(F_HBN, s); D0 = X.D(F_D0, s); iq = X.D(F_IQ, s); lim = X.D(F_LIM, s);
         const int cell = X.I(I_CELL, s);
@@ -759,6 +914,8 @@ struct Marcher {
         if (!radial) return (tn == tt) ? O_REST : O_RESP;
         const int up = (dr > 0) ? 1 : 0;
         const int f = c0 + up;
+        if (Sh::GEN && A.L.flow_theta && (info & 3) == K_WALK)      // add_flow :5016-5047, radial crossings (:730-735)
+            atomicAdd(A.O.flow4 + (size_t)4 * ((kb - kext) + c0) + (up ? 0 : 1), s0w);
         if (f == nr) return O_EXIT;
         if (f == depth) return O_SURF;
         c0 += dr;
@@ -784,7 +941,11 @@ struct Marcher {
         if (out == O_ERR) {
             err_count(A, 31); ++C.n_err;
             err_count(A, kind == K_PRE ? 2 : (kind == K_WALK ? 3 : 43));
-        } else if (out == O_SURF && kind == K_WALK) { ++C.n_surf; X.I(I_ND, slot) += 1; }   // absorbed (:755-764: one draw)
+        } else if (out == O_SURF && kind == K_WALK) {
+            ++C.n_surf;
+            if (Sh::GEN && A.L.surface_albedo > 0.0) return L_SURF;      // absorbed or reflected: decided by the SURF event
+            X.I(I_ND, slot) += 1;                                        // black surface: absorbed (:755-764: one draw)
+        }
         return c_list[kind][out];
     }
 
@@ -804,6 +965,7 @@ __device__ __forceinline__ bool run_event(const Sh& X, const KernelArgs& A, int 
     if (l == L_DEP) return ev_deposit(X, A, valid, s, C);
     if (l == L_RES) return ev_resolve(X, A, valid, s);
     if (l == L_PRE) return ev_pre(X, A, valid, s, C);
+    if (Sh::GEN && l == L_SURF) return ev_surface(X, A, valid, s, C);
     return ev_emit(X, A, valid, s, C);
 }
 
@@ -825,9 +987,9 @@ template <int NT, int NP, int MINB, int NRAY>
 __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
-    using Sh = ShT<NP, false>;
+    using Sh = ShT<NP, false, false>;
     Sh X;
-    block_setup<NT, NP, false>(A, smraw, X, false);
+    block_setup<NT, NP, false, false>(A, smraw, X, false);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 32;      // marcher steps per round
@@ -863,7 +1025,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
                     }
                     base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
                     const int rank = __popc(fm & lt);
-                    if (M[j].slot < 0 && rank < n) M[j].load(X, X.Q(L_RDY, base + rank));
+                    if (M[j].slot < 0 && rank < n) M[j].load(X, A, X.Q(L_RDY, base + rank));
                 }
             }
             // ---- `inner` steps of every ray
@@ -959,13 +1121,13 @@ __device__ __forceinline__ void ring_put(volatile short* e, int s) {
     *e = (short)s;
 }
 
-template <int NT, int NP, int MINB, bool TR>
+template <int NT, int NP, int MINB, bool TR, bool GN>
 __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
-    using Sh = ShT<NP, TR>;
+    using Sh = ShT<NP, TR, GN>;
     Sh X;
-    block_setup<NT, NP, TR>(A, smraw, X, true);
+    block_setup<NT, NP, TR, GN>(A, smraw, X, true);
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
@@ -1008,7 +1170,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             if (M.slot < 0 && rank < n) {
                 const int s = ring_take(&X.Q(L_RDY, base + rank));
                 __threadfence_block();
-                M.load(X, s);
+                M.load(X, A, s);
             }
         }
         // ---- `inner` steps in a tight loop, then the write-back of what ended
@@ -1034,7 +1196,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         }
         // ---- events: a full batch if there is one; a partial one if this warp has little else to do
         int av = 0;
-        if (lane < 5) av = vtail[lane] - vhead[lane];
+        if (lane < N_EVENT_LISTS) av = vtail[lane] - vhead[lane];
         const unsigned fullm = __ballot_sync(FULL, av >= 32);
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
@@ -1042,10 +1204,10 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
         if (fullm && (we == 0 || event_warp || nactive == 0))
             l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
-                : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
+                : (fullm & (1u << L_SURF)) ? L_SURF : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
         else if (anym && rdy_empty && nactive < starve && (!event_warp || ++idle > 8))
             l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_DEP)) ? L_DEP : (anym & (1u << L_H)) ? L_H
-                : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
+                : (anym & (1u << L_SURF)) ? L_SURF : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
         if (l >= 0) {
             int base = 0, n = 0;
             if (lane == 0) {

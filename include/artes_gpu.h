@@ -181,8 +181,8 @@ int  artes_gpu_device_info(const artes_gpu_ctx* ctx, int* sm_count, int* cc_majo
                            char* name, int name_len);
 
 /* Which transport engine the last run / trace of this context used: 1 = persistent-lane engine (faithful mode;
- * thermal source, reflecting surface, flow counters, oblate planets), 2 = ray/event engine (fast mode, everything
- * else).  Lets tests assert that the production path is the one that ran. */
+ * fast mode with flow_global or an oblate planet), 2 = ray/event engine (fast mode, everything else).  Lets tests
+ * assert that the production path is the one that ran. */
 int  artes_gpu_last_engine(const artes_gpu_ctx* ctx);
 
 /* FP64 / FP32 FMA peak microbenchmark (roofline denominator): returns TFLOP/s. */

@@ -111,10 +111,8 @@ def test_crossing_sequences_bit_exact_vs_oracle(atmospheres, oracle_factory, gpu
     L = make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, fstop=0.03, **kw)
     ro = o.trace(L, xi, max_rec=4)
     rg = g.trace(L, xi, max_rec=4)
-    # fast mode walks the ray/event engine (the production path) wherever it applies; everything else, and the
-    # faithful mode, the persistent-lane engine
-    plain = not kw.get("surface_albedo")
-    assert g.last_engine() == (2 if (mode == abi.MODE_FAST and plain) else 1)
+    # fast mode walks the ray/event engine (the production path); the faithful mode the persistent-lane engine
+    assert g.last_engine() == (2 if mode == abi.MODE_FAST else 1)
     same = (ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])
     assert same.all(), f"{(~same).sum()} of {n} sequences differ"
     np.testing.assert_array_equal(ro["head"], rg["head"])
@@ -142,6 +140,7 @@ def test_trace_thermal_source(atmospheres, oracle_factory):
             L = make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, fstop=0.03, photon_source=2,
                             photon_emission=emission, nx=1, ny=1)
             ro, rg = o.trace(L, xi), g.trace(L, xi)
+            assert g.last_engine() == (2 if mode == abi.MODE_FAST else 1)
             assert ((ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])).all()
         L = make_launch(mode=abi.MODE_FAST, n_photons=n, x_max=xm, y_max=xm, seed=3, photon_source=2,
                         photon_emission=emission, nx=1, ny=1)
@@ -221,6 +220,48 @@ def test_ray_event_engine_same_stream_vs_oracle(atmospheres, oracle_factory, gpu
     np.testing.assert_allclose(b["det"][0][same], a["det"][0][same], rtol=2e-4, atol=1e-6 * scale)
     np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=2e-5, atol=1e-7 * scale)
     np.testing.assert_allclose(b["det"][1].sum(axis=(1, 2)), a["det"][1].sum(axis=(1, 2)), rtol=2e-4, atol=1e-9 * scale * scale)
+
+
+def test_ray_event_engine_surface_flows_thermal(atmospheres, oracle_factory, gpu_factory):
+    """The general paths of the ray/event engine: Lambert surface + peel_surface, latitudinal flow counters,
+    thermal source + peel_thermal -- same Philox stream as the oracle."""
+    from artes_b200.lib import GpuTransport
+    atm = atmospheres("c4_mie_patches")
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(mode=abi.MODE_FAST, n_photons=50000, x_max=xm, y_max=xm, seed=17, nx=32, ny=32, det_phi=math.radians(40.0),
+                    surface_albedo=0.4, flow_theta=1)
+    a, b = o.run(L, flows=True), g.run(L, flows=True)
+    assert g.last_engine() == 2
+    for k in ("n_emit", "n_cell_face", "n_scatter", "n_peel", "n_surface", "n_draws"):
+        assert abs(a["stats"][k] - b["stats"][k]) <= max(2, 2e-5 * a["stats"][k]), (k, a["stats"][k], b["stats"][k])
+    assert a["stats"]["n_surface"] > 1000 and a["stats"]["n_peel"] > a["stats"]["n_scatter"]      # surface peels happened
+    scale = np.abs(a["det"][0]).max()
+    np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=5e-5, atol=1e-7 * scale)
+    assert np.abs(a["det"][2] - b["det"][2]).sum() <= max(4, 5e-5 * a["det"][2].sum())
+    np.testing.assert_allclose(b["flow4"], a["flow4"], rtol=1e-4, atol=2e-4 * np.abs(a["flow4"]).max())
+    assert np.abs(a["flow4"]).sum() > 0
+    # thermal source
+    atm3 = atmospheres("c3_molecular")
+    o3, depth = oracle_factory(atm3, 0, 2)
+    vol = host.cell_volume(atm3.rfront, atm3.thetafront(), atm3.phifront())
+    cw, lum, cdf = host.thermal_tables(depth, atm3.k_abs[0], atm3.temperature, vol, atm3.wavelengths[0] * 1e-6,
+                                       atm3.nr, atm3.ntheta, atm3.nphi)
+    o3.set_wavelength(atm3.k_sca[0], atm3.k_abs[0], atm3.uniq[0], atm3.cell_to_uniq[0], depth, cw, cdf)
+    g3 = GpuTransport((0,))
+    g3.set_grid(atm3.rfront, atm3.thetafront(), atm3.thetaplane(), atm3.phifront())
+    g3.set_wavelength(atm3.k_sca[0], atm3.k_abs[0], atm3.uniq[0], atm3.cell_to_uniq[0], depth, cw, cdf)
+    xm3 = 1.3 * atm3.rfront[-1]
+    for emission in (1, 2):
+        L3 = make_launch(mode=abi.MODE_FAST, n_photons=30000, x_max=xm3, y_max=xm3, seed=5, photon_source=2, photon_emission=emission,
+                         nx=4, ny=4, flow_theta=1)
+        a3, b3 = o3.run(L3, flows=True), g3.run(L3, flows=True)
+        assert g3.last_engine() == 2
+        np.testing.assert_allclose(b3["flux"], a3["flux"], rtol=1e-8)
+        np.testing.assert_allclose(b3["det"][0, 0].sum(), a3["det"][0, 0].sum(), rtol=2e-5)
+        np.testing.assert_allclose(b3["flow4"], a3["flow4"], rtol=1e-4, atol=2e-4 * np.abs(a3["flow4"]).max())
+        assert abs(a3["stats"]["n_cell_face"] - b3["stats"]["n_cell_face"]) <= max(2, 2e-5 * a3["stats"]["n_cell_face"])
 
 
 def test_fast_mode_oblate_planet_same_stream(atmospheres):
