@@ -76,7 +76,8 @@ struct Lay {
     __host__ __device__ Lay(int nr, int nt, int np, int NP) {
         o_r2 = nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
         o_tp = o_pf + np; o_sd = o_tp + (nt + 2) / 2 + 1; n_tab = o_sd;
-        bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
+        bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4
+                + (size_t)32 * (64 + 160) * 2;      // control words, then the warp-private ray stock / done list of kernel C (<= 32 warps)
     }
 };
 
@@ -249,6 +250,45 @@ __device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s
     X.I(I_INFO, s) = kind | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0) | (pk << PK_SHIFT);
 }
 
+// 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a): a warp instruction whose lanes read scattered
+// 32-byte pieces costs one L1 wavefront per lane whatever the width, so the wide form halves the load of the L1
+// data pipe (65 % busy in the profile of the 128-bit version) for the matrix rows, CDF entries and photon records.
+__device__ __forceinline__ void ldg256_nc(const double* p, double& a, double& b, double& c, double& d) {   // read-only tables
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {      // data written by this kernel
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// matrix_at_deg (transport.cuh) with 256-bit row reads
+__device__ __forceinline__ void matrix_at_deg_f(const DevTables& T, int cellidx, double deg, double F[16]) {
+    int lo, up;
+    const double fl = floor(deg);
+    if (deg - fl > 0.5) { up = (int)fl + 2; lo = (int)fl + 1; }
+    else { up = (int)fl + 1; lo = (int)fl; }
+    const double* base = T.M + (size_t)__ldg(T.c2u + cellidx) * (180 * 16);
+    if (up <= 1 || lo >= 180) {
+        const double* m = base + (up <= 1 ? 0 : 179) * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ldg256_nc(m + 4 * i, F[4 * i], F[4 * i + 1], F[4 * i + 2], F[4 * i + 3]);
+    } else {
+        const double* m0 = base + (lo - 1) * 16;
+        const double* m1 = base + (up - 1) * 16;
+        const double w = deg - ((double)lo - 0.5);
+        double v0[16], v1[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ldg256_nc(m0 + 4 * i, v0[4 * i], v0[4 * i + 1], v0[4 * i + 2], v0[4 * i + 3]);
+            ldg256_nc(m1 + 4 * i, v1[4 * i], v1[4 * i + 1], v1[4 * i + 2], v1[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) F[i] = (v1[i] - v0[i]) * w + v0[i];
+    }
+}
+
 // polrot_fast (transport.cuh) with the fast division / square root
 __device__ __forceinline__ int polrot_f(double c2a, double s2a, bool flip, double nc2, const double Sin[4],
                                         const double F[16], double Sout[4], bool peeling, int& soft) {
@@ -316,10 +356,11 @@ __device__ __forceinline__ int sample_angles_f(const KernelArgs& A, double xi1, 
     if (g.flip) { g.sb = -g.sb; g.cb = -g.cb; }
     const double c2b = g.cb * g.cb - g.sb * g.sb, s2b = 2.0 * g.sb * g.cb;
     const double w1 = S[0], w2 = c2b * S[1] + s2b * S[2], w3 = c2b * S[2] - s2b * S[1], w4 = S[3];
-    const double2* tab = reinterpret_cast<const double2*>(T.cdfP + (size_t)u * (181 * 4));
+    const double* tab = T.cdfP + (size_t)u * (181 * 4);
     auto cumP = [&](int i) {
-        double2 q01 = __ldg(tab + 2 * i), q23 = __ldg(tab + 2 * i + 1);
-        return w1 * q01.x + w2 * q01.y + w3 * q23.x + w4 * q23.y;
+        double q0, q1, q2, q3;
+        ldg256_nc(tab + 4 * i, q0, q1, q2, q3);
+        return w1 * q0 + w2 * q1 + w3 * q2 + w4 * q3;
     };
     samp = xi3 * cumP(180);
     lo = search6(cumP, samp, ylo, yhi);
@@ -579,16 +620,24 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     const int cell = X.I(I_CELL, s);
     const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     const int ci = c0 + T.nr * (c1 + T.nt * c2);
-    double dx = X.D(F_DX, s), dy = X.D(F_DY, s), dz = X.D(F_DZ, s);
+    // the cold record in 32-byte pieces: [px py pz dx] [dy dz S0 S1] [S2 S3 tau W0] [W1 W2 W3 hcell|pix] [nd|idlo idhi|tlen ...]
+    double* rec = X.cold + (size_t)s * REC;
+    double hx, hy, hz, dx, dy, dz, S[4], tau0, w0_, i0_, i1_, i2_, i3_;
+    ldg256(rec, hx, hy, hz, dx);
+    ldg256(rec + 4, dy, dz, S[0], S[1]);
+    ldg256(rec + 8, S[2], S[3], tau0, w0_);
+    ldg256(rec + 16, i0_, i1_, i2_, i3_);
+    (void)w0_; (void)i2_; (void)i3_;
     // the marcher stopped after adding the crossing that overshoots tau: step back by the overshoot (:705-720)
-    const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - X.D(F_TAU, s), __ldg(T.kext + ci));
-    const double px = X.D(F_PX, s) + tpos * dx, py = X.D(F_PY, s) + tpos * dy, pz = X.D(F_PZ, s) + tpos * dz;
-    double S[4] = {X.D(F_S0, s), X.D(F_S1, s), X.D(F_S2, s), X.D(F_S3, s)};
+    const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - tau0, __ldg(T.kext + ci));
+    const double px = hx + tpos * dx, py = hy + tpos * dy, pz = hz + tpos * dz;
     double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
     if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
     const double peel_deg = acos(mu) * (180.0 / PI);
-    const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
-    unsigned nd = (unsigned)X.I(I_ND, s);
+    // ints of the record: piece 4 = [nd | idlo] [idhi | tlen] ...
+    const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
+    const unsigned long long id = (w16 >> 32) | (w17 << 32);
+    unsigned nd = (unsigned)w16;
     bool alive = L.photon_scattering != 0;
     if (Sh::TRACE && (X.I(I_FLAG, s) & 1)) alive = false;       // injected stream used up (test hook only)
     double xr[5];
@@ -614,7 +663,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     double W[4] = {0.0, 0.0, 0.0, 0.0};
     {
         double F[16];
-        matrix_at_deg(T, ci, peel_deg, F);
+        matrix_at_deg_f(T, ci, peel_deg, F);
         if (!(fabs(dz) < 1.0)) err_count(A, 45);
         else {
             const double smu = fsqrt(1.0 - mu * mu);
@@ -671,7 +720,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
         }
         if (!e) {
             double F[16], Sn[4];
-            matrix_at_deg(T, ci, g.deg, F);
+            matrix_at_deg_f(T, ci, g.deg, F);
             const double nc2 = fdiv(dz - e2 * g.alpha, g.sT * fsqrt(1.0 - e2 * e2));
             int soft = 0;
             e = polrot_f(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
@@ -681,13 +730,14 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
         if (e) { err_count(A, e); ++C.n_err; }
         else { const double xi = xr[4]; ++nd; if (Sh::TRACE && (int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; tau = -log(1.0 - xi); }
     }
-    X.D(F_PX, s) = px; X.D(F_PY, s) = py; X.D(F_PZ, s) = pz; X.D(F_DX, s) = dx; X.D(F_DY, s) = dy; X.D(F_DZ, s) = dz;
-    X.D(F_S0, s) = S[0]; X.D(F_S1, s) = S[1]; X.D(F_S2, s) = S[2]; X.D(F_S3, s) = S[3]; X.D(F_TAU, s) = tau;
-    X.D(F_W0, s) = W[0]; X.D(F_W1, s) = W[1]; X.D(F_W2, s) = W[2]; X.D(F_W3, s) = W[3];
+    stg256(rec, px, py, pz, dx);
+    stg256(rec + 4, dy, dz, S[0], S[1]);
+    stg256(rec + 8, S[2], S[3], tau, W[0]);
+    stg256(rec + 12, W[1], W[2], W[3], __longlong_as_double((long long)((unsigned long long)(unsigned)cell | ((unsigned long long)(unsigned)pix << 32))));
 #ifdef E2_DEBUG
-    if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, X.D(F_TAU, s), X.D(F_ACC, s), X.D(F_T, s));
+    if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, tau0, X.D(F_ACC, s), X.D(F_T, s));
 #endif
-    X.I(I_PIX, s) = pix; X.I(I_ND, s) = (int)nd; X.I(I_HCELL, s) = cell;
+    X.I(I_ND, s) = (int)nd;
     ray_setup(X, T, s, px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF);
     return true;
 }
@@ -698,7 +748,17 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     const LaunchArgs& L = A.L;
     const int out = valid ? ((X.I(I_INFO, s) >> 8) & 15) : O_NONE;
     const double tacc = valid ? X.D(F_ACC, s) : 0.0;
-    const int pix = valid ? X.I(I_PIX, s) : -1;
+    // the cold record in 32-byte pieces (see ev_interact); an idle lane reads slot 0's record and ignores it
+    const double* rec = X.cold + (size_t)s * REC;
+    double hx, hy, hz, dx, dy, dz, s0_, s1_, s2_, s3_, tau, W0, W1, W2, W3, ipk;
+    ldg256(rec, hx, hy, hz, dx);
+    ldg256(rec + 4, dy, dz, s0_, s1_);
+    ldg256(rec + 8, s2_, s3_, tau, W0);
+    ldg256(rec + 12, W1, W2, W3, ipk);
+    (void)s0_; (void)s1_; (void)s2_; (void)s3_;
+    const unsigned long long w15 = (unsigned long long)__double_as_longlong(ipk);
+    const int hc = (int)(unsigned)w15;
+    const int pix = valid ? (int)(unsigned)(w15 >> 32) : -1;
     // Deposit.  When every depositing lane of the batch hits the same pixel (1x1 "photometry" detectors: phase
     // curves, spectra) the ten sums are reduced across the warp first, so the L2 sees one atomic per plane and
     // batch instead of 32 serialised ones on the same address.
@@ -708,8 +768,8 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     if (Sh::GEN && pk != PK_SCATTER) {
         dep = false;
         if (valid && out == O_EXIT && tacc < 50.0) {
-            const double w = (pk == PK_THERMAL) ? exp(-tacc) / (4.0 * PI) : exp(-tacc) * X.D(F_W2, s) / PI;
-            w_i = w * X.D(F_W0, s);
+            const double w = (pk == PK_THERMAL) ? exp(-tacc) / (4.0 * PI) : exp(-tacc) * W2 / PI;
+            w_i = w * W0;
             if (!(w_i > 0.0 && w_i < 1.e100)) err_count(A, pk == PK_THERMAL ? 51 : 52);
             else if (pix == -2) err_count(A, 60);
             else dep = true;
@@ -727,7 +787,7 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (dep) {
             const double w = exp(-tacc);
-            v[0] = w * X.D(F_W0, s); v[1] = -(w * X.D(F_W1, s)); v[2] = w * X.D(F_W2, s); v[3] = w * X.D(F_W3, s);
+            v[0] = w * W0; v[1] = -(w * W1); v[2] = w * W2; v[3] = w * W3;
             v[4] = v[0] * v[0]; v[5] = v[1] * v[1]; v[6] = v[2] * v[2]; v[7] = v[3] * v[3];
         }
         const size_t npx = (size_t)L.nx * L.ny;
@@ -756,20 +816,18 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
         }
     }
     if (!valid) return false;
-    const double tau = X.D(F_TAU, s);
-    const int hc = X.I(I_HCELL, s);
     if (Sh::GEN && pk == PK_THERMAL) {          // after peel_thermal the photon starts its tau pre-pass (:621-656)
-        ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
+        ray_setup(X, A.T, s, hx, hy, hz, dx, dy, dz,
                   hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, -1, K_PRE, CUDART_INF);
         return true;
     }
     if (Sh::GEN && pk == PK_SURFACE) {          // the reflected photon goes on with its old tau and running sum (:766-776)
-        ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
-                  hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, A.T.cell_depth, K_WALK, tau, X.D(F_W1, s));
+        ray_setup(X, A.T, s, hx, hy, hz, dx, dy, dz,
+                  hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, A.T.cell_depth, K_WALK, tau, W1);
         return true;
     }
     if (tau < 0.0) { X.I(I_INFO, s) = K_DEAD; return true; }
-    ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
+    ray_setup(X, A.T, s, hx, hy, hz, dx, dy, dz,
               hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, -1, K_WALK, tau);
     return true;
 }
@@ -1200,6 +1258,157 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const unsigned fullm = __ballot_sync(FULL, av >= 32);
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
+        int l = -1;
+        // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
+        if (fullm && (we == 0 || event_warp || nactive == 0))
+            l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
+                : (fullm & (1u << L_SURF)) ? L_SURF : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
+        else if (anym && rdy_empty && nactive < starve && (!event_warp || ++idle > 8))
+            l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_DEP)) ? L_DEP : (anym & (1u << L_H)) ? L_H
+                : (anym & (1u << L_SURF)) ? L_SURF : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
+        if (l >= 0) {
+            int base = 0, n = 0;
+            if (lane == 0) {
+                const int h = vhead[l];
+                n = min(32, vtail[l] - h);
+                if (n > 0 && atomicCAS(X.head + l, h, h + n) == h) base = h; else n = 0;
+            }
+            base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
+            if (n > 0) {
+                idle = 0;
+                const bool valid = lane < n;
+                int s = 0;
+                if (valid) s = ring_take(&X.Q(l, base + lane));
+                __threadfence_block();
+                const bool push = run_event(X, A, l, valid, s, C);
+                __threadfence_block();
+                const unsigned pm = __ballot_sync(FULL, push);
+                if (pm) {
+                    const int leader = __ffs(pm) - 1;
+                    int pb = 0;
+                    if (lane == leader) pb = atomicAdd(X.tail + L_RDY, __popc(pm));
+                    pb = __shfl_sync(FULL, pb, leader);
+                    if (push) ring_put(&X.Q(L_RDY, pb + __popc(pm & lt)), s);
+                }
+            }
+        }
+    }
+    flush_counters(A, C);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel C: kernel B with a warp-private stock of ready rays and a warp-private list of ended rays, so that a lane
+// whose ray ends inside a pass takes the next one at the following switch point (every `sub` steps) without any
+// block-level traffic; the block's rings are touched once per pass.
+// ---------------------------------------------------------------------------------------------------
+template <int NT, int NP, int MINB, bool TR, bool GN>
+__global__ void __launch_bounds__(NT, MINB) transport4_kernel(const __grid_constant__ KernelArgs A) {
+    extern __shared__ double smraw[];
+    const DevTables& T = A.T;
+    using Sh = ShT<NP, TR, GN>;
+    Sh X;
+    block_setup<NT, NP, TR, GN>(A, smraw, X, true);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
+    Marcher M; M.init(T);
+    volatile int* vhead = X.head;
+    volatile int* vtail = X.tail;
+    volatile int* vmisc = X.misc;
+    const int starve = 8;                                        // take partial batches when fewer lanes than this march
+    // Soft warp specialisation: the last `we` warps of the block only run events (they never claim rays), the others
+    // only march and leave full batches to them (they still take batches when they have nothing to march).  Every
+    // warp then loops over a small part of the kernel's code -- the instruction cache, not the register file, is
+    // what the roles are for.  we = 0: every warp does both.
+    const int we = A.L.e2_trips > 0 ? min(A.L.e2_trips, NT / 32 - 1) : 0;
+    const bool event_warp = (int)(threadIdx.x >> 5) >= NT / 32 - we;
+    int idle = 0;
+    // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100)
+    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / 2 + 2));
+
+    // warp-private stock of ready rays and list of ended rays (shorts, in the block's shared memory after the rings)
+    constexpr int WQ = 64, WD = 160;
+    short* wq = reinterpret_cast<short*>(X.misc + 32) + (threadIdx.x >> 5) * (WQ + WD);
+    short* wd = wq + WQ;
+    int wq_n = 0, wd_n = 0, out = O_NONE;
+    const int sub = 4;                                           // steps between two switch points
+
+    for (;;) {
+        if (vmisc[0] >= NP) break;
+        // ---- refill the warp's private stock of ready rays (one CAS on the block's ready ring per pass)
+        bool rdy_empty = event_warp;
+        if (!event_warp && wq_n < 32) {
+            int base = 0, n = 0;
+            if (lane == 0) {
+                const int want = WQ - wq_n;
+                int h = vhead[L_RDY];
+                for (;;) {
+                    n = min(want, vtail[L_RDY] - h);
+                    if (n <= 0) { n = 0; break; }
+                    const int old = atomicCAS(X.head + L_RDY, h, h + n);
+                    if (old == h) { base = h; break; }
+                    h = old;
+                }
+            }
+            base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
+            for (int i = lane; i < n; i += 32) wq[wq_n + i] = (short)ring_take(&X.Q(L_RDY, base + i));
+            __threadfence_block();
+            __syncwarp();
+            wq_n += n;
+            rdy_empty = wq_n == 0;
+        }
+        // ---- `inner` steps in sub-passes of `sub`; before each sub-pass the lanes whose ray ended write it back, note it
+        // on the warp's done list and take a new ray from the warp's stock (ballot + popc only: no atomics, no fences)
+        if (!event_warp) {
+            unsigned n_step = 0;
+            for (int k0 = 0; k0 <= inner; k0 += sub) {
+                int lst = -1;
+                if (M.slot >= 0 && out != O_NONE) { lst = M.finish(X, A, C, out); out = O_NONE; }
+                const unsigned dm = __ballot_sync(FULL, lst >= 0);
+                if (dm) {
+                    if (lst >= 0) { wd[wd_n + __popc(dm & lt)] = (short)(M.slot | (lst << 12)); M.slot = -1; }
+                    wd_n += __popc(dm);
+                }
+                if (k0 >= inner) break;                       // (the last turn only retires what ended in the last sub-pass)
+                const unsigned fm = __ballot_sync(FULL, M.slot < 0);
+                if (fm && wq_n > 0) {
+                    const int n = min(__popc(fm), wq_n);
+                    const int rank = __popc(fm & lt);
+                    if (M.slot < 0 && rank < n) {
+                        M.load(X, A, (int)wq[wq_n - 1 - rank]);
+                        out = ((M.info & 3) == K_DEAD) ? O_DEAD : O_NONE;
+                    }
+                    wq_n -= n;
+                }
+#pragma unroll 1
+                for (int k = 0; k < sub; ++k)
+                    if (M.slot >= 0 && out == O_NONE) out = M.step(X, A, n_step);
+            }
+            C.n_cf += n_step;
+            // ---- hand the ended rays of this pass to their event lists
+            if (wd_n > 0) {
+                __threadfence_block();
+                __syncwarp();
+                for (int b0 = 0; b0 < wd_n; b0 += 32) {
+                    const int e = (b0 + lane < wd_n) ? (int)wd[b0 + lane] : -1;
+                    const int lst = (e >= 0) ? (e >> 12) : -1, slot = e & 0xfff;
+                    const unsigned g = __match_any_sync(FULL, lst);
+                    const int leader = __ffs(g) - 1;
+                    int base = 0;
+                    if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (lst >= 0) ring_put(&X.Q(lst, base + __popc(g & lt)), slot);
+                }
+                __syncwarp();
+                wd_n = 0;
+            }
+        }
+        // ---- events: a full batch if there is one; a partial one if this warp has little else to do
+        int av = 0;
+        if (lane < N_EVENT_LISTS) av = vtail[lane] - vhead[lane];
+        const unsigned fullm = __ballot_sync(FULL, av >= 32);
+        const unsigned anym = __ballot_sync(FULL, av > 0);
+        const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0)) + wq_n;
         int l = -1;
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
         if (fullm && (we == 0 || event_warp || nactive == 0))
