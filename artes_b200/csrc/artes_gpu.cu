@@ -306,6 +306,8 @@ int artes_gpu_set_grid(artes_gpu_ctx* ctx, int nr, int ntheta, int nphi, const d
     }
     std::vector<double> cdfA(2 * 181, 0.0);  // fast-mode prefix sums of cos2beta / sin2beta
     for (int i = 1; i <= 180; ++i) { cdfA[i] = cdfA[i - 1] + ctx->cos2beta[i - 1]; cdfA[181 + i] = cdfA[181 + i - 1] + ctx->sin2beta[i - 1]; }
+    std::vector<double> cdfA2(2 * 181);
+    for (int i = 0; i <= 180; ++i) { cdfA2[2 * i] = cdfA[i]; cdfA2[2 * i + 1] = cdfA[181 + i]; }
     std::vector<int> tp(thetaplane, thetaplane + ntheta + 1);
     for (auto& d : ctx->devs) {
         CU(cudaSetDevice(d.dev));
@@ -325,6 +327,7 @@ int artes_gpu_set_grid(artes_gpu_ctx* ctx, int nr, int ntheta, int nphi, const d
         rc |= upload(ctx, d, d.grid_allocs, pcos.data(), pcos.size(), &T.pcos);
         rc |= upload(ctx, d, d.grid_allocs, trig.data(), trig.size(), &T.trig);
         rc |= upload(ctx, d, d.grid_allocs, cdfA.data(), cdfA.size(), &T.cdfA);
+        rc |= upload(ctx, d, d.grid_allocs, cdfA2.data(), cdfA2.size(), &T.cdfA2);
         if (rc) return rc;
         CU(cudaStreamSynchronize(d.stream));
     }

@@ -98,6 +98,19 @@ struct ShT {                     // pointers into the block's shared memory
     __device__ __forceinline__ short& Q(int l, int pos) const { return q[l * RC + (pos & (RC - 1))]; }
 };
 
+// 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a): a warp instruction whose lanes read scattered
+// 32-byte pieces costs one L1 wavefront per lane whatever the width, so the wide form halves the load of the L1
+// data pipe (65 % busy in the profile of the 128-bit version) for the matrix rows, CDF entries and photon records.
+__device__ __forceinline__ void ldg256_nc(const double* p, double& a, double& b, double& c, double& d) {   // read-only tables
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {      // data written by this kernel
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __device__ __forceinline__ int pack_cell(int c0, int c1, int c2) { return c0 | (c1 << 10) | (c2 << 20); }
 
 // Philox draws nd .. nd+4 of photon `id` (at most two counter blocks)
@@ -250,19 +263,6 @@ __device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s
     X.I(I_INFO, s) = kind | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0) | (pk << PK_SHIFT);
 }
 
-// 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a): a warp instruction whose lanes read scattered
-// 32-byte pieces costs one L1 wavefront per lane whatever the width, so the wide form halves the load of the L1
-// data pipe (65 % busy in the profile of the 128-bit version) for the matrix rows, CDF entries and photon records.
-__device__ __forceinline__ void ldg256_nc(const double* p, double& a, double& b, double& c, double& d) {   // read-only tables
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {      // data written by this kernel
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-
 // matrix_at_deg (transport.cuh) with 256-bit row reads
 __device__ __forceinline__ void matrix_at_deg_f(const DevTables& T, int cellidx, double deg, double F[16]) {
     int lo, up;
@@ -339,11 +339,11 @@ __device__ __forceinline__ int sample_angles_f(const KernelArgs& A, double xi1, 
                                                      int cellidx, FastAngles& g) {
     const DevTables& T = A.T;
     const int u = __ldg(T.c2u + cellidx);
-    const double p11 = __ldg(T.p1k + 4 * u), p12 = __ldg(T.p1k + 4 * u + 1), p13 = __ldg(T.p1k + 4 * u + 2), p14 = __ldg(T.p1k + 4 * u + 3);
+    double p11, p12, p13, p14;
+    ldg256_nc(T.p1k + 4 * u, p11, p12, p13, p14);
     const double Ac = p11 * S[0] + p14 * S[3], Bc = p12 * S[1] + p13 * S[2], Cc = p12 * S[2] - p13 * S[1];
-    const double* pc2 = T.cdfA;
-    const double* ps2 = T.cdfA + 181;
-    auto cumA = [&](int i) { return Ac * (double)i + Bc * __ldg(pc2 + i) + Cc * __ldg(ps2 + i); };
+    const double2* pcs = reinterpret_cast<const double2*>(T.cdfA2);
+    auto cumA = [&](int i) { const double2 q = __ldg(pcs + i); return Ac * (double)i + Bc * q.x + Cc * q.y; };
     double samp = xi1 * cumA(180);
     double ylo, yhi;
     int lo = search6(cumA, samp, ylo, yhi);   // bin lo: cum(lo) < samp <= cum(lo + 1)
@@ -977,7 +977,7 @@ struct Marcher {
         if (f == nr) return O_EXIT;
         if (f == depth) return O_SURF;
         c0 += dr;
-        kap = __ldg(kb + c0);
+        kap = __ldg(kb + c0);     // (measured: reading four layers at once with one 256-bit load and selecting is slower)
         // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
         double disc = fma(X.r2[c0 + up], iq, D0);
         if (disc < 0.0) {
