@@ -13,7 +13,7 @@ for i, l in enumerate(src, 1):
         if l.startswith("    ") and name in ("init", "load", "step", "finish", "trip"): name = "Marcher::" + name
         elif l.startswith("    "): continue
         if name == "__launch_bounds__":
-            name = re.search(r"(transport[23]_kernel)", l).group(1)
+            name = re.search(r"(transport[234]_kernel)", l).group(1)
         starts.append((i, name))
 def func_of(line):
     name = "engine2:other"
