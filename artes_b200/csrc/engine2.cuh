@@ -76,8 +76,7 @@ struct Lay {
     __host__ __device__ Lay(int nr, int nt, int np, int NP) {
         o_r2 = nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
         o_tp = o_pf + np; o_sd = o_tp + (nt + 2) / 2 + 1; n_tab = o_sd;
-        bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4
-                + (size_t)32 * (64 + 160) * 2;      // control words, then the warp-private ray stock / done list of kernel C (<= 32 warps)
+        bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
     }
 };
 
@@ -1258,157 +1257,6 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const unsigned fullm = __ballot_sync(FULL, av >= 32);
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
-        int l = -1;
-        // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
-        if (fullm && (we == 0 || event_warp || nactive == 0))
-            l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
-                : (fullm & (1u << L_SURF)) ? L_SURF : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
-        else if (anym && rdy_empty && nactive < starve && (!event_warp || ++idle > 8))
-            l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_DEP)) ? L_DEP : (anym & (1u << L_H)) ? L_H
-                : (anym & (1u << L_SURF)) ? L_SURF : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
-        if (l >= 0) {
-            int base = 0, n = 0;
-            if (lane == 0) {
-                const int h = vhead[l];
-                n = min(32, vtail[l] - h);
-                if (n > 0 && atomicCAS(X.head + l, h, h + n) == h) base = h; else n = 0;
-            }
-            base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
-            if (n > 0) {
-                idle = 0;
-                const bool valid = lane < n;
-                int s = 0;
-                if (valid) s = ring_take(&X.Q(l, base + lane));
-                __threadfence_block();
-                const bool push = run_event(X, A, l, valid, s, C);
-                __threadfence_block();
-                const unsigned pm = __ballot_sync(FULL, push);
-                if (pm) {
-                    const int leader = __ffs(pm) - 1;
-                    int pb = 0;
-                    if (lane == leader) pb = atomicAdd(X.tail + L_RDY, __popc(pm));
-                    pb = __shfl_sync(FULL, pb, leader);
-                    if (push) ring_put(&X.Q(L_RDY, pb + __popc(pm & lt)), s);
-                }
-            }
-        }
-    }
-    flush_counters(A, C);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// kernel C: kernel B with a warp-private stock of ready rays and a warp-private list of ended rays, so that a lane
-// whose ray ends inside a pass takes the next one at the following switch point (every `sub` steps) without any
-// block-level traffic; the block's rings are touched once per pass.
-// ---------------------------------------------------------------------------------------------------
-template <int NT, int NP, int MINB, bool TR, bool GN>
-__global__ void __launch_bounds__(NT, MINB) transport4_kernel(const __grid_constant__ KernelArgs A) {
-    extern __shared__ double smraw[];
-    const DevTables& T = A.T;
-    using Sh = ShT<NP, TR, GN>;
-    Sh X;
-    block_setup<NT, NP, TR, GN>(A, smraw, X, true);
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
-    Marcher M; M.init(T);
-    volatile int* vhead = X.head;
-    volatile int* vtail = X.tail;
-    volatile int* vmisc = X.misc;
-    const int starve = 8;                                        // take partial batches when fewer lanes than this march
-    // Soft warp specialisation: the last `we` warps of the block only run events (they never claim rays), the others
-    // only march and leave full batches to them (they still take batches when they have nothing to march).  Every
-    // warp then loops over a small part of the kernel's code -- the instruction cache, not the register file, is
-    // what the roles are for.  we = 0: every warp does both.
-    const int we = A.L.e2_trips > 0 ? min(A.L.e2_trips, NT / 32 - 1) : 0;
-    const bool event_warp = (int)(threadIdx.x >> 5) >= NT / 32 - we;
-    int idle = 0;
-    // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100)
-    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / 2 + 2));
-
-    // warp-private stock of ready rays and list of ended rays (shorts, in the block's shared memory after the rings)
-    constexpr int WQ = 64, WD = 160;
-    short* wq = reinterpret_cast<short*>(X.misc + 32) + (threadIdx.x >> 5) * (WQ + WD);
-    short* wd = wq + WQ;
-    int wq_n = 0, wd_n = 0, out = O_NONE;
-    const int sub = 4;                                           // steps between two switch points
-
-    for (;;) {
-        if (vmisc[0] >= NP) break;
-        // ---- refill the warp's private stock of ready rays (one CAS on the block's ready ring per pass)
-        bool rdy_empty = event_warp;
-        if (!event_warp && wq_n < 32) {
-            int base = 0, n = 0;
-            if (lane == 0) {
-                const int want = WQ - wq_n;
-                int h = vhead[L_RDY];
-                for (;;) {
-                    n = min(want, vtail[L_RDY] - h);
-                    if (n <= 0) { n = 0; break; }
-                    const int old = atomicCAS(X.head + L_RDY, h, h + n);
-                    if (old == h) { base = h; break; }
-                    h = old;
-                }
-            }
-            base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
-            for (int i = lane; i < n; i += 32) wq[wq_n + i] = (short)ring_take(&X.Q(L_RDY, base + i));
-            __threadfence_block();
-            __syncwarp();
-            wq_n += n;
-            rdy_empty = wq_n == 0;
-        }
-        // ---- `inner` steps in sub-passes of `sub`; before each sub-pass the lanes whose ray ended write it back, note it
-        // on the warp's done list and take a new ray from the warp's stock (ballot + popc only: no atomics, no fences)
-        if (!event_warp) {
-            unsigned n_step = 0;
-            for (int k0 = 0; k0 <= inner; k0 += sub) {
-                int lst = -1;
-                if (M.slot >= 0 && out != O_NONE) { lst = M.finish(X, A, C, out); out = O_NONE; }
-                const unsigned dm = __ballot_sync(FULL, lst >= 0);
-                if (dm) {
-                    if (lst >= 0) { wd[wd_n + __popc(dm & lt)] = (short)(M.slot | (lst << 12)); M.slot = -1; }
-                    wd_n += __popc(dm);
-                }
-                if (k0 >= inner) break;                       // (the last turn only retires what ended in the last sub-pass)
-                const unsigned fm = __ballot_sync(FULL, M.slot < 0);
-                if (fm && wq_n > 0) {
-                    const int n = min(__popc(fm), wq_n);
-                    const int rank = __popc(fm & lt);
-                    if (M.slot < 0 && rank < n) {
-                        M.load(X, A, (int)wq[wq_n - 1 - rank]);
-                        out = ((M.info & 3) == K_DEAD) ? O_DEAD : O_NONE;
-                    }
-                    wq_n -= n;
-                }
-#pragma unroll 1
-                for (int k = 0; k < sub; ++k)
-                    if (M.slot >= 0 && out == O_NONE) out = M.step(X, A, n_step);
-            }
-            C.n_cf += n_step;
-            // ---- hand the ended rays of this pass to their event lists
-            if (wd_n > 0) {
-                __threadfence_block();
-                __syncwarp();
-                for (int b0 = 0; b0 < wd_n; b0 += 32) {
-                    const int e = (b0 + lane < wd_n) ? (int)wd[b0 + lane] : -1;
-                    const int lst = (e >= 0) ? (e >> 12) : -1, slot = e & 0xfff;
-                    const unsigned g = __match_any_sync(FULL, lst);
-                    const int leader = __ffs(g) - 1;
-                    int base = 0;
-                    if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
-                    base = __shfl_sync(FULL, base, leader);
-                    if (lst >= 0) ring_put(&X.Q(lst, base + __popc(g & lt)), slot);
-                }
-                __syncwarp();
-                wd_n = 0;
-            }
-        }
-        // ---- events: a full batch if there is one; a partial one if this warp has little else to do
-        int av = 0;
-        if (lane < N_EVENT_LISTS) av = vtail[lane] - vhead[lane];
-        const unsigned fullm = __ballot_sync(FULL, av >= 32);
-        const unsigned anym = __ballot_sync(FULL, av > 0);
-        const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0)) + wq_n;
         int l = -1;
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
         if (fullm && (we == 0 || event_warp || nactive == 0))
