@@ -172,6 +172,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     mode = abi.MODE_FAST if args.mode == "fast" else abi.MODE_FAITHFUL
@@ -265,7 +266,7 @@ def main():
                 "clocks": clocks,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
                              "frac": achieved / peaks["fp64_tflops"], "traffic": traffic,
-                             "note": "dominant kernel transport2_kernel (ray/event engine); this path is FP64-issue / latency bound, "
+                             "note": "dominant kernel transport3_kernel (ray/event engine, asynchronous scheduling); this path is FP64-issue / latency bound, "
                                      "not HBM or tensor bound: algorithmic FP64 flop = exact event counters x SURVEY 8d "
                                      "per-event figures; peak = FP64 FMA rate measured in this run by artes_gpu_fma_peak "
                                      "(MEASURED_PEAKS.json holds no FP64 figure); traffic = ncu dram bytes per launch of "
