@@ -351,6 +351,12 @@ int artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const doub
         if (kext[i] > 0.0) albedo[i] = k_sca[i] / kext[i];
         if (albedo[i] < 1.e-20) albedo[i] = 1.e-20;
     }
+    std::vector<double> cellrec((size_t)4 * n, 0.0);
+    for (int i = 0; i < n; ++i) {
+        cellrec[4 * (size_t)i] = kext[i]; cellrec[4 * (size_t)i + 1] = albedo[i];
+        const long long ub = cell_to_uniq[i];
+        std::memcpy(&cellrec[4 * (size_t)i + 2], &ub, 8);
+    }
     std::vector<double> p1k((size_t)n_uniq * 4, 0.0), mrow((size_t)n_uniq * 720), cdfP((size_t)n_uniq * 181 * 4, 0.0);
     for (int u = 0; u < n_uniq; ++u) {
         for (int a = 0; a < 180; ++a)
@@ -382,6 +388,7 @@ int artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const doub
         CU(cudaEventRecord(e0, d.stream));
         int rc = 0;
         rc |= upload(ctx, d, d.wl_allocs, kext.data(), kext.size(), &T.kext);
+        rc |= upload(ctx, d, d.wl_allocs, cellrec.data(), cellrec.size(), &T.cellrec);
         rc |= upload(ctx, d, d.wl_allocs, albedo.data(), albedo.size(), &T.albedo);
         rc |= upload(ctx, d, d.wl_allocs, cell_to_uniq, (size_t)n, &T.c2u);
         rc |= upload(ctx, d, d.wl_allocs, uniq_matrix, (size_t)n_uniq * 2880, &T.M);

@@ -71,11 +71,11 @@ constexpr int REC = 20;       // doubles per cold record: 15 doubles + 10 ints =
 __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c < np_slots) c <<= 1; return c; }
 
 struct Lay {
-    int o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_sd, n_tab;   // offsets in doubles
+    int o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, o_sd, n_tab;   // offsets in doubles
     size_t bytes;
     __host__ __device__ Lay(int nr, int nt, int np, int NP) {
         o_r2 = nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
-        o_tp = o_pf + np; o_sd = o_tp + (nt + 2) / 2 + 1; n_tab = o_sd;
+        o_tp = o_pf + np; o_ca = ((o_tp + (nt + 2) / 2 + 1) + 1) & ~1; o_sd = o_ca + 2 * 181; n_tab = o_sd;   // o_ca: 16-byte aligned
         bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
     }
 };
@@ -86,6 +86,7 @@ struct ShT {                     // pointers into the block's shared memory
     static constexpr bool GEN = GN;     // thermal source, reflecting surface and latitudinal flow counters are compiled in
     const double* r; const double* r2; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
     const int* tplane;
+    const double2* cdfa;         // azimuth prefix table [181] (cos2beta, sin2beta): 17 probes per scattering, kept out of the L1 global path
     double* sd; int* si; short* q; int* head; int* tail;
     int* misc;                   // [0] slots retired for good, [1] event batch counter, [2] ready-list tail at the end of the last event phase
     double* cold;                // this block's records in global memory
@@ -263,12 +264,12 @@ __device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s
 }
 
 // matrix_at_deg (transport.cuh) with 256-bit row reads
-__device__ __forceinline__ void matrix_at_deg_f(const DevTables& T, int cellidx, double deg, double F[16]) {
+__device__ __forceinline__ void matrix_at_deg_f(const DevTables& T, int u, double deg, double F[16]) {
     int lo, up;
     const double fl = floor(deg);
     if (deg - fl > 0.5) { up = (int)fl + 2; lo = (int)fl + 1; }
     else { up = (int)fl + 1; lo = (int)fl; }
-    const double* base = T.M + (size_t)__ldg(T.c2u + cellidx) * (180 * 16);
+    const double* base = T.M + (size_t)u * (180 * 16);
     if (up <= 1 || lo >= 180) {
         const double* m = base + (up <= 1 ? 0 : 179) * 16;
 #pragma unroll
@@ -334,15 +335,15 @@ __device__ __forceinline__ int search6(F cum, double samp, double& ylo, double& 
 }
 
 // sample_angles_fast with the three random numbers supplied by the caller (engine2: stateless Philox draws)
-__device__ __forceinline__ int sample_angles_f(const KernelArgs& A, double xi1, double xi2, double xi3, const double S[4],
-                                                     int cellidx, FastAngles& g) {
+template <class Sh>
+__device__ __forceinline__ int sample_angles_f(const Sh& X, const KernelArgs& A, double xi1, double xi2, double xi3, const double S[4],
+                                                     int cellidx, FastAngles& g, int u) {
     const DevTables& T = A.T;
-    const int u = __ldg(T.c2u + cellidx);
+    (void)cellidx;
     double p11, p12, p13, p14;
     ldg256_nc(T.p1k + 4 * u, p11, p12, p13, p14);
     const double Ac = p11 * S[0] + p14 * S[3], Bc = p12 * S[1] + p13 * S[2], Cc = p12 * S[2] - p13 * S[1];
-    const double2* pcs = reinterpret_cast<const double2*>(T.cdfA2);
-    auto cumA = [&](int i) { const double2 q = __ldg(pcs + i); return Ac * (double)i + Bc * q.x + Cc * q.y; };
+    auto cumA = [&](int i) { const double2 q = X.cdfa[i]; return Ac * (double)i + Bc * q.x + Cc * q.y; };
     double samp = xi1 * cumA(180);
     double ylo, yhi;
     int lo = search6(cumA, samp, ylo, yhi);   // bin lo: cum(lo) < samp <= cum(lo + 1)
@@ -627,8 +628,13 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     ldg256(rec + 8, S[2], S[3], tau0, w0_);
     ldg256(rec + 16, i0_, i1_, i2_, i3_);
     (void)w0_; (void)i2_; (void)i3_;
+    // per-cell record {cell_opacity, cell_albedo, unique-matrix index}: one 256-bit read instead of three scattered ones
+    double kap_c, alb_c, u_bits, pad_c;
+    ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
+    (void)pad_c;
+    const int u = (int)__double_as_longlong(u_bits);
     // the marcher stopped after adding the crossing that overshoots tau: step back by the overshoot (:705-720)
-    const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - tau0, __ldg(T.kext + ci));
+    const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - tau0, kap_c);
     const double px = hx + tpos * dx, py = hy + tpos * dy, pz = hz + tpos * dz;
     double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
     if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
@@ -644,7 +650,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     if (Sh::TRACE && alive) X.I(I_FLAG, s) &= ~1;                // (only the draws actually consumed below may exhaust it)
     if (alive) { const double xi = xr[0]; ++nd; if (Sh::TRACE && (int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; if (xi < L.fstop) alive = false; }
     if (alive) {
-        const double alb = __ldg(T.albedo + ci);
+        const double alb = alb_c;
         if (alb < 1.0 && alb > 0.0) { const double g = fdiv(alb, 1.0 - L.fstop); S[0] *= g; S[1] *= g; S[2] *= g; S[3] *= g; }
         if (S[0] <= L.photon_minimum) alive = false;
     }
@@ -662,7 +668,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     double W[4] = {0.0, 0.0, 0.0, 0.0};
     {
         double F[16];
-        matrix_at_deg_f(T, ci, peel_deg, F);
+        matrix_at_deg_f(T, u, peel_deg, F);
         if (!(fabs(dz) < 1.0)) err_count(A, 45);
         else {
             const double smu = fsqrt(1.0 - mu * mu);
@@ -696,7 +702,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     double tau = -1.0;                      // < 0: the photon dies after its peel-off has been deposited
     {
         FastAngles g;
-        int e = sample_angles_f(A, xr[1], xr[2], xr[3], S, ci, g);
+        int e = sample_angles_f(X, A, xr[1], xr[2], xr[3], S, ci, g, u);
         nd += (e == 6) ? 2u : 3u;
         if (Sh::TRACE) { X.I(I_TNSC, s) += 1; if ((int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; }
         double e0 = 0, e1 = 0, e2 = 0;
@@ -719,7 +725,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
         }
         if (!e) {
             double F[16], Sn[4];
-            matrix_at_deg_f(T, ci, g.deg, F);
+            matrix_at_deg_f(T, u, g.deg, F);
             const double nc2 = fdiv(dz - e2 * g.alpha, g.sT * fsqrt(1.0 - e2 * e2));
             int soft = 0;
             e = polrot_f(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
@@ -842,15 +848,20 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
     const int cell = X.I(I_CELL, s);
     int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     const bool peel = (kind == K_PEEL);
-    const double n0 = peel ? L.det[0] : X.D(F_DX, s), n1 = peel ? L.det[1] : X.D(F_DY, s), n2 = peel ? L.det[2] : X.D(F_DZ, s);
+    const double* rec = X.cold + (size_t)s * REC;
+    double hx, hy, hz, rdx, rdy, rdz, s0_, s1_;
+    ldg256(rec, hx, hy, hz, rdx);
+    ldg256(rec + 4, rdy, rdz, s0_, s1_);
+    (void)s1_;
+    const double n0 = peel ? L.det[0] : rdx, n1 = peel ? L.det[1] : rdy, n2 = peel ? L.det[2] : rdz;
     RayK K;
     double hbn, D0, iq;
-    ray_consts(T, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), n0, n1, n2, K, hbn, D0, iq);
+    ray_consts(T, hx, hy, hz, n0, n1, n2, K, hbn, D0, iq);
     const double t = X.D(F_T, s);
     info &= 0xff;
     if (out == O_REST) {
         if (Sh::GEN && L.flow_theta && kind == K_WALK)      // add_flow :5016-5047, polar crossings (:736-742)
-            atomicAdd(A.O.flow4 + (size_t)4 * (c0 + T.nr * (c1 + T.nt * c2)) + ((info & B_TUPPER) ? 2 : 3), X.D(F_S0, s));
+            atomicAdd(A.O.flow4 + (size_t)4 * (c0 + T.nr * (c1 + T.nt * c2)) + ((info & B_TUPPER) ? 2 : 3), s0_);
         c1 += (info & B_TUPPER) ? 1 : -1;
         int upper;
         X.D(F_TT, s) = theta_next(X, T.nt, c1, t, K, upper);
@@ -878,6 +889,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     constexpr int RC = ShT<NP, TR, GN>::RC;
     X.r = sm; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
     X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
+    X.cdfa = reinterpret_cast<const double2*>(sm + lay.o_ca);
     X.sd = sm + lay.o_sd;
     X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
     X.q = reinterpret_cast<short*>(X.si + NI_HOT * NP);
@@ -891,6 +903,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
         reinterpret_cast<int*>(sm + lay.o_tp)[i] = T.tplane[i];
     }
     for (int i = tid; i < T.np; i += NT) { sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i]; }
+    for (int i = tid; i < 2 * 181; i += NT) sm[lay.o_ca + i] = T.cdfA2[i];
     if (mark_empty) for (int i = tid; i < N_LISTS * RC; i += NT) X.q[i] = (short)-1;
     __syncthreads();
     for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; X.I(I_INFO, i) = 0; }   // every slot starts by asking for a photon

@@ -26,7 +26,8 @@ struct DevTables {
     const double* Mrow;              // [n_uniq][180][4]  first matrix row, compact (polar CDF loop)
     const double* p1k;               // [n_uniq][4] cell_p11..p14_int (:72-75)
     const double* cdfA;              // fast mode: prefix sums of cos2beta | sin2beta, [2][181]
-    const double* cdfA2;             // the same, interleaved [181][2] (one 128-bit read per probe)
+    const double* cdfA2;             // the same, interleaved [181][2] (staged in shared memory by the ray/event engine)
+    const double* cellrec;           // [cells][4]: cell_opacity, cell_albedo, unique-matrix index (as int64 bits), 0 -- one 256-bit read per interaction
     const double* cdfP;              // fast mode: [n_uniq][181][4] prefix sums of P1k(i)*sinbeta(i)*pi/180
     const double* cell_weight;       // [cells] or null (:68)
     const double* emis_cdf;          // [(nr-cell_depth)*nt*np] emissivity_cumulative in the (i,j,k) loop order of :2425-2427
