@@ -46,6 +46,8 @@
 
 namespace e2 {
 
+#include "fastmath.cuh"
+
 // A block has NT marcher lanes and NP >= NT photon slots: with more photons than lanes a lane whose ray
 // ended finds another ready ray at once, and a round collects enough events to keep every warp busy in
 // the event phase.  RC = ring capacity of the lists (power of two >= NP).
@@ -245,6 +247,19 @@ __device__ __forceinline__ double phi_next(const Sh& X, int np, int c2, double t
     return (r > t) ? r : RAY_NONE;
 }
 
+// What an event asks for: the next ray of its slot.  The set-up itself (three axis solves) is done once, after the
+// event switch (run_event), so that the kernel holds one copy of that code instead of one per event.
+struct RaySpec {
+    bool make;
+    double x, y, z, n0, n1, n2, lim, acc0;
+    int c0, c1, c2, sface, kind, pk;
+    __device__ __forceinline__ void set(double x_, double y_, double z_, double n0_, double n1_, double n2_, int c0_, int c1_, int c2_,
+                                        int sface_, int kind_, double lim_, double acc0_ = 0.0, int pk_ = 0) {
+        make = true; x = x_; y = y_; z = z_; n0 = n0_; n1 = n1_; n2 = n2_; c0 = c0_; c1 = c1_; c2 = c2_;
+        sface = sface_; kind = kind_; lim = lim_; acc0 = acc0_; pk = pk_;
+    }
+};
+
 // set up the next ray of slot s: origin (x,y,z) in cell (c0,c1,c2), direction n
 template <class Sh>
 __device__ __forceinline__ void ray_setup(const Sh& X, const DevTables& T, int s, double x, double y, double z,
@@ -351,7 +366,7 @@ __device__ __forceinline__ int sample_angles_f(const Sh& X, const KernelArgs& A,
     if (!(fr == fr)) return 6;
     fr = fmin(fmax(fr, 0.0), 1.0);
     const double beta = (fr + (double)lo) * (PI / 180.0);
-    sincos(beta, &g.sb, &g.cb);
+    fm_sincos_0pi(beta, &g.sb, &g.cb);
     g.flip = xi2 > 0.5;                       // beta + pi  (:1589-1590)
     if (g.flip) { g.sb = -g.sb; g.cb = -g.cb; }
     const double c2b = g.cb * g.cb - g.sb * g.sb, s2b = 2.0 * g.sb * g.cb;
@@ -368,7 +383,7 @@ __device__ __forceinline__ int sample_angles_f(const Sh& X, const KernelArgs& A,
     if (!(fr == fr)) return 7;
     fr = fmin(fmax(fr, 0.0), 1.0);
     g.deg = fr + (double)lo;
-    sincos(g.deg * (PI / 180.0), &g.sT, &g.alpha);
+    fm_sincos_0pi(g.deg * (PI / 180.0), &g.sT, &g.alpha);
     if (g.alpha >= 1.0) { g.alpha = 1.0 - 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
     if (g.alpha <= -1.0) { g.alpha = -1.0 + 1.e-10; g.sT = sqrt(1.0 - g.alpha * g.alpha); }
     return 0;
@@ -386,7 +401,7 @@ struct Cnt {
 // EMIT, planet source: emit_photon :1117-1266 + the thermal weight and the start of peel_thermal :599-621.
 // The cell comes from a binary search on the emissivity CDF (the reference scans it linearly, :1132-1155).
 template <class Sh>
-__device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A, int s, unsigned long long id, Cnt& C) {
+__device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A, int s, unsigned long long id, Cnt& C, RaySpec& rs) {
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
     double xr[5], xq;
@@ -397,7 +412,7 @@ __device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A
     int lo = -1, hi = ncdf - 1;      // first p with cdf[p] >= samp
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(T.emis_cdf + mid) >= samp) hi = mid; else lo = mid; }
     const int c2 = hi % T.np, c1 = (hi / T.np) % T.nt, c0 = T.cell_depth + hi / (T.np * T.nt);
-    double rs = xr[1] * (X.r[c0 + 1] - X.r[c0]); rs = X.r[c0] + rs;
+    double rsam = xr[1] * (X.r[c0 + 1] - X.r[c0]); rsam = X.r[c0] + rsam;
     const double tc0 = __ldg(T.tcos + c1), tc1 = __ldg(T.tcos + c1 + 1);
     double ct = xr[2] * (tc1 - tc0); ct = tc0 + ct;
     const double st = sqrt(1.0 - ct * ct);
@@ -408,7 +423,7 @@ __device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A
     const double cp = cos(phs);
     double sp = sqrt(1.0 - cp * cp);
     if (phs > PI) sp = -sp;
-    double px = rs * st * cp, py = rs * st * sp, pz = rs * ct;
+    double px = rsam * st * cp, py = rsam * st * sp, pz = rsam * ct;
     px = T.ox * px; py = T.oy * py; pz = T.oz * pz;
     double dx, dy, dz, bias_weight = 1.0;
     int e = 0;
@@ -451,7 +466,7 @@ __device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A
         const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
         X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1);
     }
-    ray_setup(X, T, s, px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF, 0.0, PK_THERMAL);
+    rs.set(px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF, 0.0, PK_THERMAL);
     return true;
 }
 
@@ -459,7 +474,7 @@ __device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A
 // (lambertian :1369-1402) followed by the start of peel_surface :4600-4650.  The optical depth of the walk is NOT
 // resampled: the reflected photon goes on with the same tau and the running sum (:766-776).
 template <class Sh>
-__device__ __forceinline__ bool ev_surface(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+__device__ __forceinline__ bool ev_surface(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
     if (!valid) return false;
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
@@ -495,15 +510,15 @@ __device__ __forceinline__ bool ev_surface(const Sh& X, const KernelArgs& A, boo
         const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
         const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
         X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1);
-        ray_setup(X, T, s, wx, wy, wz, L.det[0], L.det[1], L.det[2], c0, c1, c2, T.cell_depth, K_PEEL, CUDART_INF, 0.0, PK_SURFACE);
+        rs.set(wx, wy, wz, L.det[0], L.det[1], L.det[2], c0, c1, c2, T.cell_depth, K_PEEL, CUDART_INF, 0.0, PK_SURFACE);
     } else
-        ray_setup(X, T, s, wx, wy, wz, e0, e1, e2, c0, c1, c2, T.cell_depth, K_WALK, tau, acc);
+        rs.set(wx, wy, wz, e0, e1, e2, c0, c1, c2, T.cell_depth, K_WALK, tau, acc);
     return true;
 }
 
 // EMIT: star emission (emit_photon :1008-1115 + initial_cell).  Returns true if a ray was set up.
 template <class Sh>
-__device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+__device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
     const int lane = threadIdx.x & 31;
@@ -543,7 +558,7 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
         X.I(I_THLO, s) = (int)(unsigned)1469598103934665603ull; X.I(I_THHI, s) = (int)(unsigned)(1469598103934665603ull >> 32);
     }
     unsigned nd = 0;
-    if (Sh::GEN && L.photon_source == 2) return ev_emit_thermal(X, A, s, id, C);
+    if (Sh::GEN && L.photon_source == 2) return ev_emit_thermal(X, A, s, id, C, rs);
     double xi, r_disk;
     if (L.limb_emission) {
         for (;;) { draws(X, A, s, id, nd, 1, &xi); ++nd; r_disk = sqrt(xi); if (r_disk > 0.9 || (Sh::TRACE && (X.I(I_FLAG, s) & 1))) break; }
@@ -578,13 +593,13 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
     X.D(F_S0, s) = 1.0; X.D(F_S1, s) = 0.0; X.D(F_S2, s) = 0.0; X.D(F_S3, s) = 0.0; X.D(F_TAU, s) = 0.0;
     X.I(I_ND, s) = (int)nd;
     X.I(I_HCELL, s) = pack_cell(c0, c1, c2) | (1 << 30);      // bit 30: the photon sits on the outer radial face
-    ray_setup(X, T, s, px, py, pz, dx, dy, dz, c0, c1, c2, T.nr, K_PRE, CUDART_INF);
+    rs.set(px, py, pz, dx, dy, dz, c0, c1, c2, T.nr, K_PRE, CUDART_INF);
     return true;
 }
 
 // PRE: the tau pre-pass ended -> first optical depth :660-685
 template <class Sh>
-__device__ __forceinline__ bool ev_pre(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+__device__ __forceinline__ bool ev_pre(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
     if (!valid) return false;
     const LaunchArgs& L = A.L;
     const int out = (X.I(I_INFO, s) >> 8) & 15;
@@ -598,14 +613,14 @@ __device__ __forceinline__ bool ev_pre(const Sh& X, const KernelArgs& A, bool va
     X.I(I_ND, s) = (int)(nd + 1u);
     double arg = 1.0 - xi;
     if (!(tacc < 1.e-6) && tacc < 50.0) {
-        const double f = 1.0 - exp(-tacc);
+        const double f = 1.0 - fm_exp_neg(tacc);
         arg = 1.0 - xi * f;
         X.D(F_S0, s) *= f; X.D(F_S1, s) *= f; X.D(F_S2, s) *= f; X.D(F_S3, s) *= f;
     }
-    const double tau = -log(arg);
+    const double tau = -fm_log(arg);
     X.D(F_TAU, s) = tau;
     const int hc = X.I(I_HCELL, s);
-    ray_setup(X, A.T, s, X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
+    rs.set(X.D(F_PX, s), X.D(F_PY, s), X.D(F_PZ, s), X.D(F_DX, s), X.D(F_DY, s), X.D(F_DZ, s),
               hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, (hc >> 30) ? A.T.nr : -1, K_WALK, tau);
     return true;
 }
@@ -613,7 +628,7 @@ __device__ __forceinline__ bool ev_pre(const Sh& X, const KernelArgs& A, bool va
 // H: the transport walk reached its optical depth.  Survival :791-813, peel-off weight and pixel (peel_photon
 // :4763-4951; the e^-tau factor is applied by DEP once the peel ray has been walked), scattering :819-845.
 template <class Sh>
-__device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+__device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
     if (!valid) return false;
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
@@ -638,7 +653,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     const double px = hx + tpos * dx, py = hy + tpos * dy, pz = hz + tpos * dz;
     double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
     if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
-    const double peel_deg = acos(mu) * (180.0 / PI);
+    const double peel_deg = fm_acos(mu) * (180.0 / PI);
     // ints of the record: piece 4 = [nd | idlo] [idhi | tlen] ...
     const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
     const unsigned long long id = (w16 >> 32) | (w17 << 32);
@@ -733,7 +748,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
             if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
         }
         if (e) { err_count(A, e); ++C.n_err; }
-        else { const double xi = xr[4]; ++nd; if (Sh::TRACE && (int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; tau = -log(1.0 - xi); }
+        else { const double xi = xr[4]; ++nd; if (Sh::TRACE && (int)nd > A.R.max_draws) X.I(I_FLAG, s) |= 1; tau = -fm_log(1.0 - xi); }
     }
     stg256(rec, px, py, pz, dx);
     stg256(rec + 4, dy, dz, S[0], S[1]);
@@ -743,13 +758,13 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, tau0, X.D(F_ACC, s), X.D(F_T, s));
 #endif
     X.I(I_ND, s) = (int)nd;
-    ray_setup(X, T, s, px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF);
+    rs.set(px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF);
     return true;
 }
 
 // DEP: the peel ray ended -> e^-tau, detector deposit :4955-4972; then the transport ray of the scattered photon
 template <class Sh>
-__device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+__device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
     const LaunchArgs& L = A.L;
     const int out = valid ? ((X.I(I_INFO, s) >> 8) & 15) : O_NONE;
     const double tacc = valid ? X.D(F_ACC, s) : 0.0;
@@ -773,7 +788,7 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     if (Sh::GEN && pk != PK_SCATTER) {
         dep = false;
         if (valid && out == O_EXIT && tacc < 50.0) {
-            const double w = (pk == PK_THERMAL) ? exp(-tacc) / (4.0 * PI) : exp(-tacc) * W2 / PI;
+            const double w = (pk == PK_THERMAL) ? fm_exp_neg(tacc) / (4.0 * PI) : fm_exp_neg(tacc) * W2 / PI;
             w_i = w * W0;
             if (!(w_i > 0.0 && w_i < 1.e100)) err_count(A, pk == PK_THERMAL ? 51 : 52);
             else if (pix == -2) err_count(A, 60);
@@ -791,7 +806,7 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     if (dm) {
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (dep) {
-            const double w = exp(-tacc);
+            const double w = fm_exp_neg(tacc);
             v[0] = w * W0; v[1] = -(w * W1); v[2] = w * W2; v[3] = w * W3;
             v[4] = v[0] * v[0]; v[5] = v[1] * v[1]; v[6] = v[2] * v[2]; v[7] = v[3] * v[3];
         }
@@ -822,17 +837,17 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     }
     if (!valid) return false;
     if (Sh::GEN && pk == PK_THERMAL) {          // after peel_thermal the photon starts its tau pre-pass (:621-656)
-        ray_setup(X, A.T, s, hx, hy, hz, dx, dy, dz,
+        rs.set(hx, hy, hz, dx, dy, dz,
                   hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, -1, K_PRE, CUDART_INF);
         return true;
     }
     if (Sh::GEN && pk == PK_SURFACE) {          // the reflected photon goes on with its old tau and running sum (:766-776)
-        ray_setup(X, A.T, s, hx, hy, hz, dx, dy, dz,
+        rs.set(hx, hy, hz, dx, dy, dz,
                   hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, A.T.cell_depth, K_WALK, tau, W1);
         return true;
     }
     if (tau < 0.0) { X.I(I_INFO, s) = K_DEAD; return true; }
-    ray_setup(X, A.T, s, hx, hy, hz, dx, dy, dz,
+    rs.set(hx, hy, hz, dx, dy, dz,
               hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, -1, K_WALK, tau);
     return true;
 }
@@ -1031,12 +1046,17 @@ struct Marcher {
 
 template <class Sh>
 __device__ __forceinline__ bool run_event(const Sh& X, const KernelArgs& A, int l, bool valid, int s, Cnt& C) {
-    if (l == L_H) return ev_interact(X, A, valid, s, C);
-    if (l == L_DEP) return ev_deposit(X, A, valid, s, C);
-    if (l == L_RES) return ev_resolve(X, A, valid, s);
-    if (l == L_PRE) return ev_pre(X, A, valid, s, C);
-    if (Sh::GEN && l == L_SURF) return ev_surface(X, A, valid, s, C);
-    return ev_emit(X, A, valid, s, C);
+    RaySpec rs;
+    rs.make = false;
+    bool push;
+    if (l == L_H) push = ev_interact(X, A, valid, s, C, rs);
+    else if (l == L_DEP) push = ev_deposit(X, A, valid, s, C, rs);
+    else if (l == L_RES) push = ev_resolve(X, A, valid, s);
+    else if (l == L_PRE) push = ev_pre(X, A, valid, s, C, rs);
+    else if (Sh::GEN && l == L_SURF) push = ev_surface(X, A, valid, s, C, rs);
+    else push = ev_emit(X, A, valid, s, C, rs);
+    if (rs.make) ray_setup(X, A.T, s, rs.x, rs.y, rs.z, rs.n0, rs.n1, rs.n2, rs.c0, rs.c1, rs.c2, rs.sface, rs.kind, rs.lim, rs.acc0, rs.pk);
+    return push;
 }
 
 __device__ __forceinline__ void flush_counters(const KernelArgs& A, const Cnt& C) {
