@@ -72,13 +72,21 @@ constexpr int REC = 20;       // doubles per cold record: 15 doubles + 10 ints =
 
 __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c < np_slots) c <<= 1; return c; }
 
+// Shared-memory layout.  The slot arrays, lists and list counters come FIRST, at offsets that depend only on the
+// template parameter NP: their addresses are immediates in the instruction stream instead of values the compiler has
+// to keep in (or spill from) registers around the whole scheduling loop.  The grid tables, whose sizes are run-time
+// values, follow.
+__host__ __device__ constexpr int fixed_doubles(int NP) {
+    return (NF_HOT * NP * 8 + NI_HOT * NP * 4 + N_LISTS * ring_cap(NP) * 2 + 64 * 4 + 15) / 16 * 2;
+}
 struct Lay {
-    int o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, o_sd, n_tab;   // offsets in doubles
+    int o_r, o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, n_end;   // offsets in doubles
     size_t bytes;
     __host__ __device__ Lay(int nr, int nt, int np, int NP) {
-        o_r2 = nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
-        o_tp = o_pf + np; o_ca = ((o_tp + (nt + 2) / 2 + 1) + 1) & ~1; o_sd = o_ca + 2 * 181; n_tab = o_sd;   // o_ca: 16-byte aligned
-        bytes = (size_t)(o_sd + NF_HOT * NP) * 8 + (size_t)NI_HOT * NP * 4 + (size_t)N_LISTS * ring_cap(NP) * 2 + 64 * 4;
+        o_r = fixed_doubles(NP);
+        o_r2 = o_r + nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
+        o_tp = o_pf + np; o_ca = ((o_tp + (nt + 2) / 2 + 1) + 1) & ~1; n_end = o_ca + 2 * 181;   // o_ca: 16-byte aligned
+        bytes = (size_t)n_end * 8;
     }
 };
 
@@ -328,25 +336,33 @@ __device__ __forceinline__ int polrot_f(double c2a, double s2a, bool flip, doubl
 }
 
 // Inversion of a 180-bin cumulative table: returns the bin lo with cum(lo) < samp <= cum(lo + 1) and the two
-// table values.  Three 6-ary rounds (steps 30, 5, 1; five independent probes each) instead of eight dependent
-// binary-search steps: the same number of table reads, a third of the load round trips.
+// table values.  Three 6-ary rounds (steps 30, 5, 1; independent probes each) instead of eight dependent
+// binary-search steps: the same number of table reads, a third of the load round trips.  The last round reads
+// the six entries lo .. lo+5, so the bracketing pair comes out of registers instead of a fourth round trip.
 template <class F>
 __device__ __forceinline__ int search6(F cum, double samp, double& ylo, double& yhi) {
     int lo = 0;
 #pragma unroll
-    for (int round = 0; round < 3; ++round) {
-        const int step = (round == 0) ? 30 : ((round == 1) ? 5 : 1);
-        const int np = (round == 2) ? 4 : 5;
+    for (int round = 0; round < 2; ++round) {
+        const int step = (round == 0) ? 30 : 5;
         double y[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) y[k] = (k < np) ? cum(lo + (k + 1) * step) : 0.0;
+        for (int k = 0; k < 5; ++k) y[k] = cum(lo + (k + 1) * step);
         int c = 0;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) if (k < np) c += (y[k] < samp) ? 1 : 0;
+        for (int k = 0; k < 5; ++k) c += (y[k] < samp) ? 1 : 0;
         lo += c * step;
     }
-    ylo = cum(lo); yhi = cum(lo + 1);
-    return lo;
+    double y[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) y[k] = cum(lo + k);
+    int c = 0;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) c += (y[k] < samp) ? 1 : 0;
+    ylo = y[0]; yhi = y[1];
+#pragma unroll
+    for (int k = 1; k < 5; ++k) if (c == k) { ylo = y[k]; yhi = y[k + 1]; }
+    return lo + c;
 }
 
 // sample_angles_fast with the three random numbers supplied by the caller (engine2: stateless Philox draws)
@@ -902,17 +918,17 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     const DevTables& T = A.T;
     const Lay lay(T.nr, T.nt, T.np, NP);
     constexpr int RC = ShT<NP, TR, GN>::RC;
-    X.r = sm; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
-    X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
-    X.cdfa = reinterpret_cast<const double2*>(sm + lay.o_ca);
-    X.sd = sm + lay.o_sd;
+    X.sd = sm;
     X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
     X.q = reinterpret_cast<short*>(X.si + NI_HOT * NP);
-    X.cold = A.O.scratch + (size_t)blockIdx.x * NP * REC;
     X.head = reinterpret_cast<int*>(X.q + N_LISTS * RC);
     X.tail = X.head + 8; X.misc = X.head + 16;
+    X.r = sm + lay.o_r; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
+    X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
+    X.cdfa = reinterpret_cast<const double2*>(sm + lay.o_ca);
+    X.cold = A.O.scratch + (size_t)blockIdx.x * NP * REC;
     const int tid = threadIdx.x;
-    for (int i = tid; i <= T.nr; i += NT) { const double r = T.rfront[i]; sm[i] = r; sm[lay.o_r2 + i] = r * r; }
+    for (int i = tid; i <= T.nr; i += NT) { const double r = T.rfront[i]; sm[lay.o_r + i] = r; sm[lay.o_r2 + i] = r * r; }
     for (int i = tid; i <= T.nt; i += NT) {
         sm[lay.o_tf + i] = T.thetafront[i]; sm[lay.o_tt + i] = T.ttan[i];
         reinterpret_cast<int*>(sm + lay.o_tp)[i] = T.tplane[i];
@@ -1233,6 +1249,10 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     const int we = A.L.e2_trips > 0 ? min(A.L.e2_trips, NT / 32 - 1) : 0;
     const bool event_warp = (int)(threadIdx.x >> 5) >= NT / 32 - we;
     int idle = 0;
+#ifdef E2_STATS
+    unsigned long long st_pass = 0, st_act0 = 0, st_rdy0 = 0, st_it = 0, st_lane = 0, st_ev = 0, st_rdy = 0, st_evb = 0, st_evl = 0;
+    bool rdy_empty = false;
+#endif
     // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100)
     const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / 2 + 2));
 
@@ -1240,7 +1260,11 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         if (vmisc[0] >= NP) break;
         // ---- free lanes claim ready rays
         const unsigned fm = event_warp ? 0u : __ballot_sync(FULL, M.slot < 0);
+#ifdef E2_STATS
+        rdy_empty = event_warp;
+#else
         bool rdy_empty = event_warp;
+#endif
         if (fm) {
             int base = 0, n = 0;
             if (lane == 0) {
@@ -1268,9 +1292,18 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         {
             int out = (M.slot >= 0 && (M.info & 3) == K_DEAD) ? O_DEAD : O_NONE;
             unsigned n_step = 0;
+#ifdef E2_STATS   // -DE2_STATS: occupancy counters of the pass structure in err slots 50-58 (tools/gpu_tune.py prints them)
+            { const int na = __popc(__ballot_sync(FULL, M.slot >= 0 && out == O_NONE));
+              st_pass++; st_act0 += na; st_rdy0 += rdy_empty ? 1 : 0; st_ev += (vtail[L_H]-vhead[L_H]) + (vtail[L_DEP]-vhead[L_DEP]) + (vtail[L_RES]-vhead[L_RES]); st_rdy += vtail[L_RDY]-vhead[L_RDY]; }
+#endif
 #pragma unroll 1
-            for (int k = 0; k < inner; ++k)
-                if (M.slot >= 0 && out == O_NONE) out = M.step(X, A, n_step);
+            for (int k = 0; k < inner; ++k) {
+                const bool go = M.slot >= 0 && out == O_NONE;
+#ifdef E2_STATS
+                { const int na = __popc(__ballot_sync(FULL, go)); st_it += na > 0; st_lane += na; }
+#endif
+                if (go) out = M.step(X, A, n_step);
+            }
             C.n_cf += n_step;
             if (M.slot >= 0 && out != O_NONE) lst = M.finish(X, A, C, out);
         }
@@ -1312,6 +1345,9 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
                 int s = 0;
                 if (valid) s = ring_take(&X.Q(l, base + lane));
                 __threadfence_block();
+#ifdef E2_STATS
+                st_evb++; st_evl += n;
+#endif
                 const bool push = run_event(X, A, l, valid, s, C);
                 __threadfence_block();
                 const unsigned pm = __ballot_sync(FULL, push);
@@ -1325,6 +1361,13 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             }
         }
     }
+#ifdef E2_STATS
+    if (lane == 0) {
+        atomicAdd(A.O.err + 50, st_pass); atomicAdd(A.O.err + 51, st_act0); atomicAdd(A.O.err + 52, st_rdy0);
+        atomicAdd(A.O.err + 53, st_it); atomicAdd(A.O.err + 54, st_lane); atomicAdd(A.O.err + 55, st_ev);
+        atomicAdd(A.O.err + 56, st_rdy); atomicAdd(A.O.err + 57, st_evb); atomicAdd(A.O.err + 58, st_evl);
+    }
+#endif
     flush_counters(A, C);
 }
 

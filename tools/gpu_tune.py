@@ -18,4 +18,8 @@ for m in modes:
     st = r["stats"]
     print(f"{name} {m} ev={os.environ.get('ARTES_DEFER_EVENTS','-')} rf={os.environ.get('ARTES_DEFER_REFILL','-')} "
           f"n={n} kernel {st['kernel_ms']:.1f} ms -> {n/st['kernel_ms']*1e3:.4e} pkt/s  launches {st['reserved']} cf/pkt {st['n_cell_face']/n:.1f} sc/pkt {st['n_scatter']/n:.2f} I={r['det'][0,0].sum():.6e}", flush=True)
+    if os.environ.get("E2_STATS"):
+        e = [int(x) for x in r["err"][50:59]]
+        print(f"  passes {e[0]:.3e} lanes@start {e[1]/max(e[0],1):.1f} rdy_empty {e[2]/max(e[0],1):.2f} step-iters/pass {e[3]/max(e[0],1):.1f} lanes/step {e[4]/max(e[3],1):.1f} "
+              f"evlist(H+DEP+RES)/block {e[5]/max(e[0],1):.0f} rdy/block {e[6]/max(e[0],1):.0f} event batches {e[7]:.3e} lanes/batch {e[8]/max(e[7],1):.1f}")
     t.close()
