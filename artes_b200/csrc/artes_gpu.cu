@@ -87,6 +87,8 @@ struct DeviceState {
     size_t out_d_cap = 0;
     unsigned long long* out_u = nullptr;   // [err 64 | stats 8 | counter 1]
     double* scratch = nullptr;             // ray/event engine: cold photon records (L2-resident working set)
+    double* geo = nullptr;                 // batched launches: [n][8] detector geometry
+    size_t geo_cap = 0;
     ncclComm_t comm = nullptr;
     unsigned long long n_photons = 0;
     int launches = 0;
@@ -168,7 +170,8 @@ void fill_launch(const artes_launch_t& L, LaunchArgs& a) {
     static const int e2_trips = env_int("ARTES_E2_TRIPS", 0);
     static const int e2_cfg = env_int("ARTES_E2_CFG", 32) & 31;      // block shape, see launch_transport2
     static const int e2_inner = env_int("ARTES_E2_INNER", 0);
-    a.e2_trips = e2_trips; a.e2_pad = e2_cfg; a.e2_inner = e2_inner; a.e2_pad2 = 0;
+    static const int e2_per_sm = env_int("ARTES_E2_PER_SM", 8) & 7;
+    a.e2_trips = e2_trips; a.e2_pad = e2_cfg; a.e2_inner = e2_inner; a.e2_pad2 = e2_per_sm;
     a.fstop = L.fstop; a.photon_minimum = L.photon_minimum; a.photon_bias = L.photon_bias;
     a.surface_albedo = L.surface_albedo; a.theta_star = L.theta_star; a.phi_star = L.phi_star;
     a.x_max = L.x_max; a.y_max = L.y_max;
@@ -271,6 +274,7 @@ int artes_gpu_destroy(artes_gpu_ctx* ctx) {
         if (d.out_d) cudaFree(d.out_d);
         if (d.out_u) cudaFree(d.out_u);
         if (d.scratch) cudaFree(d.scratch);
+        if (d.geo) cudaFree(d.geo);
         for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -572,6 +576,161 @@ int artes_gpu_run(artes_gpu_ctx* ctx, const artes_launch_t* L, double* det_sum, 
     int rc = artes_gpu_run_async(ctx, L);
     if (rc) return rc;
     return artes_gpu_wait(ctx, det_sum, flux, flow4, flow3, err_hist, stats);
+}
+
+// Several launches that differ only in the detector direction, as ONE kernel launch (the phase-curve loop
+// src/ARTES.f90:215-245 calls radiative_transfer 73 times with a new det_phi).  A transport launch ends with a drain
+// phase in which the last photons of every block finish one scattering after the other while the SMs idle; at the
+// reference's 1e6 packets per launch that is ~40 % of the launch on B200.  Batched, the work items of all launches
+// come out of one counter, every photon carries the index of its launch, and the drain is paid once per batch.
+// Launch k uses the photon ids photon_id_base(launch 0) + k * n_photons + [0, n_photons): its result equals the single
+// launch with that photon_id_base up to the order of the floating-point sums.
+int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, double* det_sum, double* flux,
+                        uint64_t* err_hist, artes_stats_t* stats) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!Ls || n < 1 || n > ARTES_MAX_BATCH) return fail(ctx, -1, "run_batch: 1 <= n <= ARTES_MAX_BATCH launches");
+    if (ctx->pending) return fail(ctx, -1, "a launch is already pending (call artes_gpu_wait)");
+    for (int k = 0; k < n; ++k) {
+        int rc = check_launch(ctx, Ls + k);
+        if (rc) return rc;
+        artes_launch_t a = Ls[k], b = Ls[0];
+        a.det_theta = b.det_theta; a.det_phi = b.det_phi; a.limb_emission = b.limb_emission;
+        if (std::memcmp(&a, &b, sizeof(a)) != 0) return fail(ctx, -1, "run_batch: launches may differ in det_theta, det_phi and limb_emission only");
+    }
+    const artes_launch_t& L0 = Ls[0];
+    if (L0.flow_global || L0.flow_theta) return fail(ctx, -1, "run_batch: flow counters are per launch; use artes_gpu_run");
+    const size_t npx = (size_t)L0.nx * L0.ny;
+    const unsigned long long P = L0.n_photons;
+    static const int engine = env_int("ARTES_ENGINE", 2);
+    bool batched = n > 1 && P > 0 && L0.mode == ARTES_MODE_FAST && engine == 2;
+    if (batched) {
+        KernelArgs a{};
+        a.T = ctx->devs[0].T;
+        fill_launch(L0, a.L);
+        batched = fast::engine2_supports(a);
+    }
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (err_hist) std::memset(err_hist, 0, ARTES_ERR_SLOTS * sizeof(uint64_t));
+    if (!batched) {   // one launch after the other: faithful mode, oblate planets, the persistent-lane engine
+        for (int k = 0; k < n; ++k) {
+            artes_launch_t Lk = Ls[k];
+            Lk.photon_id_base = L0.photon_id_base + (unsigned long long)k * P;
+            uint64_t eh[ARTES_ERR_SLOTS];
+            artes_stats_t st;
+            int rc = artes_gpu_run(ctx, &Lk, det_sum ? det_sum + (size_t)k * 12 * npx : nullptr, flux ? flux + 2 * k : nullptr, nullptr, nullptr, eh, &st);
+            if (rc) return rc;
+            if (err_hist) for (int c = 0; c < ARTES_ERR_SLOTS; ++c) err_hist[c] += eh[c];
+            if (stats) {
+                stats->n_emit += st.n_emit; stats->n_cell_face += st.n_cell_face; stats->n_scatter += st.n_scatter; stats->n_peel += st.n_peel;
+                stats->n_surface += st.n_surface; stats->n_draws += st.n_draws; stats->n_error += st.n_error; stats->reserved += st.reserved;
+                stats->kernel_ms += st.kernel_ms; stats->reduce_ms += st.reduce_ms; stats->d2h_ms += st.d2h_ms; stats->h2d_ms = st.h2d_ms;
+            }
+        }
+        return 0;
+    }
+    const int ndev = (int)ctx->devs.size();
+    const size_t n_d = (size_t)n * (10 * npx + 2);
+    constexpr int GEO = 10;   // = e2::GEO (engine2.cuh): det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi
+    std::vector<double> geo((size_t)n * GEO);
+    for (int k = 0; k < n; ++k) {
+        LaunchArgs t{};
+        fill_launch(Ls[k], t);
+        double* g = geo.data() + (size_t)k * GEO;
+        g[0] = t.det[0]; g[1] = t.det[1]; g[2] = t.det[2]; g[3] = t.sin_dt; g[4] = t.cos_dt; g[5] = t.sin_dp; g[6] = t.cos_dp;
+        g[7] = Ls[k].limb_emission ? 1.0 : 0.0; g[8] = t.det_sph_theta; g[9] = t.det_sph_phi;
+    }
+    const unsigned long long total = P * (unsigned long long)n;
+    unsigned long long per = total / ndev, rem = total % ndev, off = 0;
+    for (int i = 0; i < ndev; ++i) {
+        DeviceState& d = ctx->devs[i];
+        CU(cudaSetDevice(d.dev));
+        int rc = ensure_outputs(ctx, d, n_d);
+        if (rc) return rc;
+        if (d.geo_cap < geo.size()) {
+            if (d.geo) cudaFree(d.geo);
+            d.geo = nullptr; d.geo_cap = 0;
+            CU(cudaMalloc(&d.geo, geo.size() * sizeof(double)));
+            d.geo_cap = geo.size();
+        }
+        CU(cudaMemcpyAsync(d.geo, geo.data(), geo.size() * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemsetAsync(d.out_d, 0, n_d * sizeof(double), d.stream));
+        CU(cudaMemsetAsync(d.out_u, 0, (ARTES_ERR_SLOTS + 16) * sizeof(unsigned long long), d.stream));
+        KernelArgs a{};
+        a.T = d.T;
+        fill_launch(L0, a.L);
+        a.L.n_photons = per + ((unsigned long long)i < rem ? 1 : 0);
+        a.L.id_base = L0.photon_id_base + off;
+        a.L.n_batch = n; a.L.per_launch = P; a.L.batch_base = L0.photon_id_base; a.L.geo = d.geo;
+        off += a.L.n_photons;
+        d.n_photons = a.L.n_photons;
+        a.O.det = d.out_d;
+        a.O.flux = d.out_d + (size_t)n * 10 * npx;
+        a.O.flow4 = nullptr; a.O.flow3 = nullptr;
+        a.O.err = d.out_u;
+        a.O.stats = d.out_u + ARTES_ERR_SLOTS;
+        a.O.counter = d.out_u + ARTES_ERR_SLOTS + 8;
+        CU(cudaEventRecord(d.ev[0], d.stream));
+        d.launches = 0;
+        if (a.L.n_photons > 0) {
+            if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
+            a.O.scratch = d.scratch;
+            cudaError_t e = fast::launch_transport2(a, d.sm_count, d.stream);
+            if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
+            d.launches = 1;
+        }
+        CU(cudaEventRecord(d.ev[1], d.stream));
+    }
+    ctx->last_engine = 2;
+    if ((ndev > 1) || ctx->rank_comm) {
+        NC(g_nccl.GroupStart());
+        for (auto& d : ctx->devs) {
+            NC(g_nccl.AllReduce(d.out_d, d.out_d, n_d, ncclDouble, ncclSum, d.comm, d.stream));
+            NC(g_nccl.AllReduce(d.out_u, d.out_u, ARTES_ERR_SLOTS + 8, ncclUint64, ncclSum, d.comm, d.stream));
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    double kernel_ms = 0.0, reduce_ms = 0.0;
+    for (auto& d : ctx->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaEventRecord(d.ev[2], d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, d.ev[0], d.ev[1]);
+        cudaEventElapsedTime(&b, d.ev[1], d.ev[2]);
+        kernel_ms = std::max(kernel_ms, (double)a);
+        reduce_ms = std::max(reduce_ms, (double)b);
+    }
+    DeviceState& d0 = ctx->devs[0];
+    CU(cudaSetDevice(d0.dev));
+    std::vector<double> h(n_d);
+    std::vector<unsigned long long> hu(ARTES_ERR_SLOTS + 8);
+    CU(cudaEventRecord(d0.ev[3], d0.stream));
+    CU(cudaMemcpyAsync(h.data(), d0.out_d, n_d * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaMemcpyAsync(hu.data(), d0.out_u, hu.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaEventRecord(d0.ev[2], d0.stream));
+    CU(cudaStreamSynchronize(d0.stream));
+    float d2h = 0.f;
+    cudaEventElapsedTime(&d2h, d0.ev[3], d0.ev[2]);
+    for (int k = 0; k < n; ++k) {
+        const double* hk = h.data() + (size_t)k * 10 * npx;
+        if (det_sum) {
+            double* o = det_sum + (size_t)k * 12 * npx;
+            std::memcpy(o, hk, 9 * npx * sizeof(double));
+            for (int q = 1; q < 4; ++q) std::memcpy(o + (8 + q) * npx, hk + 9 * npx, npx * sizeof(double));
+        }
+        if (flux) { flux[2 * k] = h[(size_t)n * 10 * npx + 2 * k]; flux[2 * k + 1] = h[(size_t)n * 10 * npx + 2 * k + 1]; }
+    }
+    if (err_hist) for (int c = 0; c < ARTES_ERR_SLOTS; ++c) err_hist[c] = hu[c];
+    if (stats) {
+        const unsigned long long* u = hu.data() + ARTES_ERR_SLOTS;
+        stats->n_emit = u[0]; stats->n_cell_face = u[1]; stats->n_scatter = u[2]; stats->n_peel = u[3];
+        stats->n_surface = u[4]; stats->n_draws = u[5]; stats->n_error = u[6];
+        unsigned long long launches = 0;
+        for (auto& d : ctx->devs) launches += (unsigned long long)d.launches;
+        stats->reserved = launches;
+        stats->kernel_ms = kernel_ms; stats->reduce_ms = reduce_ms; stats->h2d_ms = ctx->last_h2d_ms; stats->d2h_ms = d2h;
+    }
+    return 0;
 }
 
 int artes_gpu_nccl_unique_id(void* id_out) {

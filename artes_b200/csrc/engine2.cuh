@@ -66,7 +66,8 @@ enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16, PK_SHIFT = 5 };   // bits 5
 enum : int { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_S0, F_S1, F_S2, F_S3, F_TAU, F_W0, F_W1, F_W2, F_W3, NF_COLD,
              F_T = NF_COLD, F_ACC, F_TR, F_TT, F_TP, F_HBN, F_D0, F_IQ, F_LIM, NF_D };
 enum : int { I_CELL = 0, I_INFO, NI_HOT, I_HCELL = NI_HOT, I_PIX, I_ND, I_IDLO, I_IDHI,
-             I_TLEN, I_TNSC, I_THLO, I_THHI, I_FLAG, NF_I };     // I_T*: walk recorder of the trace hook; I_FLAG bit 0: injected stream used up
+             I_TLEN, I_TNSC, I_THLO, I_THHI, I_FLAG, NF_I,
+             I_BATCH = I_TLEN };   // launch index of the photon in a batched launch (the walk recorder never runs batched)     // I_T*: walk recorder of the trace hook; I_FLAG bit 0: injected stream used up
 constexpr int NF_HOT = NF_D - NF_COLD;
 constexpr int REC = 20;       // doubles per cold record: 15 doubles + 10 ints = 160 bytes
 
@@ -79,23 +80,26 @@ __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c 
 __host__ __device__ constexpr int fixed_doubles(int NP) {
     return (NF_HOT * NP * 8 + NI_HOT * NP * 4 + N_LISTS * ring_cap(NP) * 2 + 64 * 4 + 15) / 16 * 2;
 }
+constexpr int GEO = 10;     // doubles per launch in the detector-geometry table: det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi
 struct Lay {
-    int o_r, o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, n_end;   // offsets in doubles
+    int o_r, o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, o_geo, n_end;   // offsets in doubles
     size_t bytes;
-    __host__ __device__ Lay(int nr, int nt, int np, int NP) {
+    __host__ __device__ Lay(int nr, int nt, int np, int NP, int nb = 1) {
         o_r = fixed_doubles(NP);
         o_r2 = o_r + nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
-        o_tp = o_pf + np; o_ca = ((o_tp + (nt + 2) / 2 + 1) + 1) & ~1; n_end = o_ca + 2 * 181;   // o_ca: 16-byte aligned
+        o_tp = o_pf + np; o_ca = ((o_tp + (nt + 2) / 2 + 1) + 1) & ~1; o_geo = o_ca + 2 * 181; n_end = o_geo + GEO * (nb < 1 ? 1 : nb);   // o_ca, o_geo: 16-byte aligned
         bytes = (size_t)n_end * 8;
     }
 };
 
-template <int NP, bool TR = false, bool GN = false>
+template <int NP, bool TR = false, bool GN = false, bool BT = false>
 struct ShT {                     // pointers into the block's shared memory
     static constexpr bool TRACE = TR;   // the injected-stream walk recorder (test hook) is compiled in
+    static constexpr bool BATCH = BT;   // batched launches: per-photon launch index, detector geometry from the shared-memory table
     static constexpr bool GEN = GN;     // thermal source, reflecting surface and latitudinal flow counters are compiled in
     const double* r; const double* r2; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
     const int* tplane;
+    const double* geo;           // [n_batch][GEO] detector geometry of the launch(es)
     const double2* cdfa;         // azimuth prefix table [181] (cos2beta, sin2beta): 17 probes per scattering, kept out of the L1 global path
     double* sd; int* si; short* q; int* head; int* tail;
     int* misc;                   // [0] slots retired for good, [1] event batch counter, [2] ready-list tail at the end of the last event phase
@@ -405,6 +409,26 @@ __device__ __forceinline__ int sample_angles_f(const Sh& X, const KernelArgs& A,
     return 0;
 }
 
+// detector geometry of launch kb (shared memory; one entry for a plain launch)
+// cos of the angle between the surface normal at (x,y,z) and the detector (:4609-4634), detector angles of the photon's launch
+__device__ __noinline__ double surface_cos_angle2(const DevTables& T, double x, double y, double z, double dth, double dph) {
+    double s0 = x / (T.ox * T.ox), s1 = y / (T.oy * T.oy), s2 = z / (T.oz * T.oz);
+    double nrm = sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+    s0 = s0 / nrm; s1 = s1 / nrm; s2 = s2 / nrm;
+    double nth = acos(s2 / sqrt(s0 * s0 + s1 * s1 + s2 * s2));
+    double nph = atan2(s1, s0);
+    if (nph < 0.0) nph = nph + 2.0 * PI;
+    return sin(dth) * cos(dph) * sin(nth) * cos(nph) + sin(dth) * sin(dph) * sin(nth) * sin(nph) + cos(dth) * cos(nth);
+}
+struct Geo { double d0, d1, d2, sdt, cdt, sdp, cdp, limb; };
+template <class Sh>
+__device__ __forceinline__ Geo geo_of(const Sh& X, const LaunchArgs& L, int kb) {
+    if (!Sh::BATCH) { Geo G; G.d0 = L.det[0]; G.d1 = L.det[1]; G.d2 = L.det[2]; G.sdt = L.sin_dt; G.cdt = L.cos_dt; G.sdp = L.sin_dp; G.cdp = L.cos_dp; G.limb = 0.0; return G; }
+    const double4 a = *reinterpret_cast<const double4*>(X.geo + GEO * kb), b = *reinterpret_cast<const double4*>(X.geo + GEO * kb + 4);
+    Geo G; G.d0 = a.x; G.d1 = a.y; G.d2 = a.z; G.sdt = a.w; G.cdt = b.x; G.sdp = b.y; G.cdp = b.z; G.limb = b.w;
+    return G;
+}
+
 struct Cnt {
     unsigned long long n_cf;
     unsigned n_emit, n_sc, n_peel, n_surf, n_err, n_draw;
@@ -417,9 +441,10 @@ struct Cnt {
 // EMIT, planet source: emit_photon :1117-1266 + the thermal weight and the start of peel_thermal :599-621.
 // The cell comes from a binary search on the emissivity CDF (the reference scans it linearly, :1132-1155).
 template <class Sh>
-__device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A, int s, unsigned long long id, Cnt& C, RaySpec& rs) {
+__device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A, int s, unsigned long long id, int kb, Cnt& C, RaySpec& rs) {
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
+    const Geo G = geo_of(X, L, kb);
     double xr[5], xq;
     unsigned nd = 0;
     draws(X, A, s, id, nd, 4, xr); nd += 4;
@@ -471,18 +496,18 @@ __device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A
     X.D(F_DX, s) = dx; X.D(F_DY, s) = dy; X.D(F_DZ, s) = dz;
     const double S0 = 1.0 * bias_weight / __ldg(T.cell_weight + c0 + T.nr * (c1 + T.nt * c2));
     X.D(F_S0, s) = S0;
-    atomicAdd(A.O.flux, S0);
+    atomicAdd(A.O.flux + 2 * kb, S0);
     // peel_thermal :4519-4598: walk to the detector, deposit e^-tau / 4 pi x I (weight applied by DEP)
     ++C.n_peel;
     X.D(F_W0, s) = S0;
     {
-        const double x_im = py * L.cos_dp - px * L.sin_dp;
-        const double y_im = pz * L.sin_dt - py * L.cos_dt * L.sin_dp - px * L.cos_dt * L.cos_dp;
+        const double x_im = py * G.cdp - px * G.sdp;
+        const double y_im = pz * G.sdt - py * G.cdt * G.sdp - px * G.cdt * G.cdp;
         const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
         const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
-        X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1);
+        X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1) + kb * 10 * L.nx * L.ny;
     }
-    rs.set(px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF, 0.0, PK_THERMAL);
+    rs.set(px, py, pz, G.d0, G.d1, G.d2, c0, c1, c2, -1, K_PEEL, CUDART_INF, 0.0, PK_THERMAL);
     return true;
 }
 
@@ -517,16 +542,19 @@ __device__ __forceinline__ bool ev_surface(const Sh& X, const KernelArgs& A, boo
     const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     X.I(I_HCELL, s) = cell;
     const double tau = X.D(F_TAU, s), acc = X.D(F_ACC, s);
-    const double cos_angle = surface_cos_angle(A, wx, wy, wz);
+    const int kb = Sh::BATCH ? X.I(I_BATCH, s) : 0;
+    const double cos_angle = Sh::BATCH ? surface_cos_angle2(T, wx, wy, wz, X.geo[GEO * kb + 8], X.geo[GEO * kb + 9])
+                                       : surface_cos_angle2(T, wx, wy, wz, L.det_sph_theta, L.det_sph_phi);
     if (cos_angle > 0.0) {
         ++C.n_peel;
         X.D(F_W0, s) = X.D(F_S0, s); X.D(F_W1, s) = acc; X.D(F_W2, s) = cos_angle;
-        const double x_im = wy * L.cos_dp - wx * L.sin_dp;
-        const double y_im = wz * L.sin_dt - wy * L.cos_dt * L.sin_dp - wx * L.cos_dt * L.cos_dp;
+        const Geo G = geo_of(X, L, kb);
+        const double x_im = wy * G.cdp - wx * G.sdp;
+        const double y_im = wz * G.sdt - wy * G.cdt * G.sdp - wx * G.cdt * G.cdp;
         const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
         const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
-        X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1);
-        rs.set(wx, wy, wz, L.det[0], L.det[1], L.det[2], c0, c1, c2, T.cell_depth, K_PEEL, CUDART_INF, 0.0, PK_SURFACE);
+        X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1) + kb * 10 * L.nx * L.ny;
+        rs.set(wx, wy, wz, G.d0, G.d1, G.d2, c0, c1, c2, T.cell_depth, K_PEEL, CUDART_INF, 0.0, PK_SURFACE);
     } else
         rs.set(wx, wy, wz, e0, e1, e2, c0, c1, c2, T.cell_depth, K_WALK, tau, acc);
     return true;
@@ -561,7 +589,7 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
     }
     if (Sh::GEN && L.photon_source == 2 && X.I(I_ND, s) > 0) {   // emergent flux of a thermal photon that left the grid (:780, :953)
         const int pinfo = X.I(I_INFO, s);
-        if ((pinfo & 3) == K_WALK && ((pinfo >> 8) & 15) == O_EXIT) atomicAdd(A.O.flux + 1, X.D(F_S0, s));
+        if ((pinfo & 3) == K_WALK && ((pinfo >> 8) & 15) == O_EXIT) atomicAdd(A.O.flux + 1 + (Sh::BATCH ? 2 * X.I(I_BATCH, s) : 0), X.D(F_S0, s));
     }
     X.I(I_ND, s) = 0;
     const unsigned long long k = base + (unsigned long long)__popc(vm & ((1u << lane) - 1u));
@@ -569,14 +597,16 @@ __device__ __forceinline__ bool ev_emit(const Sh& X, const KernelArgs& A, bool v
     ++C.n_emit;
     const unsigned long long id = L.id_base + k;
     X.I(I_IDLO, s) = (int)(unsigned)id; X.I(I_IDHI, s) = (int)(unsigned)(id >> 32);
+    int kb = 0;                              // launch of a batch this work item belongs to
+    if (Sh::BATCH) { kb = (int)((id - L.batch_base) / L.per_launch); X.I(I_BATCH, s) = kb; }
     if (Sh::TRACE) {
         X.I(I_TLEN, s) = 0; X.I(I_TNSC, s) = 0; X.I(I_FLAG, s) = 0;
         X.I(I_THLO, s) = (int)(unsigned)1469598103934665603ull; X.I(I_THHI, s) = (int)(unsigned)(1469598103934665603ull >> 32);
     }
     unsigned nd = 0;
-    if (Sh::GEN && L.photon_source == 2) return ev_emit_thermal(X, A, s, id, C, rs);
+    if (Sh::GEN && L.photon_source == 2) return ev_emit_thermal(X, A, s, id, kb, C, rs);
     double xi, r_disk;
-    if (L.limb_emission) {
+    if (Sh::BATCH ? (X.geo[GEO * kb + 7] != 0.0) : (L.limb_emission != 0)) {
         for (;;) { draws(X, A, s, id, nd, 1, &xi); ++nd; r_disk = sqrt(xi); if (r_disk > 0.9 || (Sh::TRACE && (X.I(I_FLAG, s) & 1))) break; }
     } else { draws(X, A, s, id, nd, 1, &xi); ++nd; r_disk = sqrt(xi); }
     draws(X, A, s, id, nd, 1, &xi); ++nd;
@@ -667,12 +697,15 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     // the marcher stopped after adding the crossing that overshoots tau: step back by the overshoot (:705-720)
     const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - tau0, kap_c);
     const double px = hx + tpos * dx, py = hy + tpos * dy, pz = hz + tpos * dz;
-    double mu = dx * L.det[0] + dy * L.det[1] + dz * L.det[2];
+    const unsigned long long w17_ = (unsigned long long)__double_as_longlong(i1_);
+    const int kb = Sh::BATCH ? (int)(w17_ >> 32) : 0;      // I_BATCH shares the word of I_IDHI
+    const Geo G = geo_of(X, L, kb);
+    double mu = dx * G.d0 + dy * G.d1 + dz * G.d2;
     if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
     const double peel_deg = fm_acos(mu) * (180.0 / PI);
     // ints of the record: piece 4 = [nd | idlo] [idhi | tlen] ...
     const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
-    const unsigned long long id = (w16 >> 32) | (w17 << 32);
+    const unsigned long long id = (w16 >> 32) | ((w17 & 0xffffffffull) << 32);
     unsigned nd = (unsigned)w16;
     bool alive = L.photon_scattering != 0;
     if (Sh::TRACE && (X.I(I_FLAG, s) & 1)) alive = false;       // injected stream used up (test hook only)
@@ -703,27 +736,27 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
         if (!(fabs(dz) < 1.0)) err_count(A, 45);
         else {
             const double smu = fsqrt(1.0 - mu * mu);
-            double nc = fdiv(L.det[2] - dz * mu, smu * fsqrt(1.0 - dz * dz));
+            double nc = fdiv(G.d2 - dz * mu, smu * fsqrt(1.0 - dz * dz));
             if (!(nc == nc)) err_count(A, 44);
             else {
                 nc = fmin(fmax(nc, -1.0), 1.0);
-                const double cr = dy * L.det[0] - dx * L.det[1];
-                const bool flip = (cr > 0.0) || (cr == 0.0 && dx * L.det[0] + dy * L.det[1] > 0.0);
+                const double cr = dy * G.d0 - dx * G.d1;
+                const bool flip = (cr > 0.0) || (cr == 0.0 && dx * G.d0 + dy * G.d1 > 0.0);
                 const double c2a = 2.0 * nc * nc - 1.0;
                 double s2a = 2.0 * nc * fsqrt(fmax(1.0 - nc * nc, 0.0));
                 if (flip) s2a = -s2a;
-                const double nc2 = fdiv(dz - L.det[2] * mu, smu * fsqrt(1.0 - L.det[2] * L.det[2]));
+                const double nc2 = fdiv(dz - G.d2 * mu, smu * fsqrt(1.0 - G.d2 * G.d2));
                 int soft = 0;
-                const int e = (fabs(L.det[2]) < 1.0) ? polrot_f(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
+                const int e = (fabs(G.d2) < 1.0) ? polrot_f(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
                 if (e) err_count(A, e);
                 else if (!(W[0] > 0.0 && W[0] < 1.e100)) err_count(A, 53);
                 else {
-                    const double x_im = py * L.cos_dp - px * L.sin_dp;
-                    const double y_im = pz * L.sin_dt - py * L.cos_dt * L.sin_dp - px * L.cos_dt * L.cos_dp;
+                    const double x_im = py * G.cdp - px * G.sdp;
+                    const double y_im = pz * G.sdt - py * G.cdt * G.sdp - px * G.cdt * G.cdp;
                     const int ix = (int)fdiv(L.nx * (x_im + L.x_max), 2.0 * L.x_max) + 1;
                     const int iy = (int)fdiv(L.ny * (y_im + L.y_max), 2.0 * L.y_max) + 1;
                     if (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) err_count(A, 60);
-                    else pix = (ix - 1) + L.nx * (iy - 1);
+                    else pix = (ix - 1) + L.nx * (iy - 1) + kb * 10 * L.nx * L.ny;
                 }
             }
         }
@@ -774,7 +807,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, tau0, X.D(F_ACC, s), X.D(F_T, s));
 #endif
     X.I(I_ND, s) = (int)nd;
-    rs.set(px, py, pz, L.det[0], L.det[1], L.det[2], c0, c1, c2, -1, K_PEEL, CUDART_INF);
+    rs.set(px, py, pz, G.d0, G.d1, G.d2, c0, c1, c2, -1, K_PEEL, CUDART_INF);
     return true;
 }
 
@@ -827,24 +860,34 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
             v[4] = v[0] * v[0]; v[5] = v[1] * v[1]; v[6] = v[2] * v[2]; v[7] = v[3] * v[3];
         }
         const size_t npx = (size_t)L.nx * L.ny;
-        const int pix0 = __shfl_sync(FULL, pix, __ffs(dm) - 1);
-        const bool same = __all_sync(FULL, !dep || (pix == pix0 && pk == PK_SCATTER));
         if (Sh::GEN && dep && pk != PK_SCATTER) {   // :4583-4585 / :4691-4693: Stokes I only
             double* d = A.O.det + pix;
             atomicAdd(d, w_i); atomicAdd(d + 4 * npx, w_i * w_i); atomicAdd(d + 8 * npx, 1.0);
-        } else if (same && __popc(dm) > 2) {
+        }
+        // Lanes that hit the same pixel are summed in the warp first (up to four pixel groups per batch: a batched
+        // launch has the photons of two launches in flight around each launch boundary); what is left goes lane by lane.
+        unsigned rem = __ballot_sync(FULL, dep && pk == PK_SCATTER), left = 0u;
+        const int lane = threadIdx.x & 31;
+#pragma unroll 1
+        for (int it = 0; it < 4 && rem; ++it) {
+            const int pixg = __shfl_sync(FULL, pix, __ffs(rem) - 1);
+            const unsigned grp = __ballot_sync(FULL, ((rem >> lane) & 1u) && pix == pixg);
+            rem &= ~grp;
+            if (__popc(grp) <= 2) { left |= grp; continue; }
+            const bool in = (grp >> lane) & 1u;
+            double x = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
-            const int lane = threadIdx.x & 31;
-            double* d = A.O.det + pix0;
-            if (lane < 8) {
-                double x = v[0];
-#pragma unroll
-                for (int k = 1; k < 8; ++k) if (lane == k) x = v[k];
-                atomicAdd(d + (size_t)lane * npx, x);
-            } else if (lane < 10) atomicAdd(d + (size_t)lane * npx, (double)__popc(dm));
-        } else if (dep) {
+            for (int k = 0; k < 8; ++k) {
+                double r = in ? v[k] : 0.0;
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+                if (lane == k) x = r;
+            }
+            double* d = A.O.det + pixg;
+            if (lane < 8) atomicAdd(d + (size_t)lane * npx, x);
+            else if (lane < 10) atomicAdd(d + (size_t)lane * npx, (double)__popc(grp));
+        }
+        left |= rem;
+        if ((left >> lane) & 1u) {
             double* d = A.O.det + pix;
 #pragma unroll
             for (int k = 0; k < 8; ++k) atomicAdd(d + (size_t)k * npx, v[k]);
@@ -884,7 +927,11 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
     ldg256(rec, hx, hy, hz, rdx);
     ldg256(rec + 4, rdy, rdz, s0_, s1_);
     (void)s1_;
-    const double n0 = peel ? L.det[0] : rdx, n1 = peel ? L.det[1] : rdy, n2 = peel ? L.det[2] : rdz;
+    double n0 = rdx, n1 = rdy, n2 = rdz;
+    if (peel) {
+        if (Sh::BATCH) { const double* gd = X.geo + GEO * X.I(I_BATCH, s); n0 = gd[0]; n1 = gd[1]; n2 = gd[2]; }
+        else { n0 = L.det[0]; n1 = L.det[1]; n2 = L.det[2]; }
+    }
     RayK K;
     double hbn, D0, iq;
     ray_consts(T, hx, hy, hz, n0, n1, n2, K, hbn, D0, iq);
@@ -913,11 +960,12 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
 // ---------------------------------------------------------------------------------------------------
 // block set-up and the marcher
 // ---------------------------------------------------------------------------------------------------
-template <int NT, int NP, bool TR, bool GN>
-__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP, TR, GN>& X, bool mark_empty) {
+template <int NT, int NP, bool TR, bool GN, bool BT>
+__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP, TR, GN, BT>& X, bool mark_empty) {
     const DevTables& T = A.T;
-    const Lay lay(T.nr, T.nt, T.np, NP);
-    constexpr int RC = ShT<NP, TR, GN>::RC;
+    const int nb = A.L.n_batch > 1 ? A.L.n_batch : 1;
+    const Lay lay(T.nr, T.nt, T.np, NP, nb);
+    constexpr int RC = ShT<NP, TR, GN, BT>::RC;
     X.sd = sm;
     X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
     X.q = reinterpret_cast<short*>(X.si + NI_HOT * NP);
@@ -926,6 +974,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     X.r = sm + lay.o_r; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
     X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
     X.cdfa = reinterpret_cast<const double2*>(sm + lay.o_ca);
+    X.geo = sm + lay.o_geo;
     X.cold = A.O.scratch + (size_t)blockIdx.x * NP * REC;
     const int tid = threadIdx.x;
     for (int i = tid; i <= T.nr; i += NT) { const double r = T.rfront[i]; sm[lay.o_r + i] = r; sm[lay.o_r2 + i] = r * r; }
@@ -935,6 +984,12 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     }
     for (int i = tid; i < T.np; i += NT) { sm[lay.o_ps + i] = T.psin[i]; sm[lay.o_pc + i] = T.pcos[i]; sm[lay.o_pf + i] = T.phifront[i]; }
     for (int i = tid; i < 2 * 181; i += NT) sm[lay.o_ca + i] = T.cdfA2[i];
+    if (BT && A.L.n_batch > 1) { for (int i = tid; i < GEO * nb; i += NT) sm[lay.o_geo + i] = A.L.geo[i]; }
+    else if (BT && tid < GEO) {
+        const LaunchArgs& L = A.L;
+        sm[lay.o_geo + tid] = (tid < 3) ? L.det[tid] : (tid == 3) ? L.sin_dt : (tid == 4) ? L.cos_dt : (tid == 5) ? L.sin_dp
+                            : (tid == 6) ? L.cos_dp : (tid == 7) ? (double)L.limb_emission : (tid == 8) ? L.det_sph_theta : L.det_sph_phi;
+    }
     if (mark_empty) for (int i = tid; i < N_LISTS * RC; i += NT) X.q[i] = (short)-1;
     __syncthreads();
     for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; X.I(I_INFO, i) = 0; }   // every slot starts by asking for a photon
@@ -1095,7 +1150,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
     const DevTables& T = A.T;
     using Sh = ShT<NP, false, false>;
     Sh X;
-    block_setup<NT, NP, false, false>(A, smraw, X, false);
+    block_setup<NT, NP, false, false, false>(A, smraw, X, false);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int trips = A.L.e2_trips > 0 ? A.L.e2_trips : 32;      // marcher steps per round
@@ -1227,13 +1282,13 @@ __device__ __forceinline__ void ring_put(volatile short* e, int s) {
     *e = (short)s;
 }
 
-template <int NT, int NP, int MINB, bool TR, bool GN>
+template <int NT, int NP, int MINB, bool TR, bool GN, bool BT = false>
 __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
-    using Sh = ShT<NP, TR, GN>;
+    using Sh = ShT<NP, TR, GN, BT>;
     Sh X;
-    block_setup<NT, NP, TR, GN>(A, smraw, X, true);
+    block_setup<NT, NP, TR, GN, BT>(A, smraw, X, true);
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;

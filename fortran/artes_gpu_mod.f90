@@ -82,6 +82,18 @@ module artes_gpu_mod
        type(artes_stats_t), intent(out) :: stats
      end function artes_gpu_run
 
+     ! the phase-curve loop (:215-245) as one launch: launches(n) differ in det_theta / det_phi / limb_emission only;
+     ! det_sum(nx,ny,4,3,n), flux(2,n)
+     integer(c_int) function artes_gpu_run_batch(ctx, launches, n, det_sum, flux, err_hist, stats) bind(c, name="artes_gpu_run_batch")
+       import :: c_ptr, c_int, c_double, c_int64_t, artes_launch_t, artes_stats_t
+       type(c_ptr), value               :: ctx
+       type(artes_launch_t), intent(in) :: launches(*)
+       integer(c_int), value            :: n
+       real(c_double), intent(out)      :: det_sum(*), flux(*)
+       integer(c_int64_t), intent(out)  :: err_hist(*)
+       type(artes_stats_t), intent(out) :: stats
+     end function artes_gpu_run_batch
+
   end interface
 
 end module artes_gpu_mod

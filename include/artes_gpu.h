@@ -148,6 +148,18 @@ int  artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* launch);
 int  artes_gpu_wait(artes_gpu_ctx* ctx, double* det_sum, double* flux, double* flow4, double* flow3,
                     uint64_t* err_hist, artes_stats_t* stats);
 
+/* Several launches that share every parameter except the detector direction (det_theta, det_phi,
+ * limb_emission) as ONE kernel launch: the phase-curve loop of the reference (src/ARTES.f90:215-245,
+ * 73 calls of radiative_transfer, one per det_phi) pays the drain of a launch once instead of 73 times.
+ * Launch k uses the photon ids launches[0].photon_id_base + k*n_photons + [0, n_photons), i.e. it equals
+ * artes_gpu_run with that photon_id_base (the launches are statistically independent).
+ *   det_sum [n][nx*ny*4*3], flux [n][2] (either may be NULL); err_hist / stats: sums over the batch.
+ * Flow counters are not available in a batch (error). Where the batched kernel does not apply
+ * (faithful mode, oblate planets) the launches run one after the other with the same results. */
+#define ARTES_MAX_BATCH 256
+int  artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* launches, int n,
+                         double* det_sum, double* flux, uint64_t* err_hist, artes_stats_t* stats);
+
 /* ---- multi-process NCCL (one process per GPU, e.g. under torchrun / MPI) ---------------------- */
 
 #define ARTES_NCCL_ID_BYTES 128

@@ -480,7 +480,7 @@ int main(int argc, char** argv) {
     };
 
     // `call radiative_transfer`
-    auto radiative_transfer = [&](double det_phi) -> int {
+    auto make_launch = [&](double det_phi) -> artes_launch_t {
         artes_launch_t Ln;
         std::memset(&Ln, 0, sizeof(Ln));
         Ln.struct_size = sizeof(Ln); Ln.mode = c.mode; Ln.n_photons = packages; Ln.photon_id_base = 0; Ln.seed = c.seed;
@@ -491,6 +491,10 @@ int main(int argc, char** argv) {
         Ln.fstop = c.fstop; Ln.photon_minimum = c.photon_minimum; Ln.photon_bias = c.photon_bias; Ln.surface_albedo = c.surface_albedo;
         Ln.theta_star = c.theta_star; Ln.phi_star = c.phi_star; Ln.det_theta = c.det_theta; Ln.det_phi = det_phi;
         Ln.x_max = R.x_max; Ln.y_max = R.x_max;
+        return Ln;
+    };
+    auto radiative_transfer = [&](double det_phi) -> int {
+        const artes_launch_t Ln = make_launch(det_phi);
         artes_stats_t st;
         if (artes_gpu_run(ctx, &Ln, det_sum.data(), flux, flow4.empty() ? nullptr : flow4.data(), flow3.empty() ? nullptr : flow3.data(),
                           err_hist, &st) != 0) {
@@ -629,18 +633,44 @@ int main(int argc, char** argv) {
     } else if (c.phase_curve || c.imaging_mono) {
         if (!(rc = prepare_wavelength(0))) {
             if (c.phase_curve) {
-                double det_phi = 0.0;
-                for (int i = 1; i <= 73 && !rc; ++i) {   // :215-245
-                    if (i == 1) det_phi = 1.e-5 * PI / 180.0;
-                    else if (i == 2) det_phi = 2.5 * PI / 180.0;
-                    else if (i == 73) det_phi = (180.0 - 1e-5) * PI / 180.0;
-                    else det_phi = det_phi + 2.5 * PI / 180.0;
-                    std::fprintf(stdout, "\rPhase angle: %6.1f degrees", det_phi * 180.0 / PI); std::fflush(stdout);
-                    if ((rc = radiative_transfer(det_phi))) break;
-                    finish_detector(det_sum, package_energy(R, a.wavelengths[0], det_phi, (double)packages, thermal.total));
-                    write_output(0, det_phi);
+                std::vector<double> phis(73);                // :215-245
+                for (int i = 1; i <= 73; ++i) {
+                    if (i == 1) phis[0] = 1.e-5 * PI / 180.0;
+                    else if (i == 2) phis[1] = 2.5 * PI / 180.0;
+                    else if (i == 73) phis[72] = (180.0 - 1e-5) * PI / 180.0;
+                    else phis[i - 1] = phis[i - 2] + 2.5 * PI / 180.0;
                 }
-                std::fprintf(stdout, "\n");
+                if (!c.flow_global && !c.flow_theta) {
+                    // the 73 calls of radiative_transfer as ONE batched launch (artes_gpu_run_batch): angle k walks the
+                    // photon ids k*packages + [0, packages), so the points are statistically independent like the
+                    // reference's clock-seeded runs
+                    std::vector<artes_launch_t> Ls;
+                    for (double phi : phis) Ls.push_back(make_launch(phi));
+                    std::vector<double> det_all((size_t)73 * 12 * npx), flux_all(2 * 73);
+                    artes_stats_t st;
+                    std::fprintf(stdout, "Phase angles: 73, one batched launch\n"); std::fflush(stdout);
+                    if (artes_gpu_run_batch(ctx, Ls.data(), 73, det_all.data(), flux_all.data(), err_hist, &st) != 0) {
+                        std::fprintf(stderr, "ARTES: artes_gpu_run_batch: %s\n", artes_gpu_last_error(ctx));
+                        rc = 1;
+                    } else {
+                        for (int k = 0; k < ARTES_ERR_SLOTS; ++k) if (err_hist[k]) R.errors[k] += err_hist[k];
+                        R.packets_done += 73 * packages; R.gpu_ms += st.kernel_ms + st.reduce_ms;
+                        for (int i = 0; i < 73; ++i) {
+                            std::copy(det_all.begin() + (size_t)i * 12 * npx, det_all.begin() + (size_t)(i + 1) * 12 * npx, det_sum.begin());
+                            flux[0] = flux_all[2 * i]; flux[1] = flux_all[2 * i + 1];
+                            finish_detector(det_sum, package_energy(R, a.wavelengths[0], phis[i], (double)packages, thermal.total));
+                            write_output(0, phis[i]);
+                        }
+                    }
+                } else {
+                    for (int i = 0; i < 73 && !rc; ++i) {
+                        std::fprintf(stdout, "\rPhase angle: %6.1f degrees", phis[i] * 180.0 / PI); std::fflush(stdout);
+                        if ((rc = radiative_transfer(phis[i]))) break;
+                        finish_detector(det_sum, package_energy(R, a.wavelengths[0], phis[i], (double)packages, thermal.total));
+                        write_output(0, phis[i]);
+                    }
+                    std::fprintf(stdout, "\n");
+                }
             } else {
                 if (!(rc = radiative_transfer(c.det_phi))) {
                     finish_detector(det_sum, package_energy(R, a.wavelengths[0], c.det_phi, (double)packages, thermal.total));

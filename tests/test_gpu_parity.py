@@ -379,6 +379,84 @@ def test_photon_id_sharding_is_additive(atmospheres, gpu_factory):
     assert full["stats"]["n_cell_face"] == s1["stats"]["n_cell_face"] + s2["stats"]["n_cell_face"]
 
 
+def _phase_launches(n, n_photons, det_phis, **kw):
+    out = []
+    for phi in det_phis[:n]:
+        out.append(make_launch(n_photons=n_photons, det_phi=math.radians(phi), limb_emission=int(phi >= 170.0), **kw))
+    return out
+
+
+@pytest.mark.parametrize("name,extra", [("c2_hg_deck", dict(nx=1, ny=1)), ("c4_mie_patches", dict(nx=16, ny=16)),
+                                        ("c4_mie_patches", dict(nx=8, ny=8, surface_albedo=0.5))])
+def test_batched_launches_equal_single_launches(atmospheres, gpu_factory, name, extra):
+    """artes_gpu_run_batch (the phase-curve loop :215-245 as one kernel): image k of the batch equals the single
+    launch with det_phi_k and photon_id_base = k * n_photons, up to the order of the floating-point sums."""
+    atm = atmospheres(name)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=21, **extra)
+    phis = [0.0, 35.0, 90.0, 145.0, 175.0, 180.0, 250.0]
+    P = 30000
+    Ls = _phase_launches(len(phis), P, phis, **kw)
+    b = g.run_batch(Ls)
+    assert g.last_engine() == 2 and b["stats"]["reserved"] == 1          # one kernel for the whole batch
+    tot = dict(n_emit=0, n_cell_face=0, n_scatter=0, n_peel=0, n_draws=0)
+    for k, L in enumerate(Ls):
+        L.photon_id_base = k * P
+        a = g.run(L)
+        for key in tot:
+            tot[key] += a["stats"][key]
+        np.testing.assert_array_equal(b["det"][k][2], a["det"][2])
+        scale = np.abs(a["det"][0]).max()
+        np.testing.assert_allclose(b["det"][k][0], a["det"][0], rtol=1e-9, atol=1e-12 * scale)
+        np.testing.assert_allclose(b["det"][k][1], a["det"][1], rtol=1e-9, atol=1e-12 * scale * scale)
+        np.testing.assert_allclose(b["flux"][k], a["flux"], rtol=1e-12)
+    for key in tot:
+        assert b["stats"][key] == tot[key], key
+    assert b["stats"]["n_emit"] == len(phis) * P
+
+
+def test_batched_launches_thermal_and_fallbacks(atmospheres, gpu_factory):
+    """Batch of thermal-source launches (per-launch emitted / emergent flux), and the sequential fall-back of the
+    faithful mode with the same contract."""
+    from artes_b200.lib import ArtesGpuError, GpuTransport
+    atm3 = atmospheres("c3_molecular")
+    depth = host.cell_depth(atm3.rfront, atm3.k_sca[0], atm3.k_abs[0], atm3.nr, atm3.ntheta, atm3.nphi, 2)
+    vol = host.cell_volume(atm3.rfront, atm3.thetafront(), atm3.phifront())
+    cw, lum, cdf = host.thermal_tables(depth, atm3.k_abs[0], atm3.temperature, vol, atm3.wavelengths[0] * 1e-6,
+                                       atm3.nr, atm3.ntheta, atm3.nphi)
+    g3 = GpuTransport((0,))
+    g3.set_grid(atm3.rfront, atm3.thetafront(), atm3.thetaplane(), atm3.phifront())
+    g3.set_wavelength(atm3.k_sca[0], atm3.k_abs[0], atm3.uniq[0], atm3.cell_to_uniq[0], depth, cw, cdf)
+    xm = 1.3 * atm3.rfront[-1]
+    P = 20000
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=9, photon_source=2, photon_emission=1, nx=4, ny=4)
+    Ls = _phase_launches(3, P, [10.0, 100.0, 200.0], **kw)
+    b = g3.run_batch(Ls)
+    assert g3.last_engine() == 2 and b["stats"]["reserved"] == 1
+    for k, L in enumerate(Ls):
+        L.photon_id_base = k * P
+        a = g3.run(L)
+        np.testing.assert_allclose(b["flux"][k], a["flux"], rtol=1e-10)
+        np.testing.assert_array_equal(b["det"][k][2], a["det"][2])
+        np.testing.assert_allclose(b["det"][k][0], a["det"][0], rtol=1e-9, atol=1e-12 * np.abs(a["det"][0]).max())
+    # faithful mode: no batched kernel, same results through the sequential path
+    kwf = dict(mode=abi.MODE_FAITHFUL, x_max=xm, y_max=xm, seed=9, nx=4, ny=4)
+    Lf = _phase_launches(2, 5000, [30.0, 120.0], **kwf)
+    bf = g3.run_batch(Lf)
+    assert bf["stats"]["reserved"] == 2
+    for k, L in enumerate(Lf):
+        L.photon_id_base = k * 5000
+        a = g3.run(L)
+        np.testing.assert_array_equal(bf["det"][k][2], a["det"][2])
+        np.testing.assert_allclose(bf["det"][k][0], a["det"][0], rtol=1e-9, atol=1e-12 * np.abs(a["det"][0]).max())
+    # launches that differ in more than the detector direction are refused
+    bad = _phase_launches(2, 100, [0.0, 10.0], **kwf)
+    bad[1].fstop = 0.5
+    with pytest.raises(ArtesGpuError):
+        g3.run_batch(bad)
+
+
 def test_errors_are_reported_not_fatal(atmospheres):
     from artes_b200.lib import ArtesGpuError, GpuTransport
     atm = atmospheres("c1_template_rayleigh")
