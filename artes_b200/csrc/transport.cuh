@@ -533,8 +533,12 @@ __device__ __forceinline__ double frcp(double b) {
     e = fma(-b, x, 1.0);
     return fma(x, e, x);
 }
+// The quotient and the root end with a residual correction (q += (a - b q) x, g += (a - g^2) h) that squares the
+// error once more, so ONE Newton step on the seed is enough in front of it: seed 2^-20 -> 2^-39 -> below the rounding.
 __device__ __forceinline__ double fdiv(double a, double b) {
-    const double x = frcp(b);
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(b));
+    x = fma(x, fma(-b, x, 1.0), x);
     const double q = a * x;
     return fma(fma(-b, q, a), x, q);
 }
@@ -542,9 +546,7 @@ __device__ __forceinline__ double fsqrt(double a) {   // a >= 0
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     double g = a * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g); h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
+    const double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
     g = fma(fma(-g, g, a), h, g);
     return (a > 0.0) ? g : 0.0;

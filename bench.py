@@ -122,6 +122,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--photons", type=float, default=0, help="photon packets per GPU per step")
     ap.add_argument("--mode", default="fast", choices=["fast", "faithful"])
+    ap.add_argument("--batch", type=int, default=0, help="N > 1: every step is ONE batched launch (artes_gpu_run_batch) of N launches x --photons "
+                                                         "packets whose det_phi sweeps 0..180 deg like the phase-curve loop src/ARTES.f90:215-245")
     ap.add_argument("--cpu-sample", type=float, default=300000, help="photons of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -133,13 +135,16 @@ def main():
     from tools import atmospheres as A
     builder, wl_kw, default_p = WORKLOADS[args.workload]
     atm = getattr(A, builder)()
-    P = int(args.photons) if args.photons else default_p
+    P = int(args.photons) if args.photons else (1_000_000 if args.batch > 1 else default_p)
+    NB = args.batch if args.batch > 1 else 1
     config = {"workload": f"{args.workload}:{builder} nr={atm.nr} ntheta={atm.ntheta} nphi={atm.nphi} "
                           f"image={wl_kw['nx']}x{wl_kw['ny']} det_phi={wl_kw['det_phi']}deg star source, peel-off on",
-              "photons_per_gpu_per_step": P, "mode": args.mode, "parallelism": f"photon-id sharding x{world}",
+              "photons_per_gpu_per_step": P * NB, "mode": args.mode, "parallelism": f"photon-id sharding x{world}",
               "l2": "tables (<= few MB) are L2-resident by design; 256 MiB memset flushes L2 between steps"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
+    if NB > 1:
+        config["batch"] = f"{NB} launches x {P} packets per step as one kernel (artes_gpu_run_batch), det_phi = 0..180 deg"
     if args.impl == "reference":
         if rank != 0:
             return
@@ -176,7 +181,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     mode = abi.MODE_FAST if args.mode == "fast" else abi.MODE_FAITHFUL
-    params = host.Params(nx=wl_kw["nx"], ny=wl_kw["ny"], det_phi=math.radians(wl_kw["det_phi"]))
+    params = host.Params(nx=wl_kw["nx"], ny=wl_kw["ny"], det_phi=math.radians(wl_kw["det_phi"]), phase_curve=NB > 1)
     t = host.Transport(atm, params, devices=(local_rank,), mode=mode)
     if world > 1:  # NCCL communicator of the library itself: the id travels through torch.distributed
         adist.init_library_comm(t.gpu, dist, rank, world)
@@ -190,7 +195,9 @@ def main():
         torch.cuda.synchronize()
 
     def step(i):
-        base = adist.step_base(i, world, rank, P)   # disjoint photon ids for every step and rank
+        base = adist.step_base(i, world, rank, P * NB)   # disjoint photon ids for every step and rank
+        if NB > 1:
+            return t.gpu.run_batch([t.launch_struct(P, seed=4, photon_id_base=base, det_phi=math.pi * k / (NB - 1)) for k in range(NB)])
         L = t.launch_struct(P, seed=4, photon_id_base=base)
         return t.gpu.run(L)
 
@@ -222,12 +229,12 @@ def main():
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     dev_ms, kern_ms = float(tm[0]), float(tm[1])
-    value = world * args.steps * P / (dev_ms * 1e-3)
+    value = world * args.steps * P * NB / (dev_ms * 1e-3)
 
     # ---- end to end through the public call with host buffers: upload tables, launch, download image
     a = atm
     h2d = (a.k_sca[0].nbytes + a.k_abs[0].nbytes + a.uniq[0].nbytes + a.cell_to_uniq[0].nbytes)
-    d2h = (10 * wl_kw["nx"] * wl_kw["ny"] + 2 + 7 * a.cells) * 8 + (64 + 8) * 8
+    d2h = ((10 * wl_kw["nx"] * wl_kw["ny"] + 2) * NB + (7 * a.cells if NB == 1 else 0)) * 8 + (64 + 8) * 8
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -238,7 +245,7 @@ def main():
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = world * args.steps * P / float(te[0])
+    e2e = world * args.steps * P * NB / float(te[0])
 
     if rank == 0:
         fl, by = algorithmic(agg, atm, args.mode)          # all ranks, all timed steps
@@ -255,7 +262,7 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-            traffic = tr["dram_bytes_per_launch"] * P / tr["photons_per_launch"] if tr else None   # scaled to this launch size
+            traffic = tr["dram_bytes_per_launch"] * P * NB / tr["photons_per_launch"] if tr else None   # scaled to this launch size
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -271,12 +278,12 @@ def main():
                                      "per-event figures; peak = FP64 FMA rate measured in this run by artes_gpu_fma_peak "
                                      "(MEASURED_PEAKS.json holds no FP64 figure); traffic = ncu dram bytes per launch of "
                                      "the same workload (profiles/traffic.json)",
-                             "flop_per_packet": fl / (world * args.steps * P), "fp32_peak_tflops": peaks["fp32_tflops"]},
+                             "flop_per_packet": fl / (world * args.steps * P * NB), "fp32_peak_tflops": peaks["fp32_tflops"]},
                 "roofline_hbm": {"bound": "hbm", "achieved": per_launch_by / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": per_launch_by / k_s / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback",
                                  "note": "algorithmic bytes are table reads served by L1/L2; HBM is not the bound of this path"},
-                "events_per_packet": {k: v / (world * args.steps * P) for k, v in agg.items()}}
+                "events_per_packet": {k: v / (world * args.steps * P * NB) for k, v in agg.items()}}
         if world == 1 and not args.no_cpu_baseline:
             sample = int(args.cpu_sample)
             dt, cores, _ = cpu_arm(atm, wl_kw, sample, 7)
