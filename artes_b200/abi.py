@@ -16,7 +16,7 @@ class Launch(C.Structure):
         ("photon_source", C.c_int32), ("photon_scattering", C.c_int32),
         ("photon_emission", C.c_int32), ("stellar_direction", C.c_int32),
         ("limb_emission", C.c_int32), ("flow_global", C.c_int32), ("flow_theta", C.c_int32),
-        ("nx", C.c_int32), ("ny", C.c_int32), ("reserved0", C.c_int32),
+        ("nx", C.c_int32), ("ny", C.c_int32), ("wl_index", C.c_int32),
         ("fstop", C.c_double), ("photon_minimum", C.c_double), ("photon_bias", C.c_double),
         ("surface_albedo", C.c_double), ("theta_star", C.c_double), ("phi_star", C.c_double),
         ("det_theta", C.c_double), ("det_phi", C.c_double), ("x_max", C.c_double), ("y_max", C.c_double),

@@ -112,6 +112,9 @@ struct artes_gpu_ctx {
     size_t n_out_d = 0;
     double last_h2d_ms = 0.0;
     int last_engine = 0;
+    // tables of several wavelengths at once (artes_gpu_set_wavelengths): per-cell tables are [n_wl][cells]
+    int n_wl = 1;
+    std::vector<int> wl_depth;
 };
 
 namespace {
@@ -210,6 +213,7 @@ int check_launch(artes_gpu_ctx* ctx, const artes_launch_t* L) {
     if (L->photon_source != 1 && L->photon_source != 2) return fail(ctx, -1, "photon_source must be 1 or 2");
     if (L->photon_source == 2 && !ctx->thermal) return fail(ctx, -1, "photon_source=2 needs cell_weight and emis_cdf");
     if (L->nx < 1 || L->ny < 1 || !(L->x_max > 0.0) || !(L->y_max > 0.0)) return fail(ctx, -1, "bad detector geometry");
+    if (L->wl_index < 0 || L->wl_index >= ctx->n_wl) return fail(ctx, -1, "wl_index outside the tables of set_wavelength(s)");
     return 0;
 }
 
@@ -340,14 +344,20 @@ int artes_gpu_set_grid(artes_gpu_ctx* ctx, int nr, int ntheta, int nphi, const d
     return 0;
 }
 
-int artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, int n_uniq,
-                             const double* uniq_matrix, const int32_t* cell_to_uniq, int cell_depth,
-                             const double* cell_weight, const double* emis_cdf) {
+}  // extern "C"
+
+namespace {
+// tables of n_wl wavelengths: the per-cell arrays are [n_wl][cells], cell_to_uniq indexes one common list of matrices
+int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, const double* k_abs, int n_uniq,
+                          const double* uniq_matrix, const int32_t* cell_to_uniq, const int* cell_depths,
+                          const double* cell_weight, const double* emis_cdf) {
     if (!ctx) return fail(nullptr, -1, "null context");
     if (!ctx->have_grid) return fail(ctx, -1, "set_grid first");
-    if (!k_sca || !k_abs || !uniq_matrix || !cell_to_uniq || n_uniq < 1) return fail(ctx, -1, "bad wavelength tables");
-    if (cell_depth < 0 || cell_depth >= ctx->nr) return fail(ctx, -1, "cell_depth out of range");
-    const int n = ctx->cells;
+    if (!k_sca || !k_abs || !uniq_matrix || !cell_to_uniq || n_uniq < 1 || n_wl < 1 || !cell_depths) return fail(ctx, -1, "bad wavelength tables");
+    for (int l = 0; l < n_wl; ++l) if (cell_depths[l] < 0 || cell_depths[l] >= ctx->nr) return fail(ctx, -1, "cell_depth out of range");
+    const int cell_depth = cell_depths[0];
+    if ((long long)ctx->cells * n_wl > 2000000000LL) return fail(ctx, -1, "too many cells x wavelengths for one table set");
+    const int n = ctx->cells * n_wl;
     for (int i = 0; i < n; ++i) if (cell_to_uniq[i] < 0 || cell_to_uniq[i] >= n_uniq) return fail(ctx, -1, "cell_to_uniq out of range");
     std::vector<double> kext(n), albedo(n, 0.0);
     for (int i = 0; i < n; ++i) {  // :2178-2188
@@ -413,7 +423,23 @@ int artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const doub
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
     ctx->have_wl = true;
+    ctx->n_wl = n_wl;
+    ctx->wl_depth.assign(cell_depths, cell_depths + n_wl);
     return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, int n_uniq,
+                             const double* uniq_matrix, const int32_t* cell_to_uniq, int cell_depth,
+                             const double* cell_weight, const double* emis_cdf) {
+    return set_wavelength_tables(ctx, 1, k_sca, k_abs, n_uniq, uniq_matrix, cell_to_uniq, &cell_depth, cell_weight, emis_cdf);
+}
+
+int artes_gpu_set_wavelengths(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, const double* k_abs, int n_uniq,
+                              const double* uniq_matrix, const int32_t* cell_to_uniq, const int32_t* cell_depths) {
+    return set_wavelength_tables(ctx, n_wl, k_sca, k_abs, n_uniq, uniq_matrix, cell_to_uniq, cell_depths, nullptr, nullptr);
 }
 
 int artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, const double* dense,
@@ -470,6 +496,11 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
         CU(cudaMemsetAsync(d.out_u, 0, (ARTES_ERR_SLOTS + 16) * sizeof(unsigned long long), d.stream));
         KernelArgs a{};
         a.T = d.T;
+        if (L->wl_index > 0) {   // tables of wavelength wl_index out of the stacked set
+            const size_t o = (size_t)L->wl_index * ctx->cells;
+            a.T.kext += o; a.T.albedo += o; a.T.c2u += o; a.T.cellrec += 4 * o;
+            a.T.cell_depth = ctx->wl_depth[L->wl_index];
+        }
         fill_launch(*L, a.L);
         a.L.n_photons = per + ((unsigned long long)i < rem ? 1 : 0);
         a.L.id_base = L->photon_id_base + off;
@@ -594,8 +625,8 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         int rc = check_launch(ctx, Ls + k);
         if (rc) return rc;
         artes_launch_t a = Ls[k], b = Ls[0];
-        a.det_theta = b.det_theta; a.det_phi = b.det_phi; a.limb_emission = b.limb_emission;
-        if (std::memcmp(&a, &b, sizeof(a)) != 0) return fail(ctx, -1, "run_batch: launches may differ in det_theta, det_phi and limb_emission only");
+        a.det_theta = b.det_theta; a.det_phi = b.det_phi; a.limb_emission = b.limb_emission; a.wl_index = b.wl_index;
+        if (std::memcmp(&a, &b, sizeof(a)) != 0) return fail(ctx, -1, "run_batch: launches may differ in det_theta, det_phi, limb_emission and wl_index only");
     }
     const artes_launch_t& L0 = Ls[0];
     if (L0.flow_global || L0.flow_theta) return fail(ctx, -1, "run_batch: flow counters are per launch; use artes_gpu_run");
@@ -630,7 +661,9 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
     }
     const int ndev = (int)ctx->devs.size();
     const size_t n_d = (size_t)n * (10 * npx + 2);
-    constexpr int GEO = 10;   // = e2::GEO (engine2.cuh): det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi
+    constexpr int GEO = 12;   // = e2::GEO (engine2.cuh): det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi, cell_depth, wavelength index
+    bool wl_batch = false;
+    for (int k = 0; k < n; ++k) wl_batch = wl_batch || Ls[k].wl_index != 0;
     std::vector<double> geo((size_t)n * GEO);
     for (int k = 0; k < n; ++k) {
         LaunchArgs t{};
@@ -638,6 +671,7 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         double* g = geo.data() + (size_t)k * GEO;
         g[0] = t.det[0]; g[1] = t.det[1]; g[2] = t.det[2]; g[3] = t.sin_dt; g[4] = t.cos_dt; g[5] = t.sin_dp; g[6] = t.cos_dp;
         g[7] = Ls[k].limb_emission ? 1.0 : 0.0; g[8] = t.det_sph_theta; g[9] = t.det_sph_phi;
+        g[10] = (double)ctx->wl_depth[Ls[k].wl_index]; g[11] = (double)Ls[k].wl_index;
     }
     const unsigned long long total = P * (unsigned long long)n;
     unsigned long long per = total / ndev, rem = total % ndev, off = 0;
@@ -660,7 +694,7 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         fill_launch(L0, a.L);
         a.L.n_photons = per + ((unsigned long long)i < rem ? 1 : 0);
         a.L.id_base = L0.photon_id_base + off;
-        a.L.n_batch = n; a.L.per_launch = P; a.L.batch_base = L0.photon_id_base; a.L.geo = d.geo;
+        a.L.n_batch = n; a.L.per_launch = P; a.L.batch_base = L0.photon_id_base; a.L.geo = d.geo; a.L.wl_batch = wl_batch ? 1 : 0;
         off += a.L.n_photons;
         d.n_photons = a.L.n_photons;
         a.O.det = d.out_d;

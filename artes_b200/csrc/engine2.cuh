@@ -80,7 +80,8 @@ __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c 
 __host__ __device__ constexpr int fixed_doubles(int NP) {
     return (NF_HOT * NP * 8 + NI_HOT * NP * 4 + N_LISTS * ring_cap(NP) * 2 + 64 * 4 + 15) / 16 * 2;
 }
-constexpr int GEO = 10;     // doubles per launch in the detector-geometry table: det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi
+constexpr int GEO = 12;     // doubles per launch in the launch table: det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi,
+                            // cell_depth and wavelength index of the launch (batches over wavelengths: LaunchArgs::wl_batch)
 struct Lay {
     int o_r, o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, o_geo, n_end;   // offsets in doubles
     size_t bytes;
@@ -429,6 +430,16 @@ __device__ __forceinline__ Geo geo_of(const Sh& X, const LaunchArgs& L, int kb) 
     return G;
 }
 
+// cell_depth / wavelength index of the photon's launch (they differ between the launches of a wavelength batch only)
+template <class Sh>
+__device__ __forceinline__ int depth_of(const Sh& X, const KernelArgs& A, int kb) {
+    return (Sh::BATCH && A.L.wl_batch) ? (int)X.geo[GEO * kb + 10] : A.T.cell_depth;
+}
+template <class Sh>
+__device__ __forceinline__ int wl_of(const Sh& X, const KernelArgs& A, int kb) {
+    return (Sh::BATCH && A.L.wl_batch) ? (int)X.geo[GEO * kb + 11] : 0;
+}
+
 struct Cnt {
     unsigned long long n_cf;
     unsigned n_emit, n_sc, n_peel, n_surf, n_err, n_draw;
@@ -554,9 +565,9 @@ __device__ __forceinline__ bool ev_surface(const Sh& X, const KernelArgs& A, boo
         const int ix = (int)(L.nx * (x_im + L.x_max) / (2.0 * L.x_max)) + 1;
         const int iy = (int)(L.ny * (y_im + L.y_max) / (2.0 * L.y_max)) + 1;
         X.I(I_PIX, s) = (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) ? -2 : (ix - 1) + L.nx * (iy - 1) + kb * 10 * L.nx * L.ny;
-        rs.set(wx, wy, wz, G.d0, G.d1, G.d2, c0, c1, c2, T.cell_depth, K_PEEL, CUDART_INF, 0.0, PK_SURFACE);
+        rs.set(wx, wy, wz, G.d0, G.d1, G.d2, c0, c1, c2, depth_of(X, A, kb), K_PEEL, CUDART_INF, 0.0, PK_SURFACE);
     } else
-        rs.set(wx, wy, wz, e0, e1, e2, c0, c1, c2, T.cell_depth, K_WALK, tau, acc);
+        rs.set(wx, wy, wz, e0, e1, e2, c0, c1, c2, depth_of(X, A, kb), K_WALK, tau, acc);
     return true;
 }
 
@@ -691,14 +702,13 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     (void)w0_; (void)i2_; (void)i3_;
     // per-cell record {cell_opacity, cell_albedo, unique-matrix index}: one 256-bit read instead of three scattered ones
     double kap_c, alb_c, u_bits, pad_c;
-    ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
+    const int kb = Sh::BATCH ? (int)((unsigned long long)__double_as_longlong(i1_) >> 32) : 0;      // I_BATCH shares the word of I_IDHI
+    ldg256_nc(T.cellrec + (size_t)4 * ((size_t)ci + (size_t)wl_of(X, A, kb) * T.cells), kap_c, alb_c, u_bits, pad_c);
     (void)pad_c;
     const int u = (int)__double_as_longlong(u_bits);
     // the marcher stopped after adding the crossing that overshoots tau: step back by the overshoot (:705-720)
     const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - tau0, kap_c);
     const double px = hx + tpos * dx, py = hy + tpos * dy, pz = hz + tpos * dz;
-    const unsigned long long w17_ = (unsigned long long)__double_as_longlong(i1_);
-    const int kb = Sh::BATCH ? (int)(w17_ >> 32) : 0;      // I_BATCH shares the word of I_IDHI
     const Geo G = geo_of(X, L, kb);
     double mu = dx * G.d0 + dy * G.d1 + dz * G.d2;
     if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
@@ -902,7 +912,7 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
     }
     if (Sh::GEN && pk == PK_SURFACE) {          // the reflected photon goes on with its old tau and running sum (:766-776)
         rs.set(hx, hy, hz, dx, dy, dz,
-                  hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, A.T.cell_depth, K_WALK, tau, W1);
+                  hc & 1023, (hc >> 10) & 1023, (hc >> 20) & 1023, depth_of(X, A, Sh::BATCH ? X.I(I_BATCH, s) : 0), K_WALK, tau, W1);
         return true;
     }
     if (tau < 0.0) { X.I(I_INFO, s) = K_DEAD; return true; }
@@ -988,7 +998,8 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     else if (BT && tid < GEO) {
         const LaunchArgs& L = A.L;
         sm[lay.o_geo + tid] = (tid < 3) ? L.det[tid] : (tid == 3) ? L.sin_dt : (tid == 4) ? L.cos_dt : (tid == 5) ? L.sin_dp
-                            : (tid == 6) ? L.cos_dp : (tid == 7) ? (double)L.limb_emission : (tid == 8) ? L.det_sph_theta : L.det_sph_phi;
+                            : (tid == 6) ? L.cos_dp : (tid == 7) ? (double)L.limb_emission : (tid == 8) ? L.det_sph_theta
+                            : (tid == 9) ? L.det_sph_phi : (tid == 10) ? (double)A.T.cell_depth : 0.0;
     }
     if (mark_empty) for (int i = tid; i < N_LISTS * RC; i += NT) X.q[i] = (short)-1;
     __syncthreads();
@@ -1037,6 +1048,11 @@ struct Marcher {
         c0 = cell & 1023; cell12 = cell & ~1023;
         dr = (info & B_INWARD) ? -1 : 1; ds = (info & B_INWARD) ? -1.0 : 1.0;
         kb = kext + nr * (((cell >> 10) & 1023) + nt * ((cell >> 20) & 1023));
+        if (Sh::BATCH && A.L.wl_batch) {       // wavelength batch: the opacity table and the surface layer of the photon's launch
+            const int kbi = X.I(I_BATCH, s);
+            kb += (size_t)wl_of(X, A, kbi) * A.T.cells;
+            depth = depth_of(X, A, kbi);
+        }
         kap = __ldg(kb + c0);
         if (Sh::TRACE) {
             tl = X.I(I_TLEN, s);

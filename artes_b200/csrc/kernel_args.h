@@ -50,12 +50,13 @@ struct LaunchArgs {
     // star rotation (:1080-1109), host-evaluated trigonometry
     double rot_y_cos, rot_y_sin, rot_z_cos, rot_z_sin, star_dir[3];
     // batched launches (artes_gpu_run_batch; ray/event engine only): n_photons = n_batch * per_launch work items, item w
-    // belongs to launch (id_base + w - batch_base) / per_launch; geo = [n_batch][10] {det(3), sin_dt, cos_dt, sin_dp, cos_dp,
-    // limb_emission, det_sph_theta, det_sph_phi} in device memory (null for a single launch: the fields above are used).  Images and fluxes of the
+    // belongs to launch (id_base + w - batch_base) / per_launch; geo = [n_batch][12] {det(3), sin_dt, cos_dt, sin_dp, cos_dp,
+    // limb_emission, det_sph_theta, det_sph_phi, cell_depth, wavelength index} in device memory (null for a single launch: the fields above are used).  Images and fluxes of the
     // launches follow each other in DevOutputs::det ([n_batch][10][ny][nx]) and ::flux ([n_batch][2]).
     unsigned long long per_launch, batch_base;
     const double* geo;
-    int n_batch, pad_batch;
+    int n_batch;
+    int wl_batch;                    // 1: the launches of the batch use different wavelengths: kext / cellrec are [n_wl][cells], geo[k][10..11] = cell_depth, wavelength index
 };
 
 // Device accumulators of one launch.

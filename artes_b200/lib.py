@@ -23,7 +23,7 @@ _up = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "artes_gpu_create", "artes_gpu_destroy", "artes_gpu_last_error", "artes_gpu_abi_version",
     "artes_gpu_set_grid", "artes_gpu_set_wavelength", "artes_gpu_set_wavelength_dense",
-    "artes_gpu_run", "artes_gpu_run_batch", "artes_gpu_run_async", "artes_gpu_wait", "artes_gpu_nccl_unique_id",
+    "artes_gpu_set_wavelengths", "artes_gpu_run", "artes_gpu_run_batch", "artes_gpu_run_async", "artes_gpu_wait", "artes_gpu_nccl_unique_id",
     "artes_gpu_nccl_init_rank", "artes_gpu_trace", "artes_gpu_cell_face", "artes_gpu_device_info",
     "artes_gpu_fma_peak", "artes_gpu_last_engine",
 ]
@@ -52,6 +52,7 @@ def load():
     lib.artes_gpu_set_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _dp,
                                        C.c_double, C.c_double, C.c_double]
     lib.artes_gpu_set_wavelength.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _dp, _ip, C.c_int, C.c_void_p, C.c_void_p]
+    lib.artes_gpu_set_wavelengths.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, _ip, _ip]
     lib.artes_gpu_set_wavelength_dense.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p]
     lib.artes_gpu_run.argtypes = [C.c_void_p, C.POINTER(Launch), _dp, _dp, C.c_void_p, C.c_void_p, _up, C.POINTER(Stats)]
     lib.artes_gpu_run_async.argtypes = [C.c_void_p, C.POINTER(Launch)]
@@ -136,6 +137,19 @@ class GpuTransport:
             cw, ce = a.ctypes.data, b.ctypes.data
         self._check(self.lib.artes_gpu_set_wavelength(self.h, k_sca, k_abs, uniq.shape[0], uniq, c2u, int(cell_depth), cw, ce),
                     "artes_gpu_set_wavelength")
+
+    def set_wavelengths(self, k_sca, k_abs, uniq, cell_to_uniq, cell_depths):
+        """Tables of several wavelengths at once: k_sca, k_abs, cell_to_uniq are (n_wl, cells); uniq is ONE common list."""
+        k_sca = np.ascontiguousarray(k_sca, dtype=np.float64)
+        k_abs = np.ascontiguousarray(k_abs, dtype=np.float64)
+        uniq = np.ascontiguousarray(uniq, dtype=np.float64)
+        c2u = np.ascontiguousarray(cell_to_uniq, dtype=np.int32)
+        depths = np.ascontiguousarray(cell_depths, dtype=np.int32)
+        n_wl = depths.size
+        if not (k_sca.size == n_wl * self.cells and k_abs.size == n_wl * self.cells and c2u.size == n_wl * self.cells):
+            raise ValueError("per-cell arrays do not match the grid x wavelengths")
+        self._check(self.lib.artes_gpu_set_wavelengths(self.h, n_wl, k_sca, k_abs, uniq.shape[0], uniq, c2u, depths),
+                    "artes_gpu_set_wavelengths")
 
     def set_wavelength_dense(self, k_sca, k_abs, dense, cell_depth, cell_weight=None, emis_cdf=None):
         """dense: numpy array (180, 16, nphi, ntheta, nr) = HDU 8 of atmosphere.fits for one wavelength."""

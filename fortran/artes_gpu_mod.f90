@@ -20,7 +20,7 @@ module artes_gpu_mod
      integer(c_int64_t) :: photon_id_base
      integer(c_int64_t) :: seed
      integer(c_int32_t) :: photon_source, photon_scattering, photon_emission, stellar_direction
-     integer(c_int32_t) :: limb_emission, flow_global, flow_theta, nx, ny, reserved0
+     integer(c_int32_t) :: limb_emission, flow_global, flow_theta, nx, ny, wl_index
      real(c_double)     :: fstop, photon_minimum, photon_bias, surface_albedo
      real(c_double)     :: theta_star, phi_star, det_theta, det_phi, x_max, y_max
   end type artes_launch_t

@@ -49,7 +49,7 @@
     launch%flow_theta = merge(1, 0, flow_theta)
     launch%nx = nx
     launch%ny = ny
-    launch%reserved0 = 0
+    launch%wl_index = 0
     launch%fstop = fstop
     launch%photon_minimum = photon_minimum
     launch%photon_bias = photon_bias

@@ -53,7 +53,7 @@ typedef struct artes_launch_t {
     int32_t  flow_global;       /* (:53)                                                               */
     int32_t  flow_theta;        /* (:54)                                                               */
     int32_t  nx, ny;            /* detector pixels (:48-49)                                            */
-    int32_t  reserved0;
+    int32_t  wl_index;          /* wavelength of the launch: index into the tables of artes_gpu_set_wavelengths (0 otherwise) */
     double   fstop;             /* (:29)                                                               */
     double   photon_minimum;    /* (:30)                                                               */
     double   photon_bias;       /* (:34)                                                               */
@@ -118,6 +118,14 @@ int  artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const dou
                               int n_uniq, const double* uniq_matrix, const int32_t* cell_to_uniq,
                               int cell_depth, const double* cell_weight, const double* emis_cdf);
 
+/* The tables of n_wl wavelengths at once (the wl_count loop of the spectrum / broadband modes, src/ARTES.f90:132-204):
+ * k_sca, k_abs, cell_to_uniq are [n_wl][cells], cell_to_uniq indexes ONE common list of n_uniq matrix blocks,
+ * cell_depths[n_wl].  A launch picks its wavelength with artes_launch_t::wl_index; launches of different wavelengths
+ * can then share one batched kernel launch (artes_gpu_run_batch).  Star source only (no thermal tables). */
+int  artes_gpu_set_wavelengths(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, const double* k_abs,
+                               int n_uniq, const double* uniq_matrix, const int32_t* cell_to_uniq,
+                               const int32_t* cell_depths);
+
 /* Same, taking the reference's dense array for ONE wavelength exactly as it sits in memory
  * after ftgpvd (src/ARTES.f90:2196-2198): element (cell, e, a) at cell + cells*(e + 16*a),
  * e = 0..15, a = 0..179.  De-duplicated internally (hash of each cell's 2880 doubles). */
@@ -149,7 +157,8 @@ int  artes_gpu_wait(artes_gpu_ctx* ctx, double* det_sum, double* flux, double* f
                     uint64_t* err_hist, artes_stats_t* stats);
 
 /* Several launches that share every parameter except the detector direction (det_theta, det_phi,
- * limb_emission) as ONE kernel launch: the phase-curve loop of the reference (src/ARTES.f90:215-245,
+ * limb_emission) and the wavelength (wl_index, after artes_gpu_set_wavelengths: the spectrum loop :132-165)
+ * as ONE kernel launch: the phase-curve loop of the reference (src/ARTES.f90:215-245,
  * 73 calls of radiative_transfer, one per det_phi) pays the drain of a launch once instead of 73 times.
  * Launch k uses the photon ids launches[0].photon_id_base + k*n_photons + [0, n_photons), i.e. it equals
  * artes_gpu_run with that photon_id_base (the launches are statistically independent).

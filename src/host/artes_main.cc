@@ -452,19 +452,7 @@ int main(int argc, char** argv) {
     double photometry[11];
     const auto t_start = std::chrono::steady_clock::now();
 
-    // grid_initialize(2) + table upload for wavelength index l
-    auto prepare_wavelength = [&](int l) -> int {
-        depth = cell_depth(a, c, l);
-        MatrixTable mt;
-        std::string err;
-        if (!load_matrices(a, l, mt, err)) { std::fprintf(stderr, "ARTES: %s\n", err.c_str()); return 1; }
-        const double* cw = nullptr; const double* cdf = nullptr;
-        if (c.photon_source == 2) { thermal_tables(a, c, l, depth, R.ox, R.oy, R.oz, thermal); cw = thermal.cell_weight.data(); cdf = thermal.cdf.data(); }
-        if (artes_gpu_set_wavelength(ctx, a.k_sca.data() + (size_t)l * a.cells, a.k_abs.data() + (size_t)l * a.cells, mt.n_uniq, mt.uniq.data(),
-                                     mt.cell_to_uniq.data(), depth, cw, cdf) != 0) {
-            std::fprintf(stderr, "ARTES: set_wavelength: %s\n", artes_gpu_last_error(ctx));
-            return 1;
-        }
+    auto write_optical_depth = [&](int l) {
         if (c.imaging_broad || c.spectrum) {   // optical_depth.dat :2459-2491
             double tt = 0, ts = 0, ta = 0;
             for (int i = 0; i < a.nr; ++i) {
@@ -476,10 +464,8 @@ int main(int argc, char** argv) {
                         " # Wavelength [micron] - Total optical depth - Absorption optical depth - Scattering optical depth",
                         fnum(a.wavelengths[l] * 1.e6) + fnum(tt) + fnum(ta) + fnum(ts));
         }
-        return 0;
     };
 
-    // `call radiative_transfer`
     auto make_launch = [&](double det_phi) -> artes_launch_t {
         artes_launch_t Ln;
         std::memset(&Ln, 0, sizeof(Ln));
@@ -493,6 +479,63 @@ int main(int argc, char** argv) {
         Ln.x_max = R.x_max; Ln.y_max = R.x_max;
         return Ln;
     };
+
+    // grid_initialize(2) + table upload for wavelength index l
+    auto prepare_wavelength = [&](int l) -> int {
+        depth = cell_depth(a, c, l);
+        MatrixTable mt;
+        std::string err;
+        if (!load_matrices(a, l, mt, err)) { std::fprintf(stderr, "ARTES: %s\n", err.c_str()); return 1; }
+        const double* cw = nullptr; const double* cdf = nullptr;
+        if (c.photon_source == 2) { thermal_tables(a, c, l, depth, R.ox, R.oy, R.oz, thermal); cw = thermal.cell_weight.data(); cdf = thermal.cdf.data(); }
+        if (artes_gpu_set_wavelength(ctx, a.k_sca.data() + (size_t)l * a.cells, a.k_abs.data() + (size_t)l * a.cells, mt.n_uniq, mt.uniq.data(),
+                                     mt.cell_to_uniq.data(), depth, cw, cdf) != 0) {
+            std::fprintf(stderr, "ARTES: set_wavelength: %s\n", artes_gpu_last_error(ctx));
+            return 1;
+        }
+        write_optical_depth(l);
+        return 0;
+    };
+    // all wavelengths at once (star source): stacked tables for artes_gpu_set_wavelengths, one common matrix list
+    std::vector<int32_t> wl_depths;
+    auto prepare_all_wavelengths = [&]() -> int {
+        std::vector<double> uniq;
+        std::vector<int32_t> c2u((size_t)a.nl * a.cells);
+        int n_uniq = 0;
+        wl_depths.assign(a.nl, 0);
+        for (int l = 0; l < a.nl; ++l) {
+            wl_depths[l] = cell_depth(a, c, l);
+            MatrixTable mt;
+            std::string err;
+            if (!load_matrices(a, l, mt, err)) { std::fprintf(stderr, "ARTES: %s\n", err.c_str()); return 1; }
+            uniq.insert(uniq.end(), mt.uniq.begin(), mt.uniq.end());
+            for (size_t i = 0; i < (size_t)a.cells; ++i) c2u[(size_t)l * a.cells + i] = mt.cell_to_uniq[i] + n_uniq;
+            n_uniq += mt.n_uniq;
+            write_optical_depth(l);
+        }
+        if (artes_gpu_set_wavelengths(ctx, a.nl, a.k_sca.data(), a.k_abs.data(), n_uniq, uniq.data(), c2u.data(), wl_depths.data()) != 0) {
+            std::fprintf(stderr, "ARTES: set_wavelengths: %s\n", artes_gpu_last_error(ctx));
+            return 1;
+        }
+        return 0;
+    };
+    // the wl_count loop (:132-204) as ONE batched launch: launch l = wavelength l, photon ids l*packages + [0, packages)
+    std::vector<double> det_all, flux_all;
+    auto run_all_wavelengths = [&]() -> int {
+        std::vector<artes_launch_t> Ls;
+        for (int l = 0; l < a.nl; ++l) { artes_launch_t Ln = make_launch(c.det_phi); Ln.wl_index = l; Ls.push_back(Ln); }
+        det_all.assign((size_t)a.nl * 12 * npx, 0.0); flux_all.assign((size_t)2 * a.nl, 0.0);
+        artes_stats_t st;
+        std::fprintf(stdout, "Wavelengths: %d, one batched launch\n", a.nl); std::fflush(stdout);
+        if (artes_gpu_run_batch(ctx, Ls.data(), a.nl, det_all.data(), flux_all.data(), err_hist, &st) != 0) {
+            std::fprintf(stderr, "ARTES: artes_gpu_run_batch: %s\n", artes_gpu_last_error(ctx));
+            return 1;
+        }
+        for (int k = 0; k < ARTES_ERR_SLOTS; ++k) if (err_hist[k]) R.errors[k] += err_hist[k];
+        R.packets_done += (uint64_t)a.nl * packages; R.gpu_ms += st.kernel_ms + st.reduce_ms;
+        return 0;
+    };
+    // `call radiative_transfer`
     auto radiative_transfer = [&](double det_phi) -> int {
         const artes_launch_t Ln = make_launch(det_phi);
         artes_stats_t st;
@@ -608,7 +651,28 @@ int main(int argc, char** argv) {
 
     // ---- run :121-267
     int rc = 0;
-    if (c.spectrum) {
+    // star source without flow counters: every wavelength of a spectrum / broadband image in one batched launch
+    const bool batch_wl = (c.spectrum || c.imaging_broad) && c.photon_source == 1 && !c.flow_global && !c.flow_theta &&
+                          a.nl > 1 && a.nl <= ARTES_MAX_BATCH;
+    if (batch_wl) {
+        if (!(rc = prepare_all_wavelengths()) && !(rc = run_all_wavelengths())) {
+            for (int l = 0; l < a.nl; ++l) {
+                depth = wl_depths[l];
+                flux[0] = flux_all[2 * l]; flux[1] = flux_all[2 * l + 1];
+                if (c.spectrum) {
+                    std::copy(det_all.begin() + (size_t)l * 12 * npx, det_all.begin() + (size_t)(l + 1) * 12 * npx, det_sum.begin());
+                    finish_detector(det_sum, package_energy(R, a.wavelengths[l], c.det_phi, (double)packages, thermal.total));
+                    write_output(l, c.det_phi);
+                } else {
+                    for (size_t i = 0; i < det_acc.size(); ++i) det_acc[i] += det_all[(size_t)l * 12 * npx + i];
+                }
+            }
+            if (c.imaging_broad) {   // scaled with the LAST wavelength's package energy (:175-200, 959-975)
+                finish_detector(det_acc, package_energy(R, a.wavelengths[a.nl - 1], c.det_phi, (double)packages, thermal.total));
+                write_output(a.nl - 1, c.det_phi);
+            }
+        }
+    } else if (c.spectrum) {
         for (int l = 0; l < a.nl && !rc; ++l) {
             if ((rc = prepare_wavelength(l))) break;
             std::fprintf(stdout, "\rWavelength: %7.3f micron", a.wavelengths[l] * 1.e6); std::fflush(stdout);

@@ -457,6 +457,49 @@ def test_batched_launches_thermal_and_fallbacks(atmospheres, gpu_factory):
         g3.run_batch(bad)
 
 
+def _stacked_tables(atm, wls):
+    """Per-wavelength compact tables of `atm` stacked for artes_gpu_set_wavelengths: one common matrix list."""
+    uniq, c2u, off = [], [], 0
+    for l in wls:
+        uniq.append(atm.uniq[l]); c2u.append(np.asarray(atm.cell_to_uniq[l]) + off); off += atm.uniq[l].shape[0]
+    depths = [host.cell_depth(atm.rfront, atm.k_sca[l], atm.k_abs[l], atm.nr, atm.ntheta, atm.nphi, 1) for l in wls]
+    return (np.stack([atm.k_sca[l] for l in wls]), np.stack([atm.k_abs[l] for l in wls]), np.concatenate(uniq), np.stack(c2u), depths)
+
+
+@pytest.mark.parametrize("name,extra", [("c3_molecular", dict(nx=1, ny=1)), ("c5_scale", dict(nx=16, ny=16, surface_albedo=0.3))])
+def test_wavelength_batch_equals_single_launches(atmospheres, name, extra):
+    """artes_gpu_set_wavelengths + run_batch over wl_index (the spectrum loop :132-165 as one kernel): launch k equals the
+    single launch on the tables of wavelength k (set_wavelength) with photon_id_base = k * n_photons; a single launch
+    with wl_index = k on the stacked tables gives the same again."""
+    from artes_b200.lib import GpuTransport
+    atm = atmospheres(name)
+    wls = list(range(min(len(atm.wavelengths), 6)))
+    g = GpuTransport((0,))
+    g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+    ks, ka, uq, c2u, depths = _stacked_tables(atm, wls)
+    g.set_wavelengths(ks, ka, uq, c2u, depths)
+    xm = 1.3 * atm.rfront[-1]
+    P = 20000
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=33, n_photons=P, det_phi=math.radians(75.0), **extra)
+    Ls = [make_launch(wl_index=k, **kw) for k in range(len(wls))]
+    b = g.run_batch(Ls)
+    assert g.last_engine() == 2 and b["stats"]["reserved"] == 1
+    singles = [g.run(make_launch(wl_index=k, photon_id_base=k * P, **kw)) for k in range(len(wls))]
+    g1 = GpuTransport((0,))
+    g1.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+    assert len({round(float(r["det"][0, 0].sum()), 6) for r in singles}) > 1          # the wavelengths really differ
+    for k, l in enumerate(wls):
+        g1.set_wavelength(atm.k_sca[l], atm.k_abs[l], atm.uniq[l], atm.cell_to_uniq[l], depths[k])
+        a = g1.run(make_launch(photon_id_base=k * P, **kw))
+        for r in (singles[k], dict(det=b["det"][k], stats=None)):
+            np.testing.assert_array_equal(r["det"][2], a["det"][2])
+            np.testing.assert_allclose(r["det"][0], a["det"][0], rtol=1e-9, atol=1e-12 * np.abs(a["det"][0]).max())
+        assert singles[k]["stats"]["n_cell_face"] == a["stats"]["n_cell_face"]
+    assert b["stats"]["n_cell_face"] == sum(r["stats"]["n_cell_face"] for r in singles)
+    with pytest.raises(Exception):
+        g.run(make_launch(wl_index=len(wls), **kw))                                  # wavelength outside the tables
+
+
 def test_errors_are_reported_not_fatal(atmospheres):
     from artes_b200.lib import ArtesGpuError, GpuTransport
     atm = atmospheres("c1_template_rayleigh")
