@@ -109,11 +109,31 @@ def cpu_arm(atm, wl_kw, photons, seed, nthreads=0):
     xm = 1.3 * atm.rfront[-1]
     L = make_launch(n_photons=int(photons), x_max=xm, y_max=xm, seed=seed, nx=wl_kw["nx"], ny=wl_kw["ny"],
                     det_phi=math.radians(wl_kw["det_phi"]))
+    if nthreads <= 0:     # all host cores of this process, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+        nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     r = o.run(L, rng=RNG_MZ, nthreads=nthreads)
     return r["stats"]["kernel_ms"] * 1e-3, int(r["stats"]["reserved"]), r
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries write banners to file descriptor 1 (NCCL prints its version there when NCCL_DEBUG=VERSION and ignores
+    NCCL_DEBUG_FILE at that level): point fd 1 at stderr for the run and keep the real stdout for the one JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -164,7 +184,7 @@ def main():
                                  "sample": f"{sample} packets per step of the same workload; C++ restatement of ARTES.f90 "
                                            f"(g++ -O3 -fopenmp, gfortran unavailable), all host threads"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -290,7 +310,7 @@ def main():
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} packets of the same workload; C++ restatement of ARTES.f90 "
                                               f"(g++ -O3 -fopenmp; gfortran unavailable), all host threads"}
-        print(json.dumps(line))
+        emit(line)
     t.close()
     if world > 1:
         dist.destroy_process_group()
