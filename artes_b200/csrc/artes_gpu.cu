@@ -383,13 +383,16 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
     }
     std::vector<double> cdf_lin;
     ctx->thermal = (cell_weight && emis_cdf);
-    if (ctx->thermal) {  // reorder emissivity_cumulative into its (i,j,k) construction order (:2425-2427)
+    if (ctx->thermal) {  // reorder emissivity_cumulative into its (i,j,k) construction order (:2425-2427); wavelength l at l * cells
         const int nr = ctx->nr, nt = ctx->nt, np = ctx->np;
-        cdf_lin.resize((size_t)(nr - cell_depth) * nt * np);
-        size_t p = 0;
-        for (int i = cell_depth; i < nr; ++i)
-            for (int j = 0; j < nt; ++j)
-                for (int k = 0; k < np; ++k) cdf_lin[p++] = emis_cdf[i + nr * (j + nt * k)];
+        cdf_lin.assign((size_t)n, 0.0);
+        for (int l = 0; l < n_wl; ++l) {
+            size_t p = (size_t)l * ctx->cells;
+            const double* src = emis_cdf + (size_t)l * ctx->cells;
+            for (int i = cell_depths[l]; i < nr; ++i)
+                for (int j = 0; j < nt; ++j)
+                    for (int k = 0; k < np; ++k) cdf_lin[p++] = src[i + nr * (j + nt * k)];
+        }
     }
     cudaEvent_t e0, e1;
     for (auto& d : ctx->devs) {
@@ -438,8 +441,9 @@ int artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const doub
 }
 
 int artes_gpu_set_wavelengths(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, const double* k_abs, int n_uniq,
-                              const double* uniq_matrix, const int32_t* cell_to_uniq, const int32_t* cell_depths) {
-    return set_wavelength_tables(ctx, n_wl, k_sca, k_abs, n_uniq, uniq_matrix, cell_to_uniq, cell_depths, nullptr, nullptr);
+                              const double* uniq_matrix, const int32_t* cell_to_uniq, const int32_t* cell_depths,
+                              const double* cell_weight, const double* emis_cdf) {
+    return set_wavelength_tables(ctx, n_wl, k_sca, k_abs, n_uniq, uniq_matrix, cell_to_uniq, cell_depths, cell_weight, emis_cdf);
 }
 
 int artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, const double* dense,
@@ -499,6 +503,7 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
         if (L->wl_index > 0) {   // tables of wavelength wl_index out of the stacked set
             const size_t o = (size_t)L->wl_index * ctx->cells;
             a.T.kext += o; a.T.albedo += o; a.T.c2u += o; a.T.cellrec += 4 * o;
+            if (a.T.cell_weight) { a.T.cell_weight += o; a.T.emis_cdf += o; }
             a.T.cell_depth = ctx->wl_depth[L->wl_index];
         }
         fill_launch(*L, a.L);

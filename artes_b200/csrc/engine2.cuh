@@ -459,11 +459,14 @@ __device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A
     double xr[5], xq;
     unsigned nd = 0;
     draws(X, A, s, id, nd, 4, xr); nd += 4;
-    const int ncdf = (T.nr - T.cell_depth) * T.nt * T.np;
-    const double samp = xr[0] * __ldg(T.emis_cdf + ncdf - 1);
+    const int depth = depth_of(X, A, kb);
+    const size_t wl_off = (size_t)wl_of(X, A, kb) * T.cells;      // tables of the photon's wavelength (wavelength batches)
+    const double* ecdf = T.emis_cdf + wl_off;
+    const int ncdf = (T.nr - depth) * T.nt * T.np;
+    const double samp = xr[0] * __ldg(ecdf + ncdf - 1);
     int lo = -1, hi = ncdf - 1;      // first p with cdf[p] >= samp
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(T.emis_cdf + mid) >= samp) hi = mid; else lo = mid; }
-    const int c2 = hi % T.np, c1 = (hi / T.np) % T.nt, c0 = T.cell_depth + hi / (T.np * T.nt);
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(ecdf + mid) >= samp) hi = mid; else lo = mid; }
+    const int c2 = hi % T.np, c1 = (hi / T.np) % T.nt, c0 = depth + hi / (T.np * T.nt);
     double rsam = xr[1] * (X.r[c0 + 1] - X.r[c0]); rsam = X.r[c0] + rsam;
     const double tc0 = __ldg(T.tcos + c1), tc1 = __ldg(T.tcos + c1 + 1);
     double ct = xr[2] * (tc1 - tc0); ct = tc0 + ct;
@@ -505,7 +508,7 @@ __device__ __forceinline__ bool ev_emit_thermal(const Sh& X, const KernelArgs& A
     if (e) { err_count(A, e); ++C.n_err; X.D(F_S0, s) = 1.0; X.I(I_INFO, s) = K_DEAD; return true; }
     if (fabs(dz) >= 1.0) err_count(A, 54);
     X.D(F_DX, s) = dx; X.D(F_DY, s) = dy; X.D(F_DZ, s) = dz;
-    const double S0 = 1.0 * bias_weight / __ldg(T.cell_weight + c0 + T.nr * (c1 + T.nt * c2));
+    const double S0 = 1.0 * bias_weight / __ldg(T.cell_weight + wl_off + c0 + T.nr * (c1 + T.nt * c2));
     X.D(F_S0, s) = S0;
     atomicAdd(A.O.flux + 2 * kb, S0);
     // peel_thermal :4519-4598: walk to the detector, deposit e^-tau / 4 pi x I (weight applied by DEP)
@@ -1313,13 +1316,8 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     volatile int* vtail = X.tail;
     volatile int* vmisc = X.misc;
     const int starve = 8;                                        // take partial batches when fewer lanes than this march
-    // Soft warp specialisation: the last `we` warps of the block only run events (they never claim rays), the others
-    // only march and leave full batches to them (they still take batches when they have nothing to march).  Every
-    // warp then loops over a small part of the kernel's code -- the instruction cache, not the register file, is
-    // what the roles are for.  we = 0: every warp does both.
-    const int we = A.L.e2_trips > 0 ? min(A.L.e2_trips, NT / 32 - 1) : 0;
-    const bool event_warp = (int)(threadIdx.x >> 5) >= NT / 32 - we;
-    int idle = 0;
+    // (Measured and dropped: soft warp specialisation -- the last warps of a block only run events, the others only march --
+    // to shrink the code each warp loops over: 5-10 % slower on every workload, the event warps idle too often.)
 #ifdef E2_STATS
     unsigned long long st_pass = 0, st_act0 = 0, st_rdy0 = 0, st_it = 0, st_lane = 0, st_ev = 0, st_rdy = 0, st_evb = 0, st_evl = 0;
     bool rdy_empty = false;
@@ -1330,11 +1328,11 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     for (;;) {
         if (vmisc[0] >= NP) break;
         // ---- free lanes claim ready rays
-        const unsigned fm = event_warp ? 0u : __ballot_sync(FULL, M.slot < 0);
+        const unsigned fm = __ballot_sync(FULL, M.slot < 0);
 #ifdef E2_STATS
-        rdy_empty = event_warp;
+        rdy_empty = false;
 #else
-        bool rdy_empty = event_warp;
+        bool rdy_empty = false;
 #endif
         if (fm) {
             int base = 0, n = 0;
@@ -1396,10 +1394,10 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
         int l = -1;
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
-        if (fullm && (we == 0 || event_warp || nactive == 0))
+        if (fullm)
             l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
                 : (fullm & (1u << L_SURF)) ? L_SURF : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
-        else if (anym && rdy_empty && nactive < starve && (!event_warp || ++idle > 8))
+        else if (anym && rdy_empty && nactive < starve)
             l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_DEP)) ? L_DEP : (anym & (1u << L_H)) ? L_H
                 : (anym & (1u << L_SURF)) ? L_SURF : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
         if (l >= 0) {
@@ -1411,7 +1409,6 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             }
             base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
             if (n > 0) {
-                idle = 0;
                 const bool valid = lane < n;
                 int s = 0;
                 if (valid) s = ring_take(&X.Q(l, base + lane));

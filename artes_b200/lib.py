@@ -52,7 +52,7 @@ def load():
     lib.artes_gpu_set_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _dp,
                                        C.c_double, C.c_double, C.c_double]
     lib.artes_gpu_set_wavelength.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _dp, _ip, C.c_int, C.c_void_p, C.c_void_p]
-    lib.artes_gpu_set_wavelengths.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, _ip, _ip]
+    lib.artes_gpu_set_wavelengths.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, _ip, _ip, C.c_void_p, C.c_void_p]
     lib.artes_gpu_set_wavelength_dense.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p]
     lib.artes_gpu_run.argtypes = [C.c_void_p, C.POINTER(Launch), _dp, _dp, C.c_void_p, C.c_void_p, _up, C.POINTER(Stats)]
     lib.artes_gpu_run_async.argtypes = [C.c_void_p, C.POINTER(Launch)]
@@ -138,7 +138,7 @@ class GpuTransport:
         self._check(self.lib.artes_gpu_set_wavelength(self.h, k_sca, k_abs, uniq.shape[0], uniq, c2u, int(cell_depth), cw, ce),
                     "artes_gpu_set_wavelength")
 
-    def set_wavelengths(self, k_sca, k_abs, uniq, cell_to_uniq, cell_depths):
+    def set_wavelengths(self, k_sca, k_abs, uniq, cell_to_uniq, cell_depths, cell_weight=None, emis_cdf=None):
         """Tables of several wavelengths at once: k_sca, k_abs, cell_to_uniq are (n_wl, cells); uniq is ONE common list."""
         k_sca = np.ascontiguousarray(k_sca, dtype=np.float64)
         k_abs = np.ascontiguousarray(k_abs, dtype=np.float64)
@@ -148,7 +148,15 @@ class GpuTransport:
         n_wl = depths.size
         if not (k_sca.size == n_wl * self.cells and k_abs.size == n_wl * self.cells and c2u.size == n_wl * self.cells):
             raise ValueError("per-cell arrays do not match the grid x wavelengths")
-        self._check(self.lib.artes_gpu_set_wavelengths(self.h, n_wl, k_sca, k_abs, uniq.shape[0], uniq, c2u, depths),
+        cw = ce = None
+        if cell_weight is not None:      # thermal source: (n_wl, cells) each
+            a = np.ascontiguousarray(cell_weight, dtype=np.float64)
+            b = np.ascontiguousarray(emis_cdf, dtype=np.float64)
+            if a.size != n_wl * self.cells or b.size != n_wl * self.cells:
+                raise ValueError("thermal tables do not match the grid x wavelengths")
+            self._keep = [a, b]
+            cw, ce = a.ctypes.data, b.ctypes.data
+        self._check(self.lib.artes_gpu_set_wavelengths(self.h, n_wl, k_sca, k_abs, uniq.shape[0], uniq, c2u, depths, cw, ce),
                     "artes_gpu_set_wavelengths")
 
     def set_wavelength_dense(self, k_sca, k_abs, dense, cell_depth, cell_weight=None, emis_cdf=None):

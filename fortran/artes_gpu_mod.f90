@@ -84,13 +84,14 @@ module artes_gpu_mod
 
      ! all wl_count slices at once (k_sca, k_abs, cell_to_uniq: (cells, n_wl); one common list of matrix blocks); a launch
      ! then picks its wavelength with launch%wl_index and the wavelength loop (:132-204) can be one artes_gpu_run_batch
-     integer(c_int) function artes_gpu_set_wavelengths(ctx, n_wl, k_sca, k_abs, n_uniq, uniq_matrix, cell_to_uniq, cell_depths) &
-          bind(c, name="artes_gpu_set_wavelengths")
+     integer(c_int) function artes_gpu_set_wavelengths(ctx, n_wl, k_sca, k_abs, n_uniq, uniq_matrix, cell_to_uniq, cell_depths, &
+          cell_weight, emis_cdf) bind(c, name="artes_gpu_set_wavelengths")
        import :: c_ptr, c_int, c_double, c_int32_t
        type(c_ptr), value             :: ctx
        integer(c_int), value          :: n_wl, n_uniq
        real(c_double), intent(in)     :: k_sca(*), k_abs(*), uniq_matrix(*)
        integer(c_int32_t), intent(in) :: cell_to_uniq(*), cell_depths(*)
+       type(c_ptr), value             :: cell_weight, emis_cdf   ! (cells, n_wl) for the thermal source, else c_null_ptr
      end function artes_gpu_set_wavelengths
 
      ! the phase-curve loop (:215-245) as one launch: launches(n) differ in det_theta / det_phi / limb_emission only;

@@ -121,10 +121,11 @@ int  artes_gpu_set_wavelength(artes_gpu_ctx* ctx, const double* k_sca, const dou
 /* The tables of n_wl wavelengths at once (the wl_count loop of the spectrum / broadband modes, src/ARTES.f90:132-204):
  * k_sca, k_abs, cell_to_uniq are [n_wl][cells], cell_to_uniq indexes ONE common list of n_uniq matrix blocks,
  * cell_depths[n_wl].  A launch picks its wavelength with artes_launch_t::wl_index; launches of different wavelengths
- * can then share one batched kernel launch (artes_gpu_run_batch).  Star source only (no thermal tables). */
+ * can then share one batched kernel launch (artes_gpu_run_batch).  cell_weight, emis_cdf: [n_wl][cells] for the
+ * thermal source (as in artes_gpu_set_wavelength, per wavelength) or NULL. */
 int  artes_gpu_set_wavelengths(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, const double* k_abs,
                                int n_uniq, const double* uniq_matrix, const int32_t* cell_to_uniq,
-                               const int32_t* cell_depths);
+                               const int32_t* cell_depths, const double* cell_weight, const double* emis_cdf);
 
 /* Same, taking the reference's dense array for ONE wavelength exactly as it sits in memory
  * after ftgpvd (src/ARTES.f90:2196-2198): element (cell, e, a) at cell + cells*(e + 16*a),

@@ -498,8 +498,10 @@ int main(int argc, char** argv) {
     };
     // all wavelengths at once (star source): stacked tables for artes_gpu_set_wavelengths, one common matrix list
     std::vector<int32_t> wl_depths;
+    std::vector<Thermal> wl_thermal;     // thermal source: emissivity tables of every wavelength
     auto prepare_all_wavelengths = [&]() -> int {
-        std::vector<double> uniq;
+        std::vector<double> uniq, cw_all, cdf_all;
+        if (c.photon_source == 2) { wl_thermal.assign(a.nl, Thermal()); cw_all.resize((size_t)a.nl * a.cells); cdf_all.resize((size_t)a.nl * a.cells); }
         std::vector<int32_t> c2u((size_t)a.nl * a.cells);
         int n_uniq = 0;
         wl_depths.assign(a.nl, 0);
@@ -511,9 +513,15 @@ int main(int argc, char** argv) {
             uniq.insert(uniq.end(), mt.uniq.begin(), mt.uniq.end());
             for (size_t i = 0; i < (size_t)a.cells; ++i) c2u[(size_t)l * a.cells + i] = mt.cell_to_uniq[i] + n_uniq;
             n_uniq += mt.n_uniq;
+            if (c.photon_source == 2) {
+                thermal_tables(a, c, l, wl_depths[l], R.ox, R.oy, R.oz, wl_thermal[l]);
+                std::copy(wl_thermal[l].cell_weight.begin(), wl_thermal[l].cell_weight.end(), cw_all.begin() + (size_t)l * a.cells);
+                std::copy(wl_thermal[l].cdf.begin(), wl_thermal[l].cdf.end(), cdf_all.begin() + (size_t)l * a.cells);
+            }
             write_optical_depth(l);
         }
-        if (artes_gpu_set_wavelengths(ctx, a.nl, a.k_sca.data(), a.k_abs.data(), n_uniq, uniq.data(), c2u.data(), wl_depths.data()) != 0) {
+        if (artes_gpu_set_wavelengths(ctx, a.nl, a.k_sca.data(), a.k_abs.data(), n_uniq, uniq.data(), c2u.data(), wl_depths.data(),
+                                      c.photon_source == 2 ? cw_all.data() : nullptr, c.photon_source == 2 ? cdf_all.data() : nullptr) != 0) {
             std::fprintf(stderr, "ARTES: set_wavelengths: %s\n", artes_gpu_last_error(ctx));
             return 1;
         }
@@ -651,13 +659,13 @@ int main(int argc, char** argv) {
 
     // ---- run :121-267
     int rc = 0;
-    // star source without flow counters: every wavelength of a spectrum / broadband image in one batched launch
-    const bool batch_wl = (c.spectrum || c.imaging_broad) && c.photon_source == 1 && !c.flow_global && !c.flow_theta &&
-                          a.nl > 1 && a.nl <= ARTES_MAX_BATCH;
+    // without flow counters: every wavelength of a spectrum / broadband image in one batched launch
+    const bool batch_wl = (c.spectrum || c.imaging_broad) && !c.flow_global && !c.flow_theta && a.nl > 1 && a.nl <= ARTES_MAX_BATCH;
     if (batch_wl) {
         if (!(rc = prepare_all_wavelengths()) && !(rc = run_all_wavelengths())) {
             for (int l = 0; l < a.nl; ++l) {
                 depth = wl_depths[l];
+                if (c.photon_source == 2) thermal = wl_thermal[l];
                 flux[0] = flux_all[2 * l]; flux[1] = flux_all[2 * l + 1];
                 if (c.spectrum) {
                     std::copy(det_all.begin() + (size_t)l * 12 * npx, det_all.begin() + (size_t)(l + 1) * 12 * npx, det_sum.begin());
