@@ -82,6 +82,8 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // kernel start/stop, reduce stop, spare
     std::vector<void*> grid_allocs, wl_allocs;
+    std::vector<size_t> wl_caps;           // bytes of wl_allocs[i]: the wavelength tables are re-used when the next set fits
+    size_t wl_next = 0;
     DevTables T{};
     double* out_d = nullptr;               // [det 10*npx | flux 2 | flow4 4*cells | flow3 3*cells]
     size_t out_d_cap = 0;
@@ -135,6 +137,24 @@ int upload(artes_gpu_ctx* ctx, DeviceState& d, std::vector<void*>& pool, const T
     pool.push_back(p);
     if (n) CU(cudaMemcpyAsync(p, host, n * sizeof(Tp), cudaMemcpyHostToDevice, d.stream));
     *out = static_cast<const Tp*>(p);
+    return 0;
+}
+
+// upload into the next buffer of the wavelength pool, (re)allocating only when it is too small: a spectrum calls
+// set_wavelength once per wavelength with tables of the same size, and cudaMalloc / cudaFree cost more than the copy
+template <typename Tp>
+int upload_wl(artes_gpu_ctx* ctx, DeviceState& d, const Tp* host, size_t n, const Tp** out) {
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(Tp);
+    const size_t i = d.wl_next++;
+    if (i >= d.wl_allocs.size()) { d.wl_allocs.push_back(nullptr); d.wl_caps.push_back(0); }
+    if (d.wl_caps[i] < bytes) {
+        if (d.wl_allocs[i]) cudaFree(d.wl_allocs[i]);
+        d.wl_allocs[i] = nullptr; d.wl_caps[i] = 0;
+        CU(cudaMalloc(&d.wl_allocs[i], bytes));
+        d.wl_caps[i] = bytes;
+    }
+    if (n) CU(cudaMemcpyAsync(d.wl_allocs[i], host, n * sizeof(Tp), cudaMemcpyHostToDevice, d.stream));
+    *out = static_cast<const Tp*>(d.wl_allocs[i]);
     return 0;
 }
 
@@ -274,7 +294,7 @@ int artes_gpu_destroy(artes_gpu_ctx* ctx) {
         if (d.stream) cudaStreamSynchronize(d.stream);
         if (d.comm && g_nccl.ok) g_nccl.CommDestroy(d.comm);
         free_pool(d.grid_allocs);
-        free_pool(d.wl_allocs);
+        free_pool(d.wl_allocs); d.wl_caps.clear(); d.wl_next = 0;
         if (d.out_d) cudaFree(d.out_d);
         if (d.out_u) cudaFree(d.out_u);
         if (d.scratch) cudaFree(d.scratch);
@@ -398,24 +418,24 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
     for (auto& d : ctx->devs) {
         CU(cudaSetDevice(d.dev));
         CU(cudaStreamSynchronize(d.stream));
-        free_pool(d.wl_allocs);
+        d.wl_next = 0;
         DevTables& T = d.T;
         T.cell_depth = cell_depth; T.n_uniq = n_uniq;
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, d.stream));
         int rc = 0;
-        rc |= upload(ctx, d, d.wl_allocs, kext.data(), kext.size(), &T.kext);
-        rc |= upload(ctx, d, d.wl_allocs, cellrec.data(), cellrec.size(), &T.cellrec);
-        rc |= upload(ctx, d, d.wl_allocs, albedo.data(), albedo.size(), &T.albedo);
-        rc |= upload(ctx, d, d.wl_allocs, cell_to_uniq, (size_t)n, &T.c2u);
-        rc |= upload(ctx, d, d.wl_allocs, uniq_matrix, (size_t)n_uniq * 2880, &T.M);
-        rc |= upload(ctx, d, d.wl_allocs, mrow.data(), mrow.size(), &T.Mrow);
-        rc |= upload(ctx, d, d.wl_allocs, p1k.data(), p1k.size(), &T.p1k);
-        rc |= upload(ctx, d, d.wl_allocs, cdfP.data(), cdfP.size(), &T.cdfP);
+        rc |= upload_wl(ctx, d, kext.data(), kext.size(), &T.kext);
+        rc |= upload_wl(ctx, d, cellrec.data(), cellrec.size(), &T.cellrec);
+        rc |= upload_wl(ctx, d, albedo.data(), albedo.size(), &T.albedo);
+        rc |= upload_wl(ctx, d, cell_to_uniq, (size_t)n, &T.c2u);
+        rc |= upload_wl(ctx, d, uniq_matrix, (size_t)n_uniq * 2880, &T.M);
+        rc |= upload_wl(ctx, d, mrow.data(), mrow.size(), &T.Mrow);
+        rc |= upload_wl(ctx, d, p1k.data(), p1k.size(), &T.p1k);
+        rc |= upload_wl(ctx, d, cdfP.data(), cdfP.size(), &T.cdfP);
         T.cell_weight = nullptr; T.emis_cdf = nullptr;
         if (ctx->thermal) {
-            rc |= upload(ctx, d, d.wl_allocs, cell_weight, (size_t)n, &T.cell_weight);
-            rc |= upload(ctx, d, d.wl_allocs, cdf_lin.data(), cdf_lin.size(), &T.emis_cdf);
+            rc |= upload_wl(ctx, d, cell_weight, (size_t)n, &T.cell_weight);
+            rc |= upload_wl(ctx, d, cdf_lin.data(), cdf_lin.size(), &T.emis_cdf);
         }
         if (rc) return rc;
         CU(cudaEventRecord(e1, d.stream));

@@ -41,7 +41,7 @@ WORKLOADS = {
     "c1": ("c1_template_rayleigh", dict(nx=25, ny=25, det_phi=90.0), 4_000_000),
     "c2": ("c2_hg_deck", dict(nx=1, ny=1, det_phi=60.0), 8_000_000),
     "c3": ("c3_molecular", dict(nx=1, ny=1, det_phi=90.0), 8_000_000),
-    "c4": ("c4_mie_patches", dict(nx=64, ny=64, det_phi=60.0), 8_000_000),
+    "c4": ("c4_mie_patches", dict(nx=64, ny=64, det_phi=60.0), 10_000_000),   # BASELINE.json configs[3]: 1e7 packets
     "c5": ("c5_scale", dict(nx=64, ny=64, det_phi=60.0), 4_000_000),
 }
 
