@@ -78,14 +78,24 @@ class ClockSampler(threading.Thread):
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append([c.strip() for c in line.split(",")] + [time.perf_counter()])
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples of the timed region [t0, t1] (host clock at arrival); nvidia-smi needs a few hundred ms to deliver its
+        first line, so the sampler is started during the warm-up steps (same load) and a timed region shorter than the
+        sampling period falls back to the samples under load around it."""
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
+        window = "timed region"
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[-1] <= t1]
+            if inside:
+                self.rows = inside
+            else:
+                window = "warm-up + timed region (timed region shorter than the sampling period)"
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -96,7 +106,7 @@ class ClockSampler(threading.Thread):
                         reasons.add(name)
         busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_arm(atm, wl_kw, photons, seed, nthreads=0):
@@ -221,14 +231,15 @@ def main():
         L = t.launch_struct(P, seed=4, photon_id_base=base)
         return t.gpu.run(L)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(i)
         flush.zero_()
         torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
+    t_timed0 = time.perf_counter()
     dev_ms = 0.0
     kern_ms = 0.0
     agg = dict(n_emit=0, n_cell_face=0, n_scatter=0, n_peel=0)
@@ -243,7 +254,7 @@ def main():
         flush.zero_()                          # L2 flush, outside the event-timed region
         torch.cuda.synchronize()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_timed0, time.perf_counter()) if rank == 0 else None
 
     tm = torch.tensor([dev_ms, kern_ms], dtype=torch.float64, device="cuda")
     if world > 1:
