@@ -1326,7 +1326,9 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / 2 + 2));
 
     for (;;) {
-        if (vmisc[0] >= NP) break;
+        // every slot retired: the block is done.  One lane reads, so that the whole warp leaves together (a volatile read per lane
+        // is not warp-uniform by construction, and a warp that splits here would wait for its exited lanes in the ballots below)
+        if (__shfl_sync(FULL, (int)vmisc[0], 0) >= NP) break;
         // ---- free lanes claim ready rays
         const unsigned fm = __ballot_sync(FULL, M.slot < 0);
 #ifdef E2_STATS
