@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ARTES_GPU_ABI_VERSION 1
+#define ARTES_GPU_ABI_VERSION 2 /* 2: artes_gpu_run_batch, artes_gpu_set_wavelengths, artes_launch_t::wl_index (was reserved0) */
 
 /* arithmetic modes */
 #define ARTES_MODE_FAITHFUL 0 /* reference operation order, no FMA contraction, sequential 180-bin CDFs */
