@@ -538,6 +538,36 @@ def test_wavelength_batch_thermal_source(atmospheres):
     assert len({round(float(x[0]), 3) for x in b["flux"]}) > 1            # the wavelengths emit differently
 
 
+def test_two_device_context_equals_one_device(atmospheres, gpu_factory):
+    """One process, two GPUs in one context (`gpu:devices=2` of the driver; ncclCommInitAll + all-reduce inside the call):
+    same photon ids, so the images equal the single-device ones up to the order of the sums -- plain and batched."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from artes_b200.lib import GpuTransport
+    atm = atmospheres("c4_mie_patches")
+    g1, depth = gpu_factory(atm)
+    g2 = GpuTransport((0, 1))
+    g2.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+    g2.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth)
+    xm = 1.3 * atm.rfront[-1]
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=51, nx=16, ny=16)
+    L = make_launch(n_photons=60001, det_phi=math.radians(50.0), **kw)
+    a, b = g1.run(L), g2.run(L)
+    assert b["stats"]["reserved"] == 2                                   # one kernel per device
+    np.testing.assert_array_equal(b["det"][2], a["det"][2])
+    np.testing.assert_allclose(b["det"][0], a["det"][0], rtol=1e-9, atol=1e-12 * np.abs(a["det"][0]).max())
+    for k in ("n_emit", "n_cell_face", "n_scatter", "n_peel", "n_draws"):
+        assert a["stats"][k] == b["stats"][k], k
+    Ls = _phase_launches(5, 20001, [0.0, 45.0, 90.0, 135.0, 180.0], **kw)
+    ab, bb = g1.run_batch(Ls), g2.run_batch(Ls)
+    assert bb["stats"]["reserved"] == 2
+    np.testing.assert_array_equal(bb["det"][:, 2], ab["det"][:, 2])
+    np.testing.assert_allclose(bb["det"][:, 0], ab["det"][:, 0], rtol=1e-9, atol=1e-12 * np.abs(ab["det"][:, 0]).max())
+    np.testing.assert_allclose(bb["flux"], ab["flux"], rtol=1e-12)
+    g2.close()
+
+
 def test_errors_are_reported_not_fatal(atmospheres):
     from artes_b200.lib import ArtesGpuError, GpuTransport
     atm = atmospheres("c1_template_rayleigh")
