@@ -1370,6 +1370,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
 #pragma unroll 1
             for (int k = 0; k < inner; ++k) {
                 const bool go = M.slot >= 0 && out == O_NONE;
+                if (!__any_sync(FULL, go)) break;          // every ray of the warp has ended: no empty turns
 #ifdef E2_STATS
                 { const int na = __popc(__ballot_sync(FULL, go)); st_it += na > 0; st_lane += na; }
 #endif
