@@ -418,6 +418,33 @@ def test_batched_launches_equal_single_launches(atmospheres, gpu_factory, name, 
     assert b["stats"]["n_emit"] == len(phis) * P
 
 
+def test_batched_phase_curve_vs_oracle(atmospheres, oracle_factory, gpu_factory):
+    """Phase-curve points out of ONE batched launch against the oracle replaying the same Philox stream launch by launch
+    (the reference's loop :215-245 with limb-biased emission from 170 deg on): Stokes sums, counts and their errors."""
+    atm = atmospheres("c2_hg_deck")
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    P = 30000
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=77, nx=1, ny=1)
+    phis = [1e-5, 30.0, 90.0, 150.0, 172.5, 180.0 - 1e-5]
+    Ls = _phase_launches(len(phis), P, phis, **kw)
+    b = g.run_batch(Ls)
+    assert g.last_engine() == 2 and b["stats"]["reserved"] == 1
+    tot_cf = 0
+    for k, L in enumerate(Ls):
+        L.photon_id_base = k * P
+        a = o.run(L)
+        tot_cf += a["stats"]["n_cell_face"]
+        assert np.abs(a["det"][2] - b["det"][k][2]).sum() <= max(4, 2e-5 * a["det"][2].sum())
+        scale = np.abs(a["det"][0]).max()
+        np.testing.assert_allclose(b["det"][k][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=5e-5, atol=1e-7 * scale)
+        np.testing.assert_allclose(b["det"][k][1].sum(axis=(1, 2)), a["det"][1].sum(axis=(1, 2)), rtol=5e-4, atol=1e-9 * scale * scale)
+    assert abs(tot_cf - b["stats"]["n_cell_face"]) <= max(2, 2e-5 * tot_cf)
+    I = b["det"][:, 0, 0, 0, 0]
+    assert I[0] > I[2] > I[-1] > 0                                     # full phase brighter than quadrature brighter than new phase
+
+
 def test_batched_launches_thermal_and_fallbacks(atmospheres, gpu_factory):
     """Batch of thermal-source launches (per-launch emitted / emergent flux), and the sequential fall-back of the
     faithful mode with the same contract."""
