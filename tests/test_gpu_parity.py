@@ -529,6 +529,30 @@ def test_wavelength_batch_equals_single_launches(atmospheres, name, extra):
         g.run(make_launch(wl_index=len(wls), **kw))                                  # wavelength outside the tables
 
 
+def test_batched_spectrum_vs_oracle(atmospheres, oracle_factory):
+    """Spectrum points out of ONE batched launch over wl_index against the oracle run wavelength by wavelength on the
+    same Philox stream (the wl_count loop :132-165)."""
+    from artes_b200.lib import GpuTransport
+    atm = atmospheres("c3_molecular")
+    wls = [0, 11, 23, 31]
+    g = GpuTransport((0,))
+    g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+    ks, ka, uq, c2u, depths = _stacked_tables(atm, wls)
+    g.set_wavelengths(ks, ka, uq, c2u, depths)
+    xm = 1.3 * atm.rfront[-1]
+    P = 20000
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=88, n_photons=P, nx=1, ny=1)
+    b = g.run_batch([make_launch(wl_index=k, **kw) for k in range(len(wls))])
+    assert g.last_engine() == 2 and b["stats"]["reserved"] == 1
+    for k, l in enumerate(wls):
+        o, _ = oracle_factory(atm, l)
+        a = o.run(make_launch(photon_id_base=k * P, **kw))
+        assert np.abs(a["det"][2] - b["det"][k][2]).sum() <= max(4, 2e-5 * a["det"][2].sum())
+        scale = np.abs(a["det"][0]).max()
+        np.testing.assert_allclose(b["det"][k][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=5e-5, atol=1e-7 * scale)
+        np.testing.assert_allclose(b["det"][k][1].sum(axis=(1, 2)), a["det"][1].sum(axis=(1, 2)), rtol=5e-4, atol=1e-9 * scale * scale)
+
+
 def test_wavelength_batch_thermal_source(atmospheres):
     """Thermal-emission spectrum as one batched launch: per-wavelength emissivity CDF, cell weights and cell_depth."""
     from artes_b200.lib import GpuTransport
