@@ -675,7 +675,7 @@ int main(int argc, char** argv) {
                     for (size_t i = 0; i < det_acc.size(); ++i) det_acc[i] += det_all[(size_t)l * 12 * npx + i];
                 }
             }
-            if (c.imaging_broad) {   // scaled with the LAST wavelength's package energy (:175-200, 959-975)
+            if (!c.spectrum && c.imaging_broad) {   // (`if (spectrum) ... else if (imaging_broad)`, :132/167) scaled with the LAST wavelength's package energy (:175-200, 959-975)
                 finish_detector(det_acc, package_energy(R, a.wavelengths[a.nl - 1], c.det_phi, (double)packages, thermal.total));
                 write_output(a.nl - 1, c.det_phi);
             }

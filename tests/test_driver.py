@@ -128,3 +128,38 @@ def test_driver_phase_curve_and_spectrum(driver, tmp_path, atmospheres):
     np.testing.assert_allclose(sp[:, 0], atm3.wavelengths, rtol=1e-12)
     assert (sp[:, 1] > 0).all()
     assert _read_table(tmp_path / "output" / "sp" / "output" / "optical_depth.dat").shape == (4, 4)
+
+
+@pytest.mark.gpu
+def test_driver_broadband_image_is_the_batched_wavelength_sum(driver, tmp_path):
+    """imaging_broad (:167-204) through the driver: all wavelengths in one batched launch, the image is the sum over the
+    wavelengths scaled with the LAST wavelength's package energy -- compared with the same sum made launch by launch."""
+    atm3 = A.c3_molecular(nr=30, nl=4)
+    write_input(atm3, "c3b", root=str(tmp_path))
+    # the detector:type flags are only ever SET (:4457-4466) and `spectrum` is tested first (:132), so the template's
+    # spectrum line has to go from artes.in itself; a -k override would leave both flags on and run the spectrum
+    ain = tmp_path / "input" / "c3b" / "artes.in"
+    ain.write_text(ain.read_text().replace("detector:type=spectrum", "detector:type=imaging_broad"))
+    assert "detector:type=imaging_broad" in ain.read_text()
+    n = 40000
+    r = run(driver, tmp_path, "c3b", str(n), "-o", "bb", "-k", "detector:phi=60", "-k", "gpu:seed=9")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "one batched launch" in r.stdout
+    out = tmp_path / "output" / "bb" / "output"
+    stokes = fitsio.read_hdus(str(out / "stokes.fits"))[0][1]
+    assert _read_table(out / "optical_depth.dat").shape == (4, 4)
+    npix = stokes.shape[-1]                                   # the spectrum template of c3 has a 1 x 1 detector
+    p = host.Params(nx=npix, ny=npix, det_phi=math.radians(60.0))
+    t = host.Transport(atm3, p, mode=abi.MODE_FAST)
+    acc = None
+    for l in range(4):
+        t.set_wavelength(l)
+        res = t.gpu.run(t.launch_struct(n, seed=9, photon_id_base=l * n))
+        acc = res["det"].copy() if acc is None else acc + res["det"]
+    energy = host.package_energy(p, atm3.rfront, atm3.wavelengths[3] * 1e-6, n, t.emis_total)
+    det = host.detector_from_sums(acc, energy)
+    x_fov = 2.0 * math.atan(t.x_max / p.distance_planet) * 3600.0 * 180.0 / math.pi * 1000.0
+    img = det[0] * 1e-6 / (x_fov / stokes.shape[-1]) ** 2
+    assert stokes.shape == img.shape
+    np.testing.assert_allclose(stokes, img, rtol=1e-8, atol=1e-8 * np.abs(img).max())
+    t.close()
