@@ -42,7 +42,14 @@
 //
 // Scope: everything except flow_global and oblate planets (those run on the persistent-lane engine).  The GEN
 // instantiation compiles in the thermal source, the reflecting surface (SURF event) and the latitudinal flow
-// counters; the TRACE instantiation the injected-stream walk recorder.
+// counters; the TRACE instantiation the injected-stream walk recorder; the BATCH instantiation a launch index per photon
+// (artes_gpu_run_batch: the 73 launches of a phase curve or the wavelengths of a spectrum as ONE kernel -- the work
+// counter covers all launches, detector geometry / cell_depth / wavelength of each launch sit in a shared-memory table,
+// images and fluxes of the launches follow each other in the output buffer).
+//
+// Warp-uniform decisions.  Every condition the whole warp acts on (claim, take a batch, leave the kernel) is read by ONE
+// lane and broadcast, or is the result of a vote: a volatile shared-memory read per lane is not warp-uniform, and a warp
+// that splits on it dead-locks in the next *_sync.
 
 namespace e2 {
 
