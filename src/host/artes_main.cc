@@ -533,14 +533,19 @@ int main(int argc, char** argv) {
         std::vector<artes_launch_t> Ls;
         for (int l = 0; l < a.nl; ++l) { artes_launch_t Ln = make_launch(c.det_phi); Ln.wl_index = l; Ls.push_back(Ln); }
         det_all.assign((size_t)a.nl * 12 * npx, 0.0); flux_all.assign((size_t)2 * a.nl, 0.0);
-        artes_stats_t st;
-        std::fprintf(stdout, "Wavelengths: %d, one batched launch\n", a.nl); std::fflush(stdout);
-        if (artes_gpu_run_batch(ctx, Ls.data(), a.nl, det_all.data(), flux_all.data(), err_hist, &st) != 0) {
-            std::fprintf(stderr, "ARTES: artes_gpu_run_batch: %s\n", artes_gpu_last_error(ctx));
-            return 1;
+        const int n_chunks = (a.nl + ARTES_MAX_BATCH - 1) / ARTES_MAX_BATCH;
+        std::fprintf(stdout, "Wavelengths: %d, %s\n", a.nl, n_chunks == 1 ? "one batched launch" : "batched launches of 256 wavelengths"); std::fflush(stdout);
+        for (int l0 = 0; l0 < a.nl; l0 += ARTES_MAX_BATCH) {      // a batch holds at most ARTES_MAX_BATCH launches
+            const int nb = std::min(ARTES_MAX_BATCH, a.nl - l0);
+            for (int l = l0; l < l0 + nb; ++l) Ls[l].photon_id_base = (uint64_t)l0 * packages;   // launch l walks ids l*packages + [0, packages)
+            artes_stats_t st;
+            if (artes_gpu_run_batch(ctx, Ls.data() + l0, nb, det_all.data() + (size_t)l0 * 12 * npx, flux_all.data() + 2 * l0, err_hist, &st) != 0) {
+                std::fprintf(stderr, "ARTES: artes_gpu_run_batch: %s\n", artes_gpu_last_error(ctx));
+                return 1;
+            }
+            for (int k = 0; k < ARTES_ERR_SLOTS; ++k) if (err_hist[k]) R.errors[k] += err_hist[k];
+            R.packets_done += (uint64_t)nb * packages; R.gpu_ms += st.kernel_ms + st.reduce_ms;
         }
-        for (int k = 0; k < ARTES_ERR_SLOTS; ++k) if (err_hist[k]) R.errors[k] += err_hist[k];
-        R.packets_done += (uint64_t)a.nl * packages; R.gpu_ms += st.kernel_ms + st.reduce_ms;
         return 0;
     };
     // `call radiative_transfer`
@@ -660,7 +665,7 @@ int main(int argc, char** argv) {
     // ---- run :121-267
     int rc = 0;
     // without flow counters: every wavelength of a spectrum / broadband image in one batched launch
-    const bool batch_wl = (c.spectrum || c.imaging_broad) && !c.flow_global && !c.flow_theta && a.nl > 1 && a.nl <= ARTES_MAX_BATCH;
+    const bool batch_wl = (c.spectrum || c.imaging_broad) && !c.flow_global && !c.flow_theta && a.nl > 1;
     if (batch_wl) {
         if (!(rc = prepare_all_wavelengths()) && !(rc = run_all_wavelengths())) {
             for (int l = 0; l < a.nl; ++l) {

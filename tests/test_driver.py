@@ -163,3 +163,23 @@ def test_driver_broadband_image_is_the_batched_wavelength_sum(driver, tmp_path):
     assert stokes.shape == img.shape
     np.testing.assert_allclose(stokes, img, rtol=1e-8, atol=1e-8 * np.abs(img).max())
     t.close()
+
+
+@pytest.mark.gpu
+def test_driver_spectrum_with_more_wavelengths_than_one_batch(driver, tmp_path):
+    """300 wavelengths: the driver splits the wavelength loop into batches of ARTES_MAX_BATCH = 256 launches."""
+    atm = A.c3_molecular(nr=12, nl=300)
+    write_input(atm, "c3w", root=str(tmp_path))
+    r = run(driver, tmp_path, "c3w", "3000", "-o", "sp", "-k", "gpu:seed=3")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "batched launches of 256 wavelengths" in r.stdout
+    sp = _read_table(tmp_path / "output" / "sp" / "output" / "spectrum.dat")
+    assert sp.shape == (300, 5)
+    np.testing.assert_allclose(sp[:, 0], atm.wavelengths, rtol=1e-12)
+    assert (sp[:, 1] > 0).all()
+    # wavelength 299 through the second batch equals the single launch with its photon-id range
+    t = host.Transport(atm, host.Params(nx=1, ny=1), mode=abi.MODE_FAST)
+    t.set_wavelength(299)
+    det, phot, _ = t.radiative_transfer(3000, seed=3, photon_id_base=299 * 3000)
+    np.testing.assert_allclose(sp[299, 1:5], 1e-6 * det[0, :, 0, 0], rtol=1e-8, atol=1e-30)
+    t.close()
