@@ -1,7 +1,7 @@
 """ctypes mirror of include/artes_gpu.h (struct layouts and constants)."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODE_FAITHFUL = 0
 MODE_FAST = 1
 ERR_SLOTS = 64

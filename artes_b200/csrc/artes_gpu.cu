@@ -34,11 +34,14 @@ cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cuda
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
 bool engine2_supports(const KernelArgs& a);
+bool engine2_batch_fits(const KernelArgs& a, int n);
 size_t engine2_scratch_bytes(int sm_count);
 cudaError_t launch_transport2(const KernelArgs& a, int sm_count, cudaStream_t stream);
 cudaError_t launch_transport2_trace(const KernelArgs& a, int sm_count, cudaStream_t stream);
 }  // namespace fast
 cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
+cudaError_t ingest_dedup_device(const double* src, size_t cells, size_t plane_stride, cudaStream_t stream,
+                                std::vector<double>& uniq, std::vector<int32_t>& c2u, int* exact, double* copy_ms, double* kernel_ms);
 }  // namespace artes
 
 using namespace artes;
@@ -174,11 +177,18 @@ int ensure_outputs(artes_gpu_ctx* ctx, DeviceState& d, size_t n_d) {
     return 0;
 }
 
+// Scheduling parameters are compile-time choices of the product library; the environment overrides exist only in a
+// tuning build (make TUNING=1 -> -DARTES_TUNING), which tools/gpu_tune.py uses for the measurements quoted in DESIGN.md.
 int env_int(const char* name, int dflt) {
+#ifdef ARTES_TUNING
     const char* v = std::getenv(name);
     if (!v || !*v) return dflt;
     int x = std::atoi(v);
     return x < 1 ? 1 : (x > 4096 ? 4096 : x);
+#else
+    (void)name;
+    return dflt;
+#endif
 }
 
 // LaunchArgs from the ABI struct: host-evaluated detector / star geometry (src/ARTES.f90:495-502, 1080-1109, 4628, 4871)
@@ -235,6 +245,18 @@ int check_launch(artes_gpu_ctx* ctx, const artes_launch_t* L) {
     if (L->nx < 1 || L->ny < 1 || !(L->x_max > 0.0) || !(L->y_max > 0.0)) return fail(ctx, -1, "bad detector geometry");
     if (L->wl_index < 0 || L->wl_index >= ctx->n_wl) return fail(ctx, -1, "wl_index outside the tables of set_wavelength(s)");
     return 0;
+}
+
+// device tables of wavelength wl_index out of the stacked set of artes_gpu_set_wavelengths (one place for run, trace, ...)
+DevTables tables_of(const artes_gpu_ctx* c, const DeviceState& d, int wl_index) {
+    DevTables T = d.T;
+    if (wl_index > 0) {
+        const size_t o = (size_t)wl_index * c->cells;
+        T.kext += o; T.albedo += o; T.c2u += o; T.cellrec += 4 * o;
+        if (T.cell_weight) { T.cell_weight += o; T.emis_cdf += o; }
+    }
+    T.cell_depth = c->wl_depth[wl_index];
+    return T;
 }
 
 size_t out_doubles(const artes_gpu_ctx* c, const artes_launch_t& L) {
@@ -373,6 +395,8 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
                           const double* cell_weight, const double* emis_cdf) {
     if (!ctx) return fail(nullptr, -1, "null context");
     if (!ctx->have_grid) return fail(ctx, -1, "set_grid first");
+    if (ctx->pending) return fail(ctx, -1, "a launch is pending (call artes_gpu_wait before changing the tables)");
+    ctx->have_wl = false;      // a failed upload leaves the context without wavelength tables (a later run is refused) instead of half-updated ones
     if (!k_sca || !k_abs || !uniq_matrix || !cell_to_uniq || n_uniq < 1 || n_wl < 1 || !cell_depths) return fail(ctx, -1, "bad wavelength tables");
     for (int l = 0; l < n_wl; ++l) if (cell_depths[l] < 0 || cell_depths[l] >= ctx->nr) return fail(ctx, -1, "cell_depth out of range");
     const int cell_depth = cell_depths[0];
@@ -414,14 +438,13 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
                     for (int k = 0; k < np; ++k) cdf_lin[p++] = src[i + nr * (j + nt * k)];
         }
     }
-    cudaEvent_t e0, e1;
     for (auto& d : ctx->devs) {
         CU(cudaSetDevice(d.dev));
         CU(cudaStreamSynchronize(d.stream));
         d.wl_next = 0;
         DevTables& T = d.T;
         T.cell_depth = cell_depth; T.n_uniq = n_uniq;
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        const cudaEvent_t e0 = d.ev[0], e1 = d.ev[1];      // the device's own timing events (no launch is pending: the stream was just drained)
         CU(cudaEventRecord(e0, d.stream));
         int rc = 0;
         rc |= upload_wl(ctx, d, kext.data(), kext.size(), &T.kext);
@@ -443,7 +466,6 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         ctx->last_h2d_ms = ms;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
     ctx->have_wl = true;
     ctx->n_wl = n_wl;
@@ -466,23 +488,19 @@ int artes_gpu_set_wavelengths(artes_gpu_ctx* ctx, int n_wl, const double* k_sca,
     return set_wavelength_tables(ctx, n_wl, k_sca, k_abs, n_uniq, uniq_matrix, cell_to_uniq, cell_depths, cell_weight, emis_cdf);
 }
 
-int artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, const double* dense,
-                                   int cell_depth, const double* cell_weight, const double* emis_cdf) {
-    if (!ctx) return fail(nullptr, -1, "null context");
-    if (!ctx->have_grid) return fail(ctx, -1, "set_grid first");
-    if (!dense) return fail(ctx, -1, "null matrix");
-    // De-duplicate the per-cell 180x16 blocks: python/atmosphere.py:351-372 mixes a handful of species,
-    // so the dense HDU (cells x 23 040 B) holds few distinct blocks.
+// host de-duplication of the per-cell 180x16 blocks of one wavelength; element (cell, e, a) at cell + plane_stride*(e + 16*a)
+static int dedup_host(artes_gpu_ctx* ctx, const double* dense, size_t plane_stride, std::vector<double>& uniq, std::vector<int32_t>& c2u) {
+    // python/atmosphere.py:351-372 mixes a handful of species, so the dense HDU (cells x 23 040 B) holds few distinct blocks.
     const size_t n = (size_t)ctx->cells;
     std::vector<double> block(2880);
-    std::vector<double> uniq;
-    std::vector<int32_t> c2u(n);
+    c2u.assign(n, 0);
+    uniq.clear();
     std::unordered_multimap<uint64_t, int> seen;
     for (size_t cidx = 0; cidx < n; ++cidx) {
         uint64_t h = 1469598103934665603ull;
         for (int a = 0; a < 180; ++a)
             for (int e = 0; e < 16; ++e) {
-                double v = dense[cidx + n * ((size_t)e + 16 * (size_t)a)];
+                double v = dense[cidx + plane_stride * ((size_t)e + 16 * (size_t)a)];
                 block[a * 16 + e] = v;
                 uint64_t bits; std::memcpy(&bits, &v, 8);
                 h ^= bits; h *= 1099511628211ull;
@@ -498,7 +516,44 @@ int artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, cons
         }
         c2u[cidx] = found;
     }
+    return 0;
+}
+
+// the same on the device (ingest.cu); falls back to the host path if a hash group fails the element-wise check
+static int dedup_device(artes_gpu_ctx* ctx, const double* dense, size_t plane_stride, std::vector<double>& uniq, std::vector<int32_t>& c2u) {
+    DeviceState& d = ctx->devs[0];
+    CU(cudaSetDevice(d.dev));
+    int exact = 1;
+    cudaError_t e = ingest_dedup_device(dense, (size_t)ctx->cells, plane_stride, d.stream, uniq, c2u, &exact, nullptr, nullptr);
+    if (e != cudaSuccess) return fail(ctx, -2, std::string("matrix ingest: ") + cudaGetErrorString(e));
+    if (!exact) return dedup_host(ctx, dense, plane_stride, uniq, c2u);
+    return 0;
+}
+
+int artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs, const double* dense,
+                                   int cell_depth, const double* cell_weight, const double* emis_cdf) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!ctx->have_grid) return fail(ctx, -1, "set_grid first");
+    if (!dense) return fail(ctx, -1, "null matrix");
+    std::vector<double> uniq;
+    std::vector<int32_t> c2u;
+    const int rc = dedup_device(ctx, dense, (size_t)ctx->cells, uniq, c2u);
+    if (rc) return rc;
     return artes_gpu_set_wavelength(ctx, k_sca, k_abs, (int)(uniq.size() / 2880), uniq.data(), c2u.data(), cell_depth, cell_weight, emis_cdf);
+}
+
+int artes_gpu_set_wavelength_dense_wl(artes_gpu_ctx* ctx, int n_wl, int wl_index, const double* k_sca_all, const double* k_abs_all,
+                                      const double* matrix_all, int cell_depth, const double* cell_weight, const double* emis_cdf) {
+    if (!ctx) return fail(nullptr, -1, "null context");
+    if (!ctx->have_grid) return fail(ctx, -1, "set_grid first");
+    if (!k_sca_all || !k_abs_all || !matrix_all || n_wl < 1 || wl_index < 0 || wl_index >= n_wl) return fail(ctx, -1, "bad dense wavelength arguments");
+    const size_t cells = (size_t)ctx->cells;
+    std::vector<double> uniq;
+    std::vector<int32_t> c2u;
+    int rc = dedup_device(ctx, matrix_all + cells * (size_t)wl_index, cells * (size_t)n_wl, uniq, c2u);
+    if (rc) return rc;
+    return artes_gpu_set_wavelength(ctx, k_sca_all + cells * (size_t)wl_index, k_abs_all + cells * (size_t)wl_index, (int)(uniq.size() / 2880),
+                                    uniq.data(), c2u.data(), cell_depth, cell_weight, emis_cdf);
 }
 
 int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
@@ -519,13 +574,7 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
         CU(cudaMemsetAsync(d.out_d, 0, n_d * sizeof(double), d.stream));
         CU(cudaMemsetAsync(d.out_u, 0, (ARTES_ERR_SLOTS + 16) * sizeof(unsigned long long), d.stream));
         KernelArgs a{};
-        a.T = d.T;
-        if (L->wl_index > 0) {   // tables of wavelength wl_index out of the stacked set
-            const size_t o = (size_t)L->wl_index * ctx->cells;
-            a.T.kext += o; a.T.albedo += o; a.T.c2u += o; a.T.cellrec += 4 * o;
-            if (a.T.cell_weight) { a.T.cell_weight += o; a.T.emis_cdf += o; }
-            a.T.cell_depth = ctx->wl_depth[L->wl_index];
-        }
+        a.T = tables_of(ctx, d, L->wl_index);
         fill_launch(*L, a.L);
         a.L.n_photons = per + ((unsigned long long)i < rem ? 1 : 0);
         a.L.id_base = L->photon_id_base + off;
@@ -663,7 +712,8 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         KernelArgs a{};
         a.T = ctx->devs[0].T;
         fill_launch(L0, a.L);
-        batched = fast::engine2_supports(a);
+        // a launch table too large for shared memory or an image stack whose pixel offsets leave 32 bits: one launch after the other
+        batched = fast::engine2_supports(a) && fast::engine2_batch_fits(a, n);
     }
     if (stats) std::memset(stats, 0, sizeof(*stats));
     if (err_hist) std::memset(err_hist, 0, ARTES_ERR_SLOTS * sizeof(uint64_t));
@@ -841,7 +891,7 @@ int artes_gpu_trace(artes_gpu_ctx* ctx, const artes_launch_t* L, const double* x
     if (fstate) CU(cudaMalloc(&d_f, n * 8 * sizeof(double)));
     CU(cudaMemcpyAsync(d_xi, xi, (size_t)n * max_draws * sizeof(double), cudaMemcpyHostToDevice, d.stream));
     KernelArgs a{};
-    a.T = d.T;
+    a.T = tables_of(ctx, d, L->wl_index);      // the trace hook walks the tables of the launch's wavelength, like artes_gpu_run
     fill_launch(*L, a.L);
     a.L.n_photons = n;
     a.O.det = d.out_d; a.O.flux = d.out_d + 10 * npx; a.O.flow4 = d.out_d + 10 * npx + 2;

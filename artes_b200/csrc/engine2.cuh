@@ -1167,6 +1167,7 @@ __device__ __forceinline__ void flush_counters(const KernelArgs& A, const Cnt& C
     }
 }
 
+#ifdef ARTES_TUNING   // comparison kernel, tuning builds only (make TUNING=1)
 // ---------------------------------------------------------------------------------------------------
 // kernel A: bulk-synchronous rounds (marcher phase of `trips` trips | barrier | event phase | barrier)
 // ---------------------------------------------------------------------------------------------------
@@ -1288,6 +1289,8 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
     }
     flush_counters(A, C);
 }
+
+#endif  // ARTES_TUNING
 
 // ---------------------------------------------------------------------------------------------------
 // kernel B: asynchronous.  No block barrier after set-up: every warp loops  claim rays -> one trip -> push

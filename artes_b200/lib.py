@@ -22,7 +22,7 @@ _up = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 # every symbol include/artes_gpu.h declares
 SYMBOLS = [
     "artes_gpu_create", "artes_gpu_destroy", "artes_gpu_last_error", "artes_gpu_abi_version",
-    "artes_gpu_set_grid", "artes_gpu_set_wavelength", "artes_gpu_set_wavelength_dense",
+    "artes_gpu_set_grid", "artes_gpu_set_wavelength", "artes_gpu_set_wavelength_dense", "artes_gpu_set_wavelength_dense_wl",
     "artes_gpu_set_wavelengths", "artes_gpu_run", "artes_gpu_run_batch", "artes_gpu_run_async", "artes_gpu_wait", "artes_gpu_nccl_unique_id",
     "artes_gpu_nccl_init_rank", "artes_gpu_trace", "artes_gpu_cell_face", "artes_gpu_device_info",
     "artes_gpu_fma_peak", "artes_gpu_last_engine",
@@ -54,6 +54,7 @@ def load():
     lib.artes_gpu_set_wavelength.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _dp, _ip, C.c_int, C.c_void_p, C.c_void_p]
     lib.artes_gpu_set_wavelengths.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, _ip, _ip, C.c_void_p, C.c_void_p]
     lib.artes_gpu_set_wavelength_dense.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p]
+    lib.artes_gpu_set_wavelength_dense_wl.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p]
     lib.artes_gpu_run.argtypes = [C.c_void_p, C.POINTER(Launch), _dp, _dp, C.c_void_p, C.c_void_p, _up, C.POINTER(Stats)]
     lib.artes_gpu_run_async.argtypes = [C.c_void_p, C.POINTER(Launch)]
     lib.artes_gpu_run_batch.argtypes = [C.c_void_p, C.POINTER(Launch), C.c_int, _dp, _dp, _up, C.POINTER(Stats)]
@@ -174,6 +175,25 @@ class GpuTransport:
             cw, ce = a.ctypes.data, b.ctypes.data
         self._check(self.lib.artes_gpu_set_wavelength_dense(self.h, k_sca, k_abs, dense, int(cell_depth), cw, ce),
                     "artes_gpu_set_wavelength_dense")
+
+    def set_wavelength_dense_wl(self, k_sca_all, k_abs_all, dense_all, wl_index, cell_depth, cell_weight=None, emis_cdf=None):
+        """The reference's whole arrays: k_sca_all / k_abs_all numpy (n_wl, nphi, ntheta, nr), dense_all numpy
+        (180, 16, n_wl, nphi, ntheta, nr) = HDUs 6-8 of atmosphere.fits; wavelength wl_index is picked with strides and
+        de-duplicated on the device."""
+        k_sca_all = np.ascontiguousarray(k_sca_all, dtype=np.float64)
+        k_abs_all = np.ascontiguousarray(k_abs_all, dtype=np.float64)
+        dense_all = np.ascontiguousarray(dense_all, dtype=np.float64)
+        n_wl = k_sca_all.size // self.cells
+        if dense_all.size != self.cells * 2880 * n_wl or k_abs_all.size != k_sca_all.size:
+            raise ValueError("dense arrays do not match the grid x wavelengths")
+        cw = ce = None
+        if cell_weight is not None:
+            a = np.ascontiguousarray(cell_weight, dtype=np.float64)
+            b = np.ascontiguousarray(emis_cdf, dtype=np.float64)
+            self._keep = [a, b]
+            cw, ce = a.ctypes.data, b.ctypes.data
+        self._check(self.lib.artes_gpu_set_wavelength_dense_wl(self.h, n_wl, int(wl_index), k_sca_all, k_abs_all, dense_all,
+                                                               int(cell_depth), cw, ce), "artes_gpu_set_wavelength_dense_wl")
 
     # ---- the hot path ----------------------------------------------------------------------
     def _outputs(self, launch, flows):

@@ -71,6 +71,18 @@ module artes_gpu_mod
        type(c_ptr), value         :: cell_weight, emis_cdf      ! c_null_ptr unless photon_source = 2
      end function artes_gpu_set_wavelength_dense
 
+     ! the same for wavelength wl_index (0-based) out of the WHOLE program-scope arrays cell_scattering_opacity(:,:,:,:),
+     ! cell_absorption_opacity(:,:,:,:), cell_scatter_matrix(:,:,:,:,:,:) -- no slice, no copy-in temporary; the
+     ! matrix blocks are de-duplicated on the GPU
+     integer(c_int) function artes_gpu_set_wavelength_dense_wl(ctx, n_wl, wl_index, k_sca_all, k_abs_all, matrix_all, cell_depth, &
+          cell_weight, emis_cdf) bind(c, name="artes_gpu_set_wavelength_dense_wl")
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value         :: ctx
+       integer(c_int), value      :: n_wl, wl_index, cell_depth
+       real(c_double), intent(in) :: k_sca_all(*), k_abs_all(*), matrix_all(*)
+       type(c_ptr), value         :: cell_weight, emis_cdf      ! c_null_ptr unless photon_source = 2
+     end function artes_gpu_set_wavelength_dense_wl
+
      ! det_sum(nx,ny,4,3) = the thread sum of detector_thread (:959-975, before the package_energy scaling)
      integer(c_int) function artes_gpu_run(ctx, launch, det_sum, flux, flow4, flow3, err_hist, stats) bind(c, name="artes_gpu_run")
        import :: c_ptr, c_int, c_double, c_int64_t, artes_launch_t, artes_stats_t

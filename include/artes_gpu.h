@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ARTES_GPU_ABI_VERSION 2 /* 2: artes_gpu_run_batch, artes_gpu_set_wavelengths, artes_launch_t::wl_index (was reserved0) */
+#define ARTES_GPU_ABI_VERSION 3 /* 2: artes_gpu_run_batch, artes_gpu_set_wavelengths, artes_launch_t::wl_index (was reserved0); 3: artes_gpu_set_wavelength_dense_wl, artes_gpu_run_multi */
 
 /* arithmetic modes */
 #define ARTES_MODE_FAITHFUL 0 /* reference operation order, no FMA contraction, sequential 180-bin CDFs */
@@ -133,6 +133,17 @@ int  artes_gpu_set_wavelengths(artes_gpu_ctx* ctx, int n_wl, const double* k_sca
 int  artes_gpu_set_wavelength_dense(artes_gpu_ctx* ctx, const double* k_sca, const double* k_abs,
                                     const double* matrix_dense, int cell_depth,
                                     const double* cell_weight, const double* emis_cdf);
+
+/* Same for wavelength `wl_index` (0-based) out of the reference's WHOLE program-scope arrays, without a slice copy:
+ * cell_scattering_opacity / cell_absorption_opacity (cells, n_wl) (src/ARTES.f90:64-65) and
+ * cell_scatter_matrix(cells, n_wl, 16, 180) (:69): element (cell, wl, e, a) at cell + cells*(wl + n_wl*(e + 16*a)).
+ * (A Fortran slice cell_scatter_matrix(:,:,:,wl,:,:) is not contiguous for n_wl > 1; passing it to the entry above makes
+ * the compiler copy 16.6 GB at the scale configuration.)  The 2880 (e, a) planes of the wavelength are streamed to the
+ * device, hashed per cell there and de-duplicated (get_atmosphere :2054-2235 reads them cell by cell on one core);
+ * equal hashes are verified element by element on the device before two cells share a block. */
+int  artes_gpu_set_wavelength_dense_wl(artes_gpu_ctx* ctx, int n_wl, int wl_index, const double* k_sca_all,
+                                       const double* k_abs_all, const double* matrix_all, int cell_depth,
+                                       const double* cell_weight, const double* emis_cdf);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 

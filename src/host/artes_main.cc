@@ -466,10 +466,15 @@ int main(int argc, char** argv) {
         }
     };
 
+    // Every call of radiative_transfer walks its own photon-id range (call k: k*packages + [0, packages)): the reference
+    // carries its generator state from one call to the next (:4197-4230), so successive launches are statistically
+    // independent; replaying ids 0.. for every wavelength / phase angle would correlate them and understate error.fits.
+    // The batched paths number their launches the same way, so both paths produce the same streams.
+    uint64_t launch_index = 0;
     auto make_launch = [&](double det_phi) -> artes_launch_t {
         artes_launch_t Ln;
         std::memset(&Ln, 0, sizeof(Ln));
-        Ln.struct_size = sizeof(Ln); Ln.mode = c.mode; Ln.n_photons = packages; Ln.photon_id_base = 0; Ln.seed = c.seed;
+        Ln.struct_size = sizeof(Ln); Ln.mode = c.mode; Ln.n_photons = packages; Ln.photon_id_base = launch_index * packages; Ln.seed = c.seed;
         Ln.photon_source = c.photon_source; Ln.photon_scattering = c.photon_scattering ? 1 : 0; Ln.photon_emission = c.photon_emission;
         Ln.stellar_direction = c.stellar_direction ? 1 : 0;
         Ln.limb_emission = (c.phase_curve && det_phi * 180.0 / PI >= 170.0) ? 1 : 0;
@@ -551,6 +556,7 @@ int main(int argc, char** argv) {
     // `call radiative_transfer`
     auto radiative_transfer = [&](double det_phi) -> int {
         const artes_launch_t Ln = make_launch(det_phi);
+        ++launch_index;
         artes_stats_t st;
         if (artes_gpu_run(ctx, &Ln, det_sum.data(), flux, flow4.empty() ? nullptr : flow4.data(), flow3.empty() ? nullptr : flow3.data(),
                           err_hist, &st) != 0) {

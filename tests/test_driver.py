@@ -183,3 +183,29 @@ def test_driver_spectrum_with_more_wavelengths_than_one_batch(driver, tmp_path):
     det, phot, _ = t.radiative_transfer(3000, seed=3, photon_id_base=299 * 3000)
     np.testing.assert_allclose(sp[299, 1:5], 1e-6 * det[0, :, 0, 0], rtol=1e-8, atol=1e-30)
     t.close()
+
+
+@pytest.mark.gpu
+def test_driver_flow_on_and_flow_off_paths_walk_the_same_streams(driver, tmp_path):
+    """With a flow counter on, the wavelength loop runs launch by launch (artes_gpu_run) instead of as one batched launch.
+    Every call walks its own photon-id range (call k: k*packages + [0, packages)) on both paths, so the spectra are equal
+    and the launches are statistically independent (the reference carries its generator state from call to call)."""
+    atm = A.c3_molecular(nr=30, nl=4)
+    write_input(atm, "c3f", root=str(tmp_path))
+    n = 30000
+    r0 = run(driver, tmp_path, "c3f", str(n), "-o", "batched", "-k", "gpu:seed=11")
+    r1 = run(driver, tmp_path, "c3f", str(n), "-o", "looped", "-k", "gpu:seed=11", "-k", "output:flow_latitudinal=on")
+    assert r0.returncode == 0 and r1.returncode == 0, r0.stderr + r1.stderr
+    assert "one batched launch" in r0.stdout and "one batched launch" not in r1.stdout
+    a = _read_table(tmp_path / "output" / "batched" / "output" / "spectrum.dat")
+    b = _read_table(tmp_path / "output" / "looped" / "output" / "spectrum.dat")
+    np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-30)
+    # ... and launch l is the single launch with photon_id_base = l*packages, not a replay of ids 0..packages
+    t = host.Transport(atm, host.Params(nx=1, ny=1), mode=abi.MODE_FAST)
+    t.set_wavelength(2)
+    det, _, _ = t.radiative_transfer(n, seed=11, photon_id_base=2 * n)
+    np.testing.assert_allclose(b[2, 1:5], 1e-6 * det[0, :, 0, 0], rtol=1e-8, atol=1e-30)
+    det0, _, _ = t.radiative_transfer(n, seed=11, photon_id_base=0)
+    assert abs(1e-6 * det0[0, 0, 0, 0] - b[2, 1]) > 1e-6 * abs(b[2, 1])
+    assert (tmp_path / "output" / "looped" / "output" / "flow_latitudinal.fits").exists()
+    t.close()
