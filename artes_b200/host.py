@@ -213,7 +213,23 @@ class Transport:
         self.gpu.set_wavelength(a.k_sca[l], a.k_abs[l], a.uniq[l], a.cell_to_uniq[l], self.depth, cw, cdf)
         self.wl_index = l
 
-    def launch_struct(self, packages, seed=1, photon_id_base=0, det_phi=None):
+    def set_all_wavelengths(self, wls=None):
+        """grid_initialize(2) for every wavelength of the atmosphere, uploaded as ONE stacked table set
+        (artes_gpu_set_wavelengths): launches then pick their wavelength with `wl_index` and the wavelength loop of
+        `run` (:132-204) can be one batched launch.  Star source only (the thermal tables stay per wavelength here)."""
+        a, p = self.atm, self.p
+        wls = list(range(len(a.wavelengths))) if wls is None else list(wls)
+        uniq, c2u, off = [], [], 0
+        for l in wls:
+            uniq.append(a.uniq[l]); c2u.append(np.asarray(a.cell_to_uniq[l]) + off); off += a.uniq[l].shape[0]
+        self.depths = [cell_depth(a.rfront, a.k_sca[l], a.k_abs[l], a.nr, a.ntheta, a.nphi, p.photon_source, p.ring) for l in wls]
+        self.gpu.set_wavelengths(np.stack([a.k_sca[l] for l in wls]), np.stack([a.k_abs[l] for l in wls]), np.concatenate(uniq),
+                                 np.stack(c2u), self.depths)
+        self.wl_index = wls[0]
+        self.depth = self.depths[0]
+        return wls
+
+    def launch_struct(self, packages, seed=1, photon_id_base=0, det_phi=None, wl_index=0):
         p = self.p
         det_phi = p.det_phi if det_phi is None else det_phi
         return abi.make_launch(
@@ -224,7 +240,7 @@ class Transport:
             flow_global=int(p.flow_global), flow_theta=int(p.flow_theta), nx=p.nx, ny=p.ny, fstop=p.fstop,
             photon_minimum=p.photon_minimum, photon_bias=p.photon_bias, surface_albedo=p.surface_albedo,
             theta_star=p.theta_star, phi_star=p.phi_star, det_theta=p.det_theta, det_phi=det_phi,
-            x_max=self.x_max, y_max=self.x_max)
+            x_max=self.x_max, y_max=self.x_max, wl_index=int(wl_index))
 
     def radiative_transfer(self, packages, seed=1, total_packages=None, photon_id_base=0, det_phi=None):
         """`call radiative_transfer`: returns detector(l, stokes, iy, ix), photometry(11), raw result."""

@@ -42,7 +42,8 @@ WORKLOADS = {
     "c2": ("c2_hg_deck", dict(nx=1, ny=1, det_phi=60.0), 8_000_000),
     "c3": ("c3_molecular", dict(nx=1, ny=1, det_phi=90.0), 8_000_000),
     "c4": ("c4_mie_patches", dict(nx=64, ny=64, det_phi=60.0), 10_000_000),   # BASELINE.json configs[3]: 1e7 packets
-    "c5": ("c5_scale", dict(nx=64, ny=64, det_phi=60.0), 4_000_000),
+    # BASELINE.json configs[4]: multi-wavelength; one step = ONE batched launch of all wavelengths x --photons packets each
+    "c5": ("c5_scale", dict(nx=64, ny=64, det_phi=60.0, multi_wl=True), 1_000_000),
 }
 
 # algorithmic FP64 flop per event
@@ -164,21 +165,28 @@ def main():
 
     from tools import atmospheres as A
     builder, wl_kw, default_p = WORKLOADS[args.workload]
+    wl_kw = dict(wl_kw)
+    multi_wl = bool(wl_kw.pop("multi_wl", False)) and args.batch <= 1 and args.mode == "fast"
     atm = getattr(A, builder)()
     P = int(args.photons) if args.photons else (1_000_000 if args.batch > 1 else default_p)
-    NB = args.batch if args.batch > 1 else 1
+    NB = args.batch if args.batch > 1 else (len(atm.wavelengths) if multi_wl else 1)
     config = {"workload": f"{args.workload}:{builder} nr={atm.nr} ntheta={atm.ntheta} nphi={atm.nphi} "
                           f"image={wl_kw['nx']}x{wl_kw['ny']} det_phi={wl_kw['det_phi']}deg star source, peel-off on",
               "photons_per_gpu_per_step": P * NB, "mode": args.mode, "parallelism": f"photon-id sharding x{world}",
               "l2": "tables (<= few MB) are L2-resident by design; 256 MiB memset flushes L2 between steps"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
-    if NB > 1:
+    if multi_wl:
+        config["batch"] = f"{NB} wavelengths x {P} packets per step as one kernel (artes_gpu_set_wavelengths + artes_gpu_run_batch)"
+    elif NB > 1:
         config["batch"] = f"{NB} launches x {P} packets per step as one kernel (artes_gpu_run_batch), det_phi = 0..180 deg"
     if args.impl == "reference":
         if rank != 0:
             return
         sample = int(min(args.cpu_sample, P))
+        # the CPU arm times a bounded sample of the workload (a rate: photons are independent), not the GPU arm's step size
+        config["photons_per_step_timed_on_cpu"] = sample
+        config["cpu_note"] = "photons_per_gpu_per_step is the GPU arm's step; this arm times photons_per_step_timed_on_cpu packets per step of the same workload" + (" (wavelength 0)" if multi_wl else "")
         for _ in range(min(args.warmup, 1)):
             cpu_arm(atm, wl_kw, max(sample // 10, 1000), 1)
         tot = 0.0
@@ -211,11 +219,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     mode = abi.MODE_FAST if args.mode == "fast" else abi.MODE_FAITHFUL
-    params = host.Params(nx=wl_kw["nx"], ny=wl_kw["ny"], det_phi=math.radians(wl_kw["det_phi"]), phase_curve=NB > 1)
+    params = host.Params(nx=wl_kw["nx"], ny=wl_kw["ny"], det_phi=math.radians(wl_kw["det_phi"]), phase_curve=(NB > 1 and not multi_wl))
     t = host.Transport(atm, params, devices=(local_rank,), mode=mode)
     if world > 1:  # NCCL communicator of the library itself: the id travels through torch.distributed
         adist.init_library_comm(t.gpu, dist, rank, world)
-    t.set_wavelength(0)
+
+    def load_tables(tr):
+        if multi_wl:
+            tr.set_all_wavelengths()
+        else:
+            tr.set_wavelength(0)
+
+    load_tables(t)
     peaks = t.gpu.fma_peak()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -224,10 +239,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def launches(tr, packets, base):
+        if multi_wl:
+            return [tr.launch_struct(packets, seed=4, photon_id_base=base, wl_index=k) for k in range(NB)]
+        return [tr.launch_struct(packets, seed=4, photon_id_base=base, det_phi=math.pi * k / (NB - 1)) for k in range(NB)]
+
     def step(i):
         base = adist.step_base(i, world, rank, P * NB)   # disjoint photon ids for every step and rank
         if NB > 1:
-            return t.gpu.run_batch([t.launch_struct(P, seed=4, photon_id_base=base, det_phi=math.pi * k / (NB - 1)) for k in range(NB)])
+            return t.gpu.run_batch(launches(t, P, base))
         L = t.launch_struct(P, seed=4, photon_id_base=base)
         return t.gpu.run(L)
 
@@ -242,12 +262,14 @@ def main():
     t_timed0 = time.perf_counter()
     dev_ms = 0.0
     kern_ms = 0.0
+    red_ms = 0.0
     agg = dict(n_emit=0, n_cell_face=0, n_scatter=0, n_peel=0)
     last = None
     for i in range(args.steps):
         res = step(args.warmup + i)
         dev_ms += res["stats"]["kernel_ms"] + res["stats"]["reduce_ms"]
         kern_ms += res["stats"]["kernel_ms"]
+        red_ms += res["stats"]["reduce_ms"]
         for k in agg:
             agg[k] += res["stats"][k]          # already summed over ranks by the NCCL reduce
         last = res
@@ -256,20 +278,28 @@ def main():
     barrier()
     clocks = sampler.stop(t_timed0, time.perf_counter()) if rank == 0 else None
 
-    tm = torch.tensor([dev_ms, kern_ms], dtype=torch.float64, device="cuda")
+    # max over ranks of the device times; min / max of the kernel time and of the reduce wait per rank say where a scaling loss sits:
+    # reduce_ms is the time from this rank's kernel end to the end of the all-reduce, i.e. mostly the wait for the slowest rank
+    tm = torch.tensor([dev_ms, kern_ms, red_ms], dtype=torch.float64, device="cuda")
+    tmin = tm.clone()
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     dev_ms, kern_ms = float(tm[0]), float(tm[1])
+    rank_times = {"kernel_ms_per_step_min": float(tmin[1]) / args.steps, "kernel_ms_per_step_max": float(tm[1]) / args.steps,
+                  "reduce_ms_per_step_min": float(tmin[2]) / args.steps, "reduce_ms_per_step_max": float(tm[2]) / args.steps,
+                  "note": "per rank: kernel = transport kernel; reduce = from the rank's kernel end to the end of the NCCL all-reduce (includes the wait for the slowest rank)"}
     value = world * args.steps * P * NB / (dev_ms * 1e-3)
 
     # ---- end to end through the public call with host buffers: upload tables, launch, download image
     a = atm
-    h2d = (a.k_sca[0].nbytes + a.k_abs[0].nbytes + a.uniq[0].nbytes + a.cell_to_uniq[0].nbytes)
+    nwl_up = len(a.wavelengths) if multi_wl else 1
+    h2d = sum(a.k_sca[l].nbytes + a.k_abs[l].nbytes + a.uniq[l].nbytes + a.cell_to_uniq[l].nbytes for l in range(nwl_up))
     d2h = ((10 * wl_kw["nx"] * wl_kw["ny"] + 2) * NB + (7 * a.cells if NB == 1 else 0)) * 8 + (64 + 8) * 8
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        t.set_wavelength(0)
+        load_tables(t)
         step(args.warmup + args.steps + i)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -277,6 +307,45 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * args.steps * P * NB / float(te[0])
+
+    # ---- shard check: the N-rank result of one small step against the same photon ids walked by rank 0 alone.
+    # Philox is keyed by the global photon id, so the two differ only in the order of the floating-point sums:
+    # the count planes must be identical, the Stokes sums equal to rounding.
+    pc = int(min(P, 200_000))
+    shards = world if world > 1 else 2          # one GPU: two half-launches on the same device added on the host
+    base0 = 1 << 40                             # ids no timed step used
+    if world > 1:
+        rs = t.gpu.run_batch(launches(t, pc, base0 + rank * pc * NB)) if NB > 1 else t.gpu.run(t.launch_struct(pc, seed=4, photon_id_base=base0 + rank * pc))
+        det_n = rs["det"]
+    else:
+        det_n = None
+        for r_ in range(shards):
+            rs = t.gpu.run_batch(launches(t, pc, base0 + r_ * pc * NB)) if NB > 1 else t.gpu.run(t.launch_struct(pc, seed=4, photon_id_base=base0 + r_ * pc))
+            det_n = rs["det"].copy() if det_n is None else det_n + rs["det"]
+    shard_check = None
+    if rank == 0:
+        t1 = host.Transport(atm, params, devices=(local_rank,), mode=mode)      # a second context WITHOUT the communicator
+        load_tables(t1)
+        if NB > 1:       # launch k of shard r walks ids base0 + r*pc*NB + k*pc + [0, pc): the same ids, shard by shard
+            det_1 = None
+            for r_ in range(shards):
+                rr = t1.gpu.run_batch(launches(t1, pc, base0 + r_ * pc * NB))
+                det_1 = rr["det"].copy() if det_1 is None else det_1 + rr["det"]
+        else:
+            det_1 = t1.gpu.run(t1.launch_struct(pc * shards, seed=4, photon_id_base=base0))["det"]
+        t1.close()
+        cn, c1 = det_n[..., 2, :, :, :], det_1[..., 2, :, :, :]
+        sn, s1 = det_n[..., 0, :, :, :], det_1[..., 0, :, :, :]
+        scale = float(np.abs(s1).max()) or 1.0
+        shard_check = {"photons": pc * shards * NB, "shards": shards,
+                       "counts_sum_sharded": float(cn.sum()), "counts_sum_single": float(c1.sum()),
+                       "count_planes_identical": bool(np.array_equal(cn, c1)),
+                       "sum_I_sharded": float(sn[..., 0, :, :].sum()), "sum_I_single": float(s1[..., 0, :, :].sum()),
+                       "sum_I_rel_diff": float(abs(sn[..., 0, :, :].sum() - s1[..., 0, :, :].sum()) / abs(s1[..., 0, :, :].sum())),
+                       "max_pixel_diff_over_max": float(np.abs(sn - s1).max() / scale),
+                       "ok": bool(np.array_equal(cn, c1) and np.abs(sn - s1).max() <= 1e-9 * scale),
+                       "what": "one small step: photon ids sharded over the ranks and NCCL-summed (one GPU: two half-launches) vs the "
+                               "same ids in one launch on rank 0, a context without communicator"}
 
     if rank == 0:
         fl, by = algorithmic(agg, atm, args.mode)          # all ranks, all timed steps
@@ -302,6 +371,8 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": args.steps * world,
                 "clocks": clocks,
+                "rank_times": rank_times,
+                "shard_check": shard_check,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
                              "frac": achieved / peaks["fp64_tflops"], "traffic": traffic,
                              "note": "dominant kernel transport3_kernel (ray/event engine, asynchronous scheduling); this path is FP64-issue / latency bound, "
@@ -316,7 +387,7 @@ def main():
                                  "note": "algorithmic bytes are table reads served by L1/L2; HBM is not the bound of this path"},
                 "events_per_packet": {k: v / (world * args.steps * P * NB) for k, v in agg.items()}}
         if world == 1 and not args.no_cpu_baseline:
-            sample = int(args.cpu_sample)
+            sample = int(min(args.cpu_sample, P))
             dt, cores, _ = cpu_arm(atm, wl_kw, sample, 7)
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} packets of the same workload; C++ restatement of ARTES.f90 "
