@@ -143,7 +143,7 @@ def detector_from_sums(det_sum, energy):
     """:959-975: detector(:,:,:,1) = sum*E, (:,:,:,2) = sum*E^2, (:,:,:,3) = counts."""
     det = np.array(det_sum, copy=True)
     det[0] *= energy
-    det[1] *= energy * energy
+    det[1] = det[1] * energy * energy      # the reference's order: (sum * E) * E
     return det
 
 

@@ -1076,6 +1076,86 @@ int artes_ref_cell_depth(const artes_ref_ctx* c, int photon_source, int ring) {
     return cell_max;
 }
 
+// ---- host side of radiative_transfer / write_output (the product's driver and Python mirror are checked against these) ----
+
+// planck_function :1350-1367 (wavelength in metres)
+double artes_ref_planck(double temperature, double wavelength, int photon_source) {
+    const double pi = 4.0 * std::atan(1.0);
+    const double k_b = 1.3806488e-23, hh = 6.62606957e-34, cc = 2.99792458e8;      // :9-16
+    if (photon_source == 1) return (2.0 * pi * hh * cc * cc / std::pow(wavelength, 5.0)) / (std::exp(hh * cc / (wavelength * k_b * temperature)) - 1.0);
+    return (2.0 * hh * cc * cc / std::pow(wavelength, 5.0)) / (std::exp(hh * cc / (wavelength * k_b * temperature)) - 1.0);
+}
+
+// photon_package :2509-2539
+double artes_ref_package_energy(int photon_source, double t_star, double r_star, double orbit, double distance_planet, double rfront_nr,
+                                double wavelength, double packages, int phase_curve, double det_phi, double emissivity_total) {
+    const double pi = 4.0 * std::atan(1.0);
+    double package_energy = 0.0;
+    if (photon_source == 1) {
+        const double planck_flux = artes_ref_planck(t_star, wavelength, 1);
+        package_energy = pi * planck_flux * rfront_nr * rfront_nr * r_star * r_star / (orbit * orbit * distance_planet * distance_planet * packages);
+        if (phase_curve && det_phi * 180.0 / pi >= 170.0)
+            package_energy = package_energy * (pi * r_star * r_star - 0.9 * 0.9 * pi * r_star * r_star) / (pi * r_star * r_star);
+    } else if (photon_source == 2) {
+        package_energy = emissivity_total / (distance_planet * distance_planet * packages);
+    }
+    return package_energy;
+}
+
+// The tail of radiative_transfer :957-1004: detector(nx,ny,4,3) from the thread sum and the package energy, photometry(11).
+// det_sum / detector are in the reference's array order (ix fastest, then iy, Stokes index, l); sums run in that order like
+// the Fortran intrinsic.  photometry(10) = PI / I is 0 for I = 0 (the reference divides by zero there).
+void artes_ref_finish_detector(int nx, int ny, const double* det_sum, double package_energy, double* detector, double* photometry) {
+    const size_t npx = (size_t)nx * ny;
+    for (int l = 1; l <= 3; ++l)
+        for (int k = 0; k < 4; ++k)
+            for (size_t i = 0; i < npx; ++i) {
+                const size_t x = ((size_t)(l - 1) * 4 + k) * npx + i;
+                if (l == 1) detector[x] = det_sum[x] * package_energy;
+                else if (l == 2) detector[x] = det_sum[x] * package_energy * package_energy;
+                else detector[x] = det_sum[x];
+            }
+    auto plane_sum = [&](int k, int l) { double t = 0.0; const double* p = detector + ((size_t)(l - 1) * 4 + k) * npx; for (size_t i = 0; i < npx; ++i) t = t + p[i]; return t; };
+    for (int i = 0; i < 11; ++i) photometry[i] = 0.0;
+    photometry[0] = plane_sum(0, 1); photometry[2] = plane_sum(1, 1); photometry[4] = plane_sum(2, 1); photometry[6] = plane_sum(3, 1);
+    photometry[8] = std::sqrt(plane_sum(1, 1) * plane_sum(1, 1) + plane_sum(2, 1) * plane_sum(2, 1));
+    photometry[9] = photometry[0] != 0.0 ? photometry[8] / photometry[0] : 0.0;
+    for (int i = 1; i <= 4; ++i) {
+        if (plane_sum(i - 1, 3) > 0.0) {
+            const double dummy = (plane_sum(i - 1, 2) / plane_sum(i - 1, 3)) - std::pow(plane_sum(i - 1, 1) / plane_sum(i - 1, 3), 2);
+            if (dummy > 0.0) photometry[i * 2 - 1] = std::sqrt(dummy) * std::sqrt(plane_sum(i - 1, 3));
+        }
+    }
+    if (photometry[2] * photometry[2] + photometry[4] * photometry[4] > 0.0) {
+        const double dpi = std::sqrt((std::pow(photometry[2] * photometry[3], 2) + std::pow(photometry[4] * photometry[5], 2)) /
+                                     (2.0 * (photometry[2] * photometry[2] + photometry[4] * photometry[4])));
+        photometry[10] = photometry[9] * std::sqrt(std::pow(dpi / photometry[8], 2) + std::pow(photometry[1] / photometry[0], 2));
+    }
+}
+
+// write_output :3481-3519: error(nx,ny,5) = sigma of I, Q, U, V and of the degree of polarisation.  A pixel with Q = U = 0
+// reads `pol` and `dpol` uninitialised / stale in the reference (:3506-3516); here its sigma_P is 0.
+void artes_ref_stokes_error(int nx, int ny, const double* detector, double* error) {
+    const size_t npx = (size_t)nx * ny;
+    auto det = [&](size_t i, int k, int l) { return detector[((size_t)(l - 1) * 4 + (k - 1)) * npx + i]; };
+    for (size_t i = 0; i < 5 * npx; ++i) error[i] = 0.0;
+    for (int k = 1; k <= 4; ++k)
+        for (size_t i = 0; i < npx; ++i)
+            if (det(i, k, 3) > 0.0) {
+                const double dummy = (det(i, k, 2) / det(i, k, 3)) - std::pow(det(i, k, 1) / det(i, k, 3), 2);
+                if (dummy > 0.0) error[(size_t)(k - 1) * npx + i] = std::sqrt(dummy) * std::sqrt(det(i, k, 3));
+            }
+    for (size_t i = 0; i < npx; ++i) {
+        const double q = det(i, 2, 1), u = det(i, 3, 1);
+        if (q * q + u * u > 0.0) {
+            const double pol = std::sqrt(q * q + u * u);
+            const double dpol = std::sqrt((std::pow(q * error[npx + i], 2) + std::pow(u * error[2 * npx + i], 2)) / (2.0 * (q * q + u * u)));
+            if (det(i, 1, 1) > 0.0)
+                error[4 * npx + i] = (pol / det(i, 1, 1)) * std::sqrt(std::pow(dpol / pol, 2) + std::pow(error[i] / det(i, 1, 1), 2));
+        }
+    }
+}
+
 int artes_ref_run(artes_ref_ctx* c, const artes_launch_t* L, int rng_kind, int nthreads, int emulate_stat,
                   double* det_sum, double* flux, double* flow4, double* flow3, uint64_t* err_hist,
                   artes_stats_t* stats) {

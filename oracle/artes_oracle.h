@@ -68,6 +68,16 @@ void artes_ref_mz_uniforms(int32_t s1, int n, double* out);
  * restated here so that tests can check the product's host helpers. */
 int artes_ref_cell_depth(const artes_ref_ctx* c, int photon_source, int ring);
 
+/* Host side of the path, restated for checks of the driver / Python mirror:
+ * planck_function (:1350-1367), photon_package (:2509-2539), the tail of radiative_transfer (:957-1004: detector from the
+ * thread sums, photometry(11)) and the error planes of write_output (:3481-3519).  Arrays in the reference's order
+ * detector(nx,ny,4,3), error(nx,ny,5). */
+double artes_ref_planck(double temperature, double wavelength, int photon_source);
+double artes_ref_package_energy(int photon_source, double t_star, double r_star, double orbit, double distance_planet, double rfront_nr,
+                                double wavelength, double packages, int phase_curve, double det_phi, double emissivity_total);
+void artes_ref_finish_detector(int nx, int ny, const double* det_sum, double package_energy, double* detector, double* photometry);
+void artes_ref_stokes_error(int nx, int ny, const double* detector, double* error);
+
 #ifdef __cplusplus
 }
 #endif

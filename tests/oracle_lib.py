@@ -39,6 +39,12 @@ def _load():
     lib.artes_ref_philox_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_int, _dp]
     lib.artes_ref_mz_uniforms.argtypes = [C.c_int32, C.c_int, _dp]
     lib.artes_ref_cell_depth.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.artes_ref_planck.restype = C.c_double
+    lib.artes_ref_planck.argtypes = [C.c_double, C.c_double, C.c_int]
+    lib.artes_ref_package_energy.restype = C.c_double
+    lib.artes_ref_package_energy.argtypes = [C.c_int] + [C.c_double] * 7 + [C.c_int, C.c_double, C.c_double]
+    lib.artes_ref_finish_detector.argtypes = [C.c_int, C.c_int, _dp, C.c_double, _dp, _dp]
+    lib.artes_ref_stokes_error.argtypes = [C.c_int, C.c_int, _dp, _dp]
     return lib
 
 
@@ -179,3 +185,28 @@ def mz_uniforms(s1, n):
     out = np.zeros(n)
     lib().artes_ref_mz_uniforms(s1, n, out)
     return out
+
+
+def package_energy(p, rfront, wavelength, packages, emis_total=0.0):
+    """photon_package :2509-2539 for an artes_b200.host.Params-like object (wavelength in metres)."""
+    return lib().artes_ref_package_energy(int(p.photon_source), p.t_star, p.r_star, p.orbit, p.distance_planet, float(rfront[-1]),
+                                          float(wavelength), float(packages), int(p.phase_curve), float(p.det_phi), float(emis_total))
+
+
+def finish_detector(det_sum, energy):
+    """:957-1004 on det_sum[l, stokes, iy, ix] -> detector (same layout), photometry(11)."""
+    d = np.ascontiguousarray(det_sum, dtype=np.float64)
+    ny, nx = d.shape[-2:]
+    out = np.zeros_like(d)
+    phot = np.zeros(11)
+    lib().artes_ref_finish_detector(nx, ny, d.ravel(), float(energy), out.reshape(-1), phot)
+    return out, phot
+
+
+def stokes_error(detector):
+    """write_output :3481-3519 -> error[5, iy, ix]."""
+    d = np.ascontiguousarray(detector, dtype=np.float64)
+    ny, nx = d.shape[-2:]
+    err = np.zeros((5, ny, nx))
+    lib().artes_ref_stokes_error(nx, ny, d.ravel(), err.reshape(-1))
+    return err

@@ -107,6 +107,15 @@ def test_driver_imaging_mono_matches_python_host(driver, tmp_path, atmospheres):
     tab = _read_table(out / "output" / "photometry.dat")
     np.testing.assert_allclose(tab[0, 0], atm.wavelengths[0], rtol=1e-12)
     np.testing.assert_allclose(tab[0, 1:9], 1e-6 * phot[:8], rtol=1e-9, atol=1e-30)
+    # ... and against the ORACLE's restatement of photon_package (:2509-2539), the reduction / photometry tail (:957-1004)
+    # and the error planes (:3481-3519), fed with the raw GPU sums of the same launch
+    import oracle_lib
+    raw = t.gpu.run(t.launch_struct(n, seed=5))["det"]
+    e_ref = oracle_lib.package_energy(p, atm.rfront, atm.wavelengths[0] * 1e-6, n)
+    det_ref, phot_ref = oracle_lib.finish_detector(raw, e_ref)
+    np.testing.assert_allclose(stokes, det_ref[0] * 1e-6 / (x_fov / 25) ** 2, rtol=1e-9, atol=1e-12 * np.abs(img).max())
+    np.testing.assert_allclose(err, oracle_lib.stokes_error(det_ref), rtol=1e-6, atol=1e-6 * np.abs(err).max())
+    np.testing.assert_allclose(tab[0, 1:9], 1e-6 * phot_ref[:8], rtol=1e-9, atol=1e-30)
     t.close()
 
 

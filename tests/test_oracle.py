@@ -94,6 +94,74 @@ def test_thin_rayleigh_single_scattering_polarisation(oracle_factory):
     assert abs(U) / I < 0.01 and V == 0.0
 
 
+def rayleigh_deep_observables(runner, n, seed=3):
+    """(pi * I / n at full phase, -Q/I and U/I at 90 deg) of A.rayleigh_deep through `runner(launch) -> result`."""
+    atm = A.rayleigh_deep()
+    xm = 1.3 * atm.rfront[-1]
+    out = []
+    for adeg in (0.0573, 90.0):     # det_phi is kept 1e-3 rad off zero by the reference (:492)
+        L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=seed, surface_albedo=1.0, det_phi=math.radians(adeg), nx=1, ny=1, fstop=1e-7)
+        r = runner(atm, L)
+        assert int(r["err"].sum()) == 0
+        out.append([r["det"][0, k].sum() / n for k in range(4)])
+    (i0, _, _, _), (i90, q90, u90, _) = out
+    return math.pi * i0, -q90 / i90, u90 / i90
+
+
+def test_rayleigh_semi_infinite_literature_anchor():
+    """Multiple scattering WITH polarisation against the literature: the conservative semi-infinite Rayleigh planet has
+    geometric albedo 0.7975 when polarisation is carried through every scattering (Prather 1974; Buenzli & Schmid 2009,
+    A&A 504, 259) but 0.75 in the scalar approximation, and a disk-integrated polarisation of ~0.325 near quadrature,
+    perpendicular to the scattering plane (stored Q < 0, :4956).  A wrong Mueller algebra, rotation sign or phase-function
+    sampling in the oracle's scattering loop moves these numbers by several per cent (the scalar value is 6 % away)."""
+    from oracle_lib import Oracle
+
+    def runner(atm, L):
+        o = Oracle()
+        o.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+        o.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)    # surface = the planet (no tau > 30 cut)
+        return o.run(L)
+    ag, p90, u90 = rayleigh_deep_observables(runner, 40000)
+    assert abs(ag / 0.7975 - 1.0) < 0.015, ag          # 40 000 packets: sigma ~ 0.5 %
+    assert 0.310 < p90 < 0.340, p90
+    assert abs(u90) < 0.01
+
+
+def test_host_photometry_and_error_planes_match_oracle_restatement():
+    """The tail of radiative_transfer (:957-1004) and the error planes of write_output (:3481-3519): the Python host
+    mirror (artes_b200/host.py, which the driver tests compare bin/ARTES with) against the oracle's restatement, on
+    detectors with empty pixels, single-deposit pixels and unpolarised pixels."""
+    import oracle_lib
+    from artes_b200 import host
+    rs = np.random.RandomState(1)
+    for nx, ny in ((1, 1), (7, 5), (25, 25)):
+        cnt = rs.poisson(2.0, (4, ny, nx)).astype(float)
+        cnt[1:] = cnt[1]                                        # Q, U, V share one count plane (:4969-4972)
+        w = rs.random_sample((4, ny, nx)) * cnt
+        w[1:3] -= 0.5 * cnt[1:3]
+        w2 = w ** 2 / np.maximum(cnt, 1.0) + rs.random_sample((4, ny, nx)) * (cnt > 1)      # single deposits: variance exactly 0
+        if nx > 1:
+            w[1:3, 0, 0] = 0.0                                  # an unpolarised pixel: sigma_P stays 0
+        det_sum = np.stack([w, w2, cnt])
+        energy = 3.3e-20
+        d1, p1 = oracle_lib.finish_detector(det_sum, energy)
+        d2 = host.detector_from_sums(det_sum, energy)
+        p2 = host.photometry(d2)
+        np.testing.assert_array_equal(d1, d2)
+        np.testing.assert_allclose(p2, p1, rtol=1e-12, atol=0.0)
+        e1, e2 = oracle_lib.stokes_error(d1), host.stokes_error(d2)
+        np.testing.assert_allclose(e2, e1, rtol=1e-12, atol=1e-14 * np.abs(e1).max())
+        if nx > 1:
+            assert e1[4, 0, 0] == 0.0
+    p = host.Params(phase_curve=True, det_phi=math.radians(172.5))
+    for src in (1, 2):
+        p.photon_source = src
+        a = oracle_lib.package_energy(p, [1.0, 7.0e7], 0.7e-6, 1e6, 4.2e11)
+        b = host.package_energy(p, [1.0, 7.0e7], 0.7e-6, 1e6, 4.2e11)
+        assert abs(a / b - 1.0) < 1e-14
+    assert abs(oracle_lib.lib().artes_ref_planck(5800.0, 0.7e-6, 1) / host.planck_function(5800.0, 0.7e-6, 1) - 1.0) < 1e-14
+
+
 def test_mirror_symmetry_of_detector_azimuth(oracle_factory, atmospheres):
     """phi_det -> -phi_det mirrors the scene: same I and Q, opposite U (within noise)."""
     atm = atmospheres("c2_hg_deck")

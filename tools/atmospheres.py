@@ -422,6 +422,20 @@ def lambert_sphere():
     return b.finish("lambert_sphere", artes_in=_artes_in(**{"planet:surface_albedo": "1"}))
 
 
+def rayleigh_deep(tau=32.0, nr=8, thickness=8e3):
+    """Literature anchor: a homogeneous, conservative Rayleigh atmosphere of radial optical depth `tau` over a white
+    Lambert surface (planet:surface_albedo=1, cell_depth 0) -- for tau >~ 30 the conservative semi-infinite Rayleigh
+    planet of Prather (1974) / Buenzli & Schmid (2009): geometric albedo 0.7975 with polarisation (0.75 without),
+    disk-integrated polarisation ~ 0.325 near 90 deg phase angle."""
+    rfront = R_JUP + np.linspace(0.0, thickness, nr + 1)
+    b = _Builder(rfront, [0.0, 180.0], [0.0], [0.7])
+    b.add_region(rayleigh([0.7]), 1.0, (0, nr), (0, 1), (0, 1))
+    atm = b.finish("rayleigh_deep", artes_in=_artes_in(**{"planet:surface_albedo": "1"}))
+    atm.k_sca = atm.k_sca * (tau / atm.radial_tau())
+    atm.k_abs = atm.k_abs * 0.0
+    return atm
+
+
 CONFIGS = {"c1": c1_template_rayleigh, "c2": c2_hg_deck, "c3": c3_molecular, "c4": c4_mie_patches, "c5": c5_scale}
 
 
