@@ -351,6 +351,53 @@ def test_dense_matrix_entry_equals_compact(atmospheres, gpu_factory):
     np.testing.assert_allclose(a["det"][0], b["det"][0], rtol=1e-9, atol=1e-12)
 
 
+def test_dense_whole_array_entry_picks_the_wavelength_and_dedups_on_the_device(atmospheres):
+    """artes_gpu_set_wavelength_dense_wl takes the reference's WHOLE arrays (cells, n_wl[, 16, 180]) as they sit in memory
+    and picks one wavelength with strides (no Fortran slice copy); the (element, angle) planes are hashed and verified on
+    the device.  Results must equal the compact entry for that wavelength."""
+    from artes_b200.lib import GpuTransport
+    atm = A.c5_scale(nr=12, ntheta=10, nphi=16, nl=3)
+    nl = len(atm.wavelengths)
+    dense_all = np.ascontiguousarray(np.stack([atm.dense_matrix(l) for l in range(nl)], axis=2))     # (180, 16, nl, nphi, ntheta, nr)
+    xm = 1.3 * atm.rfront[-1]
+    for l in (0, 2):
+        depth = host.cell_depth(atm.rfront, atm.k_sca[l], atm.k_abs[l], atm.nr, atm.ntheta, atm.nphi, 1)
+        ga, gb = GpuTransport((0,)), GpuTransport((0,))
+        for g in (ga, gb):
+            g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+        ga.set_wavelength(atm.k_sca[l], atm.k_abs[l], atm.uniq[l], atm.cell_to_uniq[l], depth)
+        gb.set_wavelength_dense_wl(atm.k_sca, atm.k_abs, dense_all, l, depth)
+        L = make_launch(mode=abi.MODE_FAST, n_photons=30000, x_max=xm, y_max=xm, seed=4, nx=16, ny=16, det_phi=math.radians(50.0))
+        a, b = ga.run(L), gb.run(L)
+        np.testing.assert_array_equal(a["det"][2], b["det"][2])
+        np.testing.assert_allclose(a["det"][0], b["det"][0], rtol=1e-9, atol=1e-12 * np.abs(a["det"][0]).max())
+        for k in ("n_cell_face", "n_scatter", "n_draws"):
+            assert a["stats"][k] == b["stats"][k]
+        ga.close(); gb.close()
+
+
+def test_trace_hook_walks_the_tables_of_its_wavelength(atmospheres):
+    """After artes_gpu_set_wavelengths the trace hook must walk the tables of launch.wl_index (it used to walk wavelength 0):
+    crossing sequences equal the oracle loaded with that wavelength, and differ from wavelength 0's."""
+    from oracle_lib import Oracle
+    atm = atmospheres("c3_molecular")
+    wls = [0, 9, 31]
+    t = host.Transport(atm, host.Params(nx=1, ny=1), mode=abi.MODE_FAST)
+    t.set_all_wavelengths(wls)
+    xi = np.random.RandomState(5).random_sample((3000, 160))
+    hashes = []
+    for k, l in enumerate(wls):
+        o = Oracle(); depth = o.set_atmosphere(atm, l)
+        assert depth == t.depths[k]
+        for mode in MODES:
+            L = make_launch(mode=mode, n_photons=3000, x_max=t.x_max, y_max=t.x_max, fstop=0.03, nx=1, ny=1, wl_index=k)
+            ro, rg = o.trace(L, xi), t.gpu.trace(L, xi)
+            assert ((ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])).all(), (l, mode)
+        hashes.append(rg["hash"])
+    assert (hashes[0] != hashes[2]).mean() > 0.5
+    t.close()
+
+
 def test_async_equals_sync_and_empty_launch(atmospheres, gpu_factory):
     atm = atmospheres("c1_template_rayleigh")
     g, _ = gpu_factory(atm)

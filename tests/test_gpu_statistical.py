@@ -1,0 +1,157 @@
+"""Statistical parity on ALL FIVE BASELINE.json configurations at their image sizes: libartes_gpu (Philox streams, fast
+mode = the production ray/event engine) against the CPU oracle running the reference's own Marsaglia-Zaman generator --
+fully independent random streams.  Gate (tests/stat_gate.py): per pixel / phase point / spectrum point,
+|a - b| <= 3 sigma of the combined photon noise for Stokes I, Q, U and for the degree of polarisation P with the
+reference's error propagation; at most 1 % of the valid points beyond 3 sigma, none beyond 5 sigma."""
+import math
+
+import numpy as np
+import pytest
+
+import stat_gate
+from artes_b200 import abi, host
+from artes_b200.abi import make_launch
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_batches(o, K, n, seed0, **kw):
+    import oracle_lib
+    return [o.run(make_launch(n_photons=n, seed=seed0 + i, **kw), rng=oracle_lib.RNG_MZ)["det"] for i in range(K)]
+
+
+def _gpu_batches(g, K, n, seed, mode=abi.MODE_FAST, **kw):
+    return [g.run(make_launch(mode=mode, n_photons=n, seed=seed, photon_id_base=i * n, **kw))["det"] for i in range(K)]
+
+
+IMAGES = [
+    # name, pixels, det_phi [deg], batches, packets per batch (total = the config's order of magnitude), minimum valid pixels
+    ("c1_template_rayleigh", 25, 90.0, 32, 15000, 100),     # template: 25 x 25, detector at 90/90 deg
+    ("c4_mie_patches", 64, 60.0, 32, 31250, 800),           # 3-D Mie patches: 64 x 64, 1e6 packets
+    ("c5_scale", 64, 60.0, 32, 31250, 800),                 # scale grid 100 x 60 x 120: 64 x 64, 1e6 packets
+]
+
+
+@pytest.mark.parametrize("name,npix,phi,K,n,min_valid", IMAGES)
+def test_images_agree_within_photon_noise(atmospheres, oracle_factory, gpu_factory, name, npix, phi, K, n, min_valid):
+    atm = atmospheres(name)
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    kw = dict(x_max=xm, y_max=xm, nx=npix, ny=npix, det_phi=math.radians(phi))
+    ba = _oracle_batches(o, K, n, 1000, **kw)
+    bb = _gpu_batches(g, K, n, 7, **kw)
+    assert g.last_engine() == 2
+    rep = stat_gate.z_report(ba, bb)
+    stat_gate.assert_gate(rep, names=("I", "Q", "U", "P"), min_valid=min_valid, what=name)
+    tz = stat_gate.totals_z(ba, bb)                       # disk-integrated I, Q, U and degree of polarisation
+    assert max(tz.values()) < 3.5, (name, tz)
+
+
+def test_faithful_mode_image_agrees_within_photon_noise(atmospheres, oracle_factory, gpu_factory):
+    """The faithful mode (persistent-lane engine) through the same gate, on the 3-D Mie configuration."""
+    atm = atmospheres("c4_mie_patches")
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    kw = dict(x_max=xm, y_max=xm, nx=64, ny=64, det_phi=math.radians(60.0))
+    ba = _oracle_batches(o, 32, 12000, 3000, **kw)
+    bb = _gpu_batches(g, 32, 12000, 11, mode=abi.MODE_FAITHFUL, **kw)
+    assert g.last_engine() == 1
+    stat_gate.assert_gate(stat_gate.z_report(ba, bb), names=("I", "Q", "U", "P"), min_valid=500, what="c4 faithful")
+
+
+def _points_as_image(dets):
+    """[n_points] detectors of 1 x 1 pixels -> one det[l, stokes, 1, n_points], so that the points go through the pixel gate."""
+    return np.concatenate(dets, axis=-1)
+
+
+def test_phase_curve_all_73_angles(atmospheres, oracle_factory, gpu_factory):
+    """C2: the full phase curve of `run` (:215-245; 73 detector azimuths, limb-biased emission from 170 deg on) as batched
+    launches on the GPU against the oracle's 73 separate launches: I, Q, U and P of every angle through the gate."""
+    atm = atmospheres("c2_hg_deck")
+    o, _ = oracle_factory(atm)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    phis = [1.e-5 * math.pi / 180.0, 2.5 * math.pi / 180.0]
+    while len(phis) < 72:
+        phis.append(phis[-1] + 2.5 * math.pi / 180.0)
+    phis.append((180.0 - 1e-5) * math.pi / 180.0)
+    assert len(phis) == 73
+    # the reference keeps det_phi 1e-3 rad away from 0 and pi (:492-493)
+    phis_c = [min(max(p, 1.e-3), math.pi - 1.e-3) for p in phis]
+    K, n = 32, 1500
+    kw = dict(x_max=xm, y_max=xm, nx=1, ny=1)
+    limb = [int(p * 180.0 / math.pi >= 170.0) for p in phis]
+    assert sum(limb) == 5
+    import oracle_lib
+    ba, bb = [], []
+    for i in range(K):
+        ba.append(_points_as_image([o.run(make_launch(n_photons=n, seed=20000 + 73 * i + a, det_phi=phis_c[a], limb_emission=limb[a], **kw),
+                                          rng=oracle_lib.RNG_MZ)["det"] for a in range(73)]))
+        Ls = [make_launch(mode=abi.MODE_FAST, n_photons=n, seed=9, photon_id_base=i * 73 * n, det_phi=phis_c[a], limb_emission=limb[a], **kw)
+              for a in range(73)]
+        r = g.run_batch(Ls)
+        assert r["stats"]["reserved"] == 1 and g.last_engine() == 2           # ONE kernel for the 73 angles
+        bb.append(_points_as_image(list(r["det"])))
+    rep = stat_gate.z_report(ba, bb)
+    stat_gate.assert_gate(rep, names=("I", "Q", "U", "P"), min_valid=60, what="c2 phase curve")
+    # the curve itself: bright at full phase, faint towards new phase, polarised in between
+    tot = np.sum(bb, axis=0)
+    assert tot[0, 0, 0, 0] > 5 * tot[0, 0, 0, 60]
+    p = np.hypot(tot[0, 1, 0], tot[0, 2, 0]) / tot[0, 0, 0]
+    assert p[36] > 3 * p[1]
+
+
+def test_spectrum_all_wavelengths(atmospheres, gpu_factory):
+    """C3: the spectrum of `run` (:132-165; 32 wavelengths, 100 radial layers) as ONE batched launch over the stacked
+    wavelength tables against the oracle's per-wavelength launches."""
+    import oracle_lib
+    from artes_b200.lib import GpuTransport
+    atm = atmospheres("c3_molecular")
+    nl = len(atm.wavelengths)
+    assert nl == 32 and atm.nr == 100
+    p = host.Params(nx=1, ny=1)
+    t = host.Transport(atm, p, mode=abi.MODE_FAST)
+    t.set_all_wavelengths()
+    xm = t.x_max
+    K, n = 32, 1000
+    kw = dict(x_max=xm, y_max=xm, nx=1, ny=1)
+    oracles = []
+    for l in range(nl):
+        o = oracle_lib.Oracle()
+        depth = o.set_atmosphere(atm, l)
+        assert depth == t.depths[l]
+        oracles.append(o)
+    ba, bb = [], []
+    for i in range(K):
+        ba.append(_points_as_image([oracles[l].run(make_launch(n_photons=n, seed=50000 + nl * i + l, **kw), rng=oracle_lib.RNG_MZ)["det"]
+                                    for l in range(nl)]))
+        r = t.gpu.run_batch([t.launch_struct(n, seed=13, photon_id_base=i * nl * n, wl_index=l) for l in range(nl)])
+        assert r["stats"]["reserved"] == 1
+        bb.append(_points_as_image(list(r["det"])))
+    rep = stat_gate.z_report(ba, bb)
+    stat_gate.assert_gate(rep, names=("I", "Q", "U", "P"), min_valid=nl, what="c3 spectrum")
+    t.close()
+
+
+def test_rayleigh_semi_infinite_literature_anchor_on_gpu():
+    """The literature anchor of tests/test_oracle.py on the product (both engines): conservative semi-infinite Rayleigh
+    planet, geometric albedo 0.7975 with polarisation (0.75 without), P ~ 0.325 at quadrature."""
+    from artes_b200.lib import GpuTransport
+    from test_oracle import rayleigh_deep_observables
+
+    for mode, n, tol in ((abi.MODE_FAST, 1000000, 0.008), (abi.MODE_FAITHFUL, 100000, 0.015)):
+        def runner(atm, L):
+            g = GpuTransport((0,))
+            g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+            g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)
+            L.mode = mode
+            r = g.run(L)
+            g.close()
+            return r
+        ag, p90, u90 = rayleigh_deep_observables(runner, n)
+        print("rayleigh_deep", "fast" if mode == abi.MODE_FAST else "faithful", "A_g", ag, "P(90)", p90, "U/I", u90)
+        assert abs(ag / 0.7975 - 1.0) < tol, (mode, ag)
+        assert 0.315 < p90 < 0.335, (mode, p90)
+        assert abs(u90) < 0.005

@@ -162,6 +162,26 @@ def test_host_photometry_and_error_planes_match_oracle_restatement():
     assert abs(oracle_lib.lib().artes_ref_planck(5800.0, 0.7e-6, 1) / host.planck_function(5800.0, 0.7e-6, 1) - 1.0) < 1e-14
 
 
+def test_reference_sigma_underestimates_the_noise(oracle_factory, atmospheres):
+    """Why the statistical gate (tests/stat_gate.py) measures the photon noise from independent batches instead of using
+    the reference's per-pixel sigma (:3490-3493): two runs of the oracle ITSELF with different seeds are consistent under
+    the batch variance (rms z ~ 1) but differ by ~3 of the reference's sigmas in Stokes I on the template atmosphere --
+    that estimate ignores the correlation of the ~40 peel-off deposits a packet makes into neighbouring pixels."""
+    import oracle_lib
+    import stat_gate
+    atm = atmospheres("c1_template_rayleigh")
+    o, _ = oracle_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    K, n = 16, 8000
+    runs = [[o.run(make_launch(n_photons=n, x_max=xm, y_max=xm, seed=s0 + i, nx=25, ny=25), rng=oracle_lib.RNG_MZ)["det"] for i in range(K)]
+            for s0 in (100, 5000)]
+    rep = stat_gate.z_report(*runs)
+    for nm in "IQU":
+        assert 0.7 < rep[nm][3] < 1.3 and rep[nm][2] < 5.0, rep
+    ref = stat_gate.z_report_ref_sigma(*runs)
+    assert ref["I"][3] > 2.0 and ref["I"][1] > 0.1, ref          # rms z > 2, > 10 % of the pixels beyond "3 sigma"
+
+
 def test_mirror_symmetry_of_detector_azimuth(oracle_factory, atmospheres):
     """phi_det -> -phi_det mirrors the scene: same I and Q, opposite U (within noise)."""
     atm = atmospheres("c2_hg_deck")
