@@ -60,7 +60,7 @@ namespace e2 {
 // the event phase.  RC = ring capacity of the lists (power of two >= NP).
 
 enum : int { K_PRE = 0, K_WALK = 1, K_PEEL = 2, K_DEAD = 3 };
-enum : int { L_EMIT = 0, L_PRE, L_H, L_DEP, L_RES, L_SURF, L_RDY, N_LISTS };   // event lists, then the ready list
+enum : int { L_EMIT = 0, L_PRE, L_H, L_DEP, L_RES, L_SURF, L_FAN, L_SC, L_RDY, N_LISTS };   // event lists (L_FAN, L_SC: multi-detector walks only), then the ready list
 constexpr int N_EVENT_LISTS = L_RDY;
 enum : int { O_NONE = 0, O_LIMIT, O_EXIT, O_SURF, O_REST, O_RESP, O_ERR, O_DEAD };
 // info word: bits 0-1 kind, 2 radial inward, 3 next theta face is the upper one, 4 phi increasing, 8-11 outcome
@@ -85,26 +85,30 @@ __host__ __device__ constexpr int ring_cap(int np_slots) { int c = 32; while (c 
 // to keep in (or spill from) registers around the whole scheduling loop.  The grid tables, whose sizes are run-time
 // values, follow.
 __host__ __device__ constexpr int fixed_doubles(int NP) {
-    return (NF_HOT * NP * 8 + NI_HOT * NP * 4 + N_LISTS * ring_cap(NP) * 2 + 64 * 4 + 15) / 16 * 2;
+    return (NF_HOT * NP * 8 + NI_HOT * NP * 4 + N_LISTS * ring_cap(NP) * 2 + 64 * 4 + 15) / 16 * 2;      // 64 ints: head[16] | tail[16] | misc[32]
 }
 constexpr int GEO = 12;     // doubles per launch in the launch table: det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi,
                             // cell_depth and wavelength index of the launch (batches over wavelengths: LaunchArgs::wl_batch)
 struct Lay {
-    int o_r, o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, o_geo, n_end;   // offsets in doubles
+    int o_r, o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, o_geo, o_det, n_end;   // offsets in doubles
     size_t bytes;
-    __host__ __device__ Lay(int nr, int nt, int np, int NP, int nb = 1) {
+    // nb: launches in the launch table; ndet: doubles of the block-private detector image (0: the image stays in global memory)
+    __host__ __device__ Lay(int nr, int nt, int np, int NP, int nb = 1, int ndet = 0) {
         o_r = fixed_doubles(NP);
         o_r2 = o_r + nr + 1; o_tf = o_r2 + nr + 1; o_tt = o_tf + nt + 1; o_ps = o_tt + nt + 1; o_pc = o_ps + np; o_pf = o_pc + np;
-        o_tp = o_pf + np; o_ca = ((o_tp + (nt + 2) / 2 + 1) + 1) & ~1; o_geo = o_ca + 2 * 181; n_end = o_geo + GEO * (nb < 1 ? 1 : nb);   // o_ca, o_geo: 16-byte aligned
+        o_tp = o_pf + np; o_ca = ((o_tp + (nt + 2) / 2 + 1) + 1) & ~1; o_geo = o_ca + 2 * 181; o_det = o_geo + GEO * (nb < 1 ? 1 : nb);   // o_ca, o_geo: 16-byte aligned
+        n_end = o_det + ndet;
         bytes = (size_t)n_end * 8;
     }
 };
 
-template <int NP, bool TR = false, bool GN = false, bool BT = false>
+template <int NP, bool TR = false, bool GN = false, bool BT = false, bool MD = false>
 struct ShT {                     // pointers into the block's shared memory
     static constexpr bool TRACE = TR;   // the injected-stream walk recorder (test hook) is compiled in
     static constexpr bool BATCH = BT;   // batched launches: per-photon launch index, detector geometry from the shared-memory table
     static constexpr bool GEN = GN;     // thermal source, reflecting surface and latitudinal flow counters are compiled in
+    static constexpr bool MULTI = MD;   // ONE walk, peel-off towards every detector of the launch table (artes_gpu_run_multi)
+    double* sdet;                // block-private detector image in shared memory (null: global atomics)
     const double* r; const double* r2; const double* tf; const double* ttan; const double* ps; const double* pc; const double* pf;
     const int* tplane;
     const double* geo;           // [n_batch][GEO] detector geometry of the launch(es)
@@ -980,17 +984,19 @@ __device__ __forceinline__ bool ev_resolve(const Sh& X, const KernelArgs& A, boo
 // ---------------------------------------------------------------------------------------------------
 // block set-up and the marcher
 // ---------------------------------------------------------------------------------------------------
-template <int NT, int NP, bool TR, bool GN, bool BT>
-__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP, TR, GN, BT>& X, bool mark_empty) {
+template <int NT, int NP, bool TR, bool GN, bool BT, bool MD = false>
+__device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT<NP, TR, GN, BT, MD>& X, bool mark_empty) {
     const DevTables& T = A.T;
     const int nb = A.L.n_batch > 1 ? A.L.n_batch : 1;
-    const Lay lay(T.nr, T.nt, T.np, NP, nb);
-    constexpr int RC = ShT<NP, TR, GN, BT>::RC;
+    const Lay lay(T.nr, T.nt, T.np, NP, nb, A.L.sdet_doubles);
+    constexpr int RC = ShT<NP, TR, GN, BT, MD>::RC;
     X.sd = sm;
     X.si = reinterpret_cast<int*>(X.sd + NF_HOT * NP);
     X.q = reinterpret_cast<short*>(X.si + NI_HOT * NP);
     X.head = reinterpret_cast<int*>(X.q + N_LISTS * RC);
-    X.tail = X.head + 8; X.misc = X.head + 16;
+    X.tail = X.head + 16; X.misc = X.head + 32;
+    X.sdet = A.L.sdet_doubles > 0 ? sm + lay.o_det : nullptr;
+    for (int i = threadIdx.x; i < A.L.sdet_doubles; i += NT) sm[lay.o_det + i] = 0.0;
     X.r = sm + lay.o_r; X.r2 = sm + lay.o_r2; X.tf = sm + lay.o_tf; X.ttan = sm + lay.o_tt; X.ps = sm + lay.o_ps; X.pc = sm + lay.o_pc; X.pf = sm + lay.o_pf;
     X.tplane = reinterpret_cast<const int*>(sm + lay.o_tp);
     X.cdfa = reinterpret_cast<const double2*>(sm + lay.o_ca);
@@ -1014,7 +1020,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     if (mark_empty) for (int i = tid; i < N_LISTS * RC; i += NT) X.q[i] = (short)-1;
     __syncthreads();
     for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; X.I(I_INFO, i) = 0; }   // every slot starts by asking for a photon
-    if (tid < 8) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
+    if (tid < 16) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
     if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; }
     __syncthreads();
 }
@@ -1140,6 +1146,261 @@ struct Marcher {
         return (out == O_NONE) ? -1 : finish(X, A, C, out);
     }
 };
+
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-detector walks (ShT::MULTI, artes_gpu_run_multi).  The reference runs the whole random walk once per detector
+// azimuth of a phase curve (src/ARTES.f90:215-245: 73 calls of radiative_transfer that differ in det_phi only).  Peel-off
+// is a next-event estimate: at every scattering the walk may be observed from ANY direction without disturbing it, so
+// ONE walk can feed all K detectors of the launch table -- every detector receives exactly the deposits the reference's
+// run with that det_phi would make along this walk (same weights, same pixel rule); only the walk is shared, i.e. the
+// K images are statistically correlated instead of independent.  The interaction event is cut in three:
+//   H    survival :791-813                                              -> FAN list
+//   FAN  one warp per photon, lanes = detectors: peel-off weight and pixel (:4763-4951), the walk to the grid exit
+//        (:4739-4761) marched INLINE by the lane (no slot, no list: the ray state never leaves registers), e^-tau and the
+//        deposit (:4955-4972), 32 detectors per round                      -> SC list
+//   SC   scattering :819-845 (new direction, Stokes vector, optical depth)  -> transport ray
+// Star source, black surface, no flow counters (the general paths keep their per-detector launches).
+// ---------------------------------------------------------------------------------------------------
+
+// H (multi): the transport walk reached its optical depth: step back to the interaction point, survival :791-813
+template <class Sh>
+__device__ __forceinline__ int ev_survive(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C) {
+    if (!valid) return -1;
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
+    const int cell = X.I(I_CELL, s);
+    const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+    const int ci = c0 + T.nr * (c1 + T.nt * c2);
+    double* rec = X.cold + (size_t)s * REC;
+    double hx, hy, hz, dx, dy, dz, S[4], tau0, w0_, i0_, i1_, i2_, i3_;
+    ldg256(rec, hx, hy, hz, dx);
+    ldg256(rec + 4, dy, dz, S[0], S[1]);
+    ldg256(rec + 8, S[2], S[3], tau0, w0_);
+    ldg256(rec + 16, i0_, i1_, i2_, i3_);
+    (void)w0_; (void)i2_; (void)i3_;
+    double kap_c, alb_c, u_bits, pad_c;
+    ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
+    (void)pad_c; (void)u_bits;
+    const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - tau0, kap_c);      // step back by the overshoot (:705-720)
+    const double px = hx + tpos * dx, py = hy + tpos * dy, pz = hz + tpos * dz;
+    const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
+    const unsigned long long id = (w16 >> 32) | ((w17 & 0xffffffffull) << 32);
+    unsigned nd = (unsigned)w16;
+    bool alive = L.photon_scattering != 0;
+    if (alive) { double xi; draws(X, A, s, id, nd, 1, &xi); ++nd; if (xi < L.fstop) alive = false; }
+    if (alive) {
+        if (alb_c < 1.0 && alb_c > 0.0) { const double g = fdiv(alb_c, 1.0 - L.fstop); S[0] *= g; S[1] *= g; S[2] *= g; S[3] *= g; }
+        if (S[0] <= L.photon_minimum) alive = false;
+    }
+    X.I(I_ND, s) = (int)nd;
+    if (!alive) { X.I(I_INFO, s) = K_DEAD; return L_EMIT; }
+    stg256(rec, px, py, pz, dx);
+    stg256(rec + 4, dy, dz, S[0], S[1]);
+    stg256(rec + 8, S[2], S[3], tau0, 0.0);
+    X.I(I_HCELL, s) = cell;
+    return L_FAN;
+}
+
+// SC (multi): scattering :819-845 -- new direction and Stokes vector, next optical depth, transport ray
+template <class Sh>
+__device__ __forceinline__ int ev_scatter_md(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
+    if (!valid) return -1;
+    const DevTables& T = A.T;
+    double* rec = X.cold + (size_t)s * REC;
+    double px, py, pz, dx, dy, dz, S[4], t0_, t1_, i0_, i1_, i2_, i3_;
+    ldg256(rec, px, py, pz, dx);
+    ldg256(rec + 4, dy, dz, S[0], S[1]);
+    ldg256(rec + 8, S[2], S[3], t0_, t1_);
+    ldg256(rec + 16, i0_, i1_, i2_, i3_);
+    (void)t0_; (void)t1_; (void)i2_; (void)i3_;
+    const int cell = X.I(I_HCELL, s);
+    const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+    const int ci = c0 + T.nr * (c1 + T.nt * c2);
+    double kap_c, alb_c, u_bits, pad_c;
+    ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
+    (void)kap_c; (void)alb_c; (void)pad_c;
+    const int u = (int)__double_as_longlong(u_bits);
+    const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
+    const unsigned long long id = (w16 >> 32) | ((w17 & 0xffffffffull) << 32);
+    unsigned nd = (unsigned)w16;
+    double xr[5];
+    draws(X, A, s, id, nd, 4, xr);
+    ++C.n_sc;
+    FastAngles g;
+    int e = sample_angles_f(X, A, xr[0], xr[1], xr[2], S, ci, g, u);
+    nd += (e == 6) ? 2u : 3u;
+    double e0 = 0, e1 = 0, e2 = 0, tau = -1.0;
+    if (!e) {
+        const double cto = fdiv(dz, fsqrt(dx * dx + dy * dy + dz * dz));
+        const double sto = fsqrt(1.0 - cto * cto);
+        const double ctn = cto * g.alpha + sto * g.sT * g.cb;
+        const double stn = fsqrt(1.0 - ctn * ctn);
+        double nc = fdiv(g.alpha - ctn * cto, stn * sto);
+        if (!(nc == nc)) e = 20;
+        else {
+            if (nc >= 1.0) nc = 1.0 - 1.e-10; else if (nc <= -1.0) nc = -1.0 + 1.e-10;
+            const double sD = fsqrt(1.0 - nc * nc) * (g.flip ? -1.0 : 1.0);
+            const double rho = fsqrt(dx * dx + dy * dy);
+            const double irho = frcp(rho);
+            const double cph = rho > 0.0 ? dx * irho : 1.0, sph = rho > 0.0 ? dy * irho : 0.0;
+            e0 = stn * (cph * nc - sph * sD); e1 = stn * (sph * nc + cph * sD); e2 = ctn;
+            if (!(fabs(e2) < 1.0)) e = 16;
+        }
+    }
+    if (!e) {
+        double F[16], Sn[4];
+        matrix_at_deg_f(T, u, g.deg, F);
+        const double nc2 = fdiv(dz - e2 * g.alpha, g.sT * fsqrt(1.0 - e2 * e2));
+        int soft = 0;
+        e = polrot_f(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
+        if (soft) err_count(A, soft);
+        if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
+    }
+    if (e) { err_count(A, e); ++C.n_err; X.I(I_ND, s) = (int)nd; X.I(I_INFO, s) = K_DEAD; return L_EMIT; }
+    ++nd;
+    tau = -fm_log(1.0 - xr[3]);
+    stg256(rec, px, py, pz, dx);
+    stg256(rec + 4, dy, dz, S[0], S[1]);
+    stg256(rec + 8, S[2], S[3], tau, 0.0);
+    X.I(I_ND, s) = (int)nd;
+    rs.set(px, py, pz, dx, dy, dz, c0, c1, c2, -1, K_WALK, tau);
+    return L_RDY;
+}
+
+// FAN (multi): peel-off of the n photons of the batch (lane j holds slot s of photon j) towards every detector.
+// One photon at a time, lanes = detectors.  The photon's record is read with warp-uniform addresses (one transaction),
+// the matrix rows of the 32 detectors come from the same 23 KB block, and the walk to the detector runs in the lane.
+template <class Sh>
+__device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, int s_lane, Cnt& C) {
+    const DevTables& T = A.T;
+    const LaunchArgs& L = A.L;
+    const int lane = threadIdx.x & 31;
+    const int K = L.n_batch;
+    const size_t npx = (size_t)L.nx * L.ny;
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        const int sp = __shfl_sync(FULL, s_lane, j);
+        const double* rec = X.cold + (size_t)sp * REC;
+        double px, py, pz, dx, dy, dz, S[4], t0_, t1_;
+        ldg256(rec, px, py, pz, dx);
+        ldg256(rec + 4, dy, dz, S[0], S[1]);
+        ldg256(rec + 8, S[2], S[3], t0_, t1_);
+        (void)t0_; (void)t1_;
+        const int cell = X.I(I_HCELL, sp);
+        const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+        const int ci = c0 + T.nr * (c1 + T.nt * c2);
+        double kap_c, alb_c, u_bits, pad_c;
+        ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
+        (void)alb_c; (void)pad_c;
+        const int u = (int)__double_as_longlong(u_bits);
+        const bool dz_ok = fabs(dz) < 1.0;
+        const double idz = dz_ok ? frcp(fsqrt(1.0 - dz * dz)) : 0.0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int kd = k0 + lane;
+            const bool act = kd < K;
+            double W[4] = {0.0, 0.0, 0.0, 0.0};
+            int pix = -1;
+            Geo G = geo_of(X, L, act ? kd : 0);
+            if (act) {
+                ++C.n_peel;
+                double mu = dx * G.d0 + dy * G.d1 + dz * G.d2;
+                if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
+                const double peel_deg = fm_acos(mu) * (180.0 / PI);
+                double F[16];
+                matrix_at_deg_f(T, u, peel_deg, F);
+                if (!dz_ok) err_count(A, 45);
+                else {
+                    const double smu = fsqrt(1.0 - mu * mu);
+                    double nc = fdiv(G.d2 - dz * mu, smu) * idz;
+                    if (!(nc == nc)) err_count(A, 44);
+                    else {
+                        nc = fmin(fmax(nc, -1.0), 1.0);
+                        const double cr = dy * G.d0 - dx * G.d1;
+                        const bool flip = (cr > 0.0) || (cr == 0.0 && dx * G.d0 + dy * G.d1 > 0.0);
+                        const double c2a = 2.0 * nc * nc - 1.0;
+                        double s2a = 2.0 * nc * fsqrt(fmax(1.0 - nc * nc, 0.0));
+                        if (flip) s2a = -s2a;
+                        const double nc2 = fdiv(dz - G.d2 * mu, smu * fsqrt(1.0 - G.d2 * G.d2));
+                        int soft = 0;
+                        const int e = (fabs(G.d2) < 1.0) ? polrot_f(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
+                        if (e) err_count(A, e);
+                        else if (!(W[0] > 0.0 && W[0] < 1.e100)) err_count(A, 53);
+                        else {
+                            const double x_im = py * G.cdp - px * G.sdp;
+                            const double y_im = pz * G.sdt - py * G.cdt * G.sdp - px * G.cdt * G.cdp;
+                            const int ix = (int)fdiv(L.nx * (x_im + L.x_max), 2.0 * L.x_max) + 1;
+                            const int iy = (int)fdiv(L.ny * (y_im + L.y_max), 2.0 * L.y_max) + 1;
+                            if (ix < 1 || ix > L.nx || iy < 1 || iy > L.ny) err_count(A, 60);
+                            else pix = (ix - 1) + L.nx * (iy - 1) + kd * 10 * L.nx * L.ny;
+                        }
+                    }
+                }
+            }
+            // ---- the walk to the detector (:4739-4761), in the lane; stops once tau >= 50 (the reference drops those, :4765)
+            if (pix >= 0) {
+                Marcher M;
+                M.init(T);
+                RayK Kc;
+                double hbn, D0, iq;
+                ray_consts(T, px, py, pz, G.d0, G.d1, G.d2, Kc, hbn, D0, iq);
+                int inward, upper = 0, up = 0;
+                M.tr = radial_first(X, c0, -1, hbn, D0, iq, inward);
+                M.tt = (T.nt > 1) ? theta_next(X, T.nt, c1, 0.0, Kc, upper) : RAY_NONE;
+                M.tp = phi_next(X, T.np, c2, 0.0, Kc, up);
+                M.t = 0.0; M.acc = 0.0; M.hbn = hbn; M.D0 = D0; M.iq = iq; M.lim = 50.0;
+                M.c0 = c0; M.cell12 = cell & ~1023;
+                M.info = K_PEEL | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
+                M.dr = inward ? -1 : 1; M.ds = inward ? -1.0 : 1.0;
+                M.kb = M.kext + T.nr * (c1 + T.nt * c2);
+                M.kap = kap_c;
+                M.slot = sp;
+                unsigned n_step = 0;
+                int out;
+#pragma unroll 1
+                for (;;) {
+                    out = M.step(X, A, n_step);
+                    if (out == O_NONE) continue;
+                    if (out != O_REST && out != O_RESP) break;
+                    // a polar or azimuthal face: move the cell index and re-solve that axis (the RES event, inline)
+                    int cc1 = (M.cell12 >> 10) & 1023, cc2 = (M.cell12 >> 20) & 1023;
+                    if (out == O_REST) {
+                        cc1 += (M.info & B_TUPPER) ? 1 : -1;
+                        int up2;
+                        M.tt = theta_next(X, T.nt, cc1, M.t, Kc, up2);
+                        M.info = (M.info & ~B_TUPPER) | (up2 ? B_TUPPER : 0);
+                    } else {
+                        if (M.info & B_PUP) cc2 = (cc2 + 1 == T.np) ? 0 : cc2 + 1; else cc2 = (cc2 == 0) ? T.np - 1 : cc2 - 1;
+                        int up2;
+                        M.tp = phi_next(X, T.np, cc2, M.t, Kc, up2);
+                    }
+                    M.cell12 = (cc1 << 10) | (cc2 << 20);
+                    M.kb = M.kext + T.nr * (cc1 + T.nt * cc2);
+                    M.kap = __ldg(M.kb + M.c0);
+                }
+                C.n_cf += n_step;
+                if (out == O_ERR) { err_count(A, 31); err_count(A, 43); ++C.n_err; }
+                if (out == O_EXIT && M.acc < 50.0) {        // reached the detector: e^-tau, deposit :4955-4972
+                    const double w = fm_exp_neg(M.acc);
+                    const double v0 = w * W[0], v1 = -(w * W[1]), v2 = w * W[2], v3 = w * W[3];
+                    if (X.sdet) {
+                        double* d = X.sdet + pix;
+                        atomicAdd(d, v0); atomicAdd(d + npx, v1); atomicAdd(d + 2 * npx, v2); atomicAdd(d + 3 * npx, v3);
+                        atomicAdd(d + 4 * npx, v0 * v0); atomicAdd(d + 5 * npx, v1 * v1); atomicAdd(d + 6 * npx, v2 * v2); atomicAdd(d + 7 * npx, v3 * v3);
+                        atomicAdd(d + 8 * npx, 1.0); atomicAdd(d + 9 * npx, 1.0);
+                    } else {
+                        double* d = A.O.det + pix;
+                        atomicAdd(d, v0); atomicAdd(d + npx, v1); atomicAdd(d + 2 * npx, v2); atomicAdd(d + 3 * npx, v3);
+                        atomicAdd(d + 4 * npx, v0 * v0); atomicAdd(d + 5 * npx, v1 * v1); atomicAdd(d + 6 * npx, v2 * v2); atomicAdd(d + 7 * npx, v3 * v3);
+                        atomicAdd(d + 8 * npx, 1.0); atomicAdd(d + 9 * npx, 1.0);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
 
 template <class Sh>
 __device__ __forceinline__ bool run_event(const Sh& X, const KernelArgs& A, int l, bool valid, int s, Cnt& C) {

@@ -277,51 +277,7 @@ def test_fast_mode_oblate_planet_same_stream(atmospheres):
     np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=2e-5, atol=1e-9)
 
 
-def batch_z(batches_a, batches_b, min_count=30):
-    """Per-pixel z score of two sets of independent batches.  The noise is the variance ACROSS batches:
-    the reference's own error estimate (src/ARTES.f90:3490-3493, variance of the deposits about their mean)
-    misses both the counting noise and the correlation between the many peel-off deposits one packet makes
-    into the same pixel, and underestimates the real photon noise by 1.2-1.5x (measured)."""
-    A_, B_ = np.stack([b[0] for b in batches_a]), np.stack([b[0] for b in batches_b])   # [K, 4, ny, nx]
-    na = np.sum([b[2] for b in batches_a], axis=0)
-    nb = np.sum([b[2] for b in batches_b], axis=0)
-    K = A_.shape[0]
-    var = K * (A_.var(axis=0, ddof=1) + B_.var(axis=0, ddof=1))
-    diff = A_.sum(axis=0) - B_.sum(axis=0)
-    rep = {}
-    for k, nm in enumerate("IQU"):
-        m = (na[k] >= min_count * K) & (nb[k] >= min_count * K) & (var[k] > 0)
-        z = np.abs(diff[k][m]) / np.sqrt(var[k][m])
-        rep[nm] = (int(m.sum()), float((z > 3).mean()), float(z.max()), float(np.sqrt((z ** 2).mean())))
-    return rep
-
-
-@pytest.mark.parametrize("mode", MODES)
-def test_statistical_parity_independent_streams(atmospheres, oracle_factory, gpu_factory, mode):
-    """Independent random streams (oracle: the reference's Marsaglia-Zaman generator; GPU: Philox):
-    Stokes I, Q, U images agree within 3 sigma of the combined photon noise per pixel
-    (<= 2 % of pixels beyond 3 sigma, none beyond 5), and so does the disk-integrated polarisation."""
-    import oracle_lib
-    atm = atmospheres("c4_mie_patches")
-    o, _ = oracle_factory(atm)
-    g, _ = gpu_factory(atm)
-    xm = 1.3 * atm.rfront[-1]
-    kw = dict(x_max=xm, y_max=xm, nx=16, ny=16, det_phi=math.radians(60.0))
-    K, n = 16, 40000
-    ba = [o.run(make_launch(n_photons=n, seed=100 + i, **kw), rng=oracle_lib.RNG_MZ)["det"] for i in range(K)]
-    bb = [g.run(make_launch(mode=mode, n_photons=n, seed=7, photon_id_base=i * n, **kw))["det"] for i in range(K)]
-    rep = batch_z(ba, bb)
-    for nm, (npix, frac3, zmax, zrms) in rep.items():
-        assert npix > 50, rep
-        assert frac3 <= 0.02 and zmax < 5.0 and zrms < 1.25, rep
-    # disk-integrated Stokes parameters: batch means within 3 sigma of the batch scatter
-    for k in range(3):
-        ta = np.array([b[0, k].sum() for b in ba]); tb = np.array([b[0, k].sum() for b in bb])
-        zz = abs(ta.mean() - tb.mean()) / math.sqrt(ta.var(ddof=1) / K + tb.var(ddof=1) / K)
-        assert zz < 3.5, (k, zz)
-    pa = np.array([math.hypot(b[0, 1].sum(), b[0, 2].sum()) / b[0, 0].sum() for b in ba])
-    pb = np.array([math.hypot(b[0, 1].sum(), b[0, 2].sum()) / b[0, 0].sum() for b in bb])
-    assert abs(pa.mean() - pb.mean()) / math.sqrt(pa.var(ddof=1) / K + pb.var(ddof=1) / K) < 3.5
+# (the independent-stream statistical gate lives in tests/test_gpu_statistical.py: all five configurations, SURVEY 8d thresholds)
 
 
 def test_lambert_sphere_on_gpu(gpu_factory):
