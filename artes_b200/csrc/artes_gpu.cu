@@ -35,6 +35,7 @@ cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const dou
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
 bool engine2_supports(const KernelArgs& a);
 bool engine2_batch_fits(const KernelArgs& a, int n);
+int engine2_sdet_doubles(const KernelArgs& a, int n);
 size_t engine2_scratch_bytes(int sm_count);
 cudaError_t launch_transport2(const KernelArgs& a, int sm_count, cudaStream_t stream);
 cudaError_t launch_transport2_trace(const KernelArgs& a, int sm_count, cudaStream_t stream);
@@ -662,6 +663,7 @@ int artes_gpu_wait(artes_gpu_ctx* ctx, double* det_sum, double* flux, double* fl
     if (flux) { flux[0] = h[10 * npx]; flux[1] = h[10 * npx + 1]; }
     if (flow4) std::memcpy(flow4, h.data() + 10 * npx + 2, (size_t)4 * ctx->cells * sizeof(double));
     if (flow3) std::memcpy(flow3, h.data() + 10 * npx + 2 + (size_t)4 * ctx->cells, (size_t)3 * ctx->cells * sizeof(double));
+    if (hu[ARTES_ERR_SLOTS - 1]) return fail(ctx, -5, "transport kernel stopped by its watchdog (no scheduling progress): results discarded");
     if (err_hist) for (int k = 0; k < ARTES_ERR_SLOTS; ++k) err_hist[k] = hu[k];
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -690,8 +692,8 @@ int artes_gpu_run(artes_gpu_ctx* ctx, const artes_launch_t* L, double* det_sum, 
 // come out of one counter, every photon carries the index of its launch, and the drain is paid once per batch.
 // Launch k uses the photon ids photon_id_base(launch 0) + k * n_photons + [0, n_photons): its result equals the single
 // launch with that photon_id_base up to the order of the floating-point sums.
-int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, double* det_sum, double* flux,
-                        uint64_t* err_hist, artes_stats_t* stats) {
+static int run_batch_impl(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, double* det_sum, double* flux,
+                          uint64_t* err_hist, artes_stats_t* stats, bool multi) {
     if (!ctx) return fail(nullptr, -1, "null context");
     if (!Ls || n < 1 || n > ARTES_MAX_BATCH) return fail(ctx, -1, "run_batch: 1 <= n <= ARTES_MAX_BATCH launches");
     if (ctx->pending) return fail(ctx, -1, "a launch is already pending (call artes_gpu_wait)");
@@ -707,13 +709,24 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
     const size_t npx = (size_t)L0.nx * L0.ny;
     const unsigned long long P = L0.n_photons;
     static const int engine = env_int("ARTES_ENGINE", 2);
-    bool batched = n > 1 && P > 0 && L0.mode == ARTES_MODE_FAST && engine == 2;
+    bool batched = (n > 1 || multi) && P > 0 && L0.mode == ARTES_MODE_FAST && engine == 2;
+    int sdet_doubles = 0;
     if (batched) {
         KernelArgs a{};
         a.T = ctx->devs[0].T;
         fill_launch(L0, a.L);
         // a launch table too large for shared memory or an image stack whose pixel offsets leave 32 bits: one launch after the other
         batched = fast::engine2_supports(a) && fast::engine2_batch_fits(a, n);
+        if (multi) sdet_doubles = fast::engine2_sdet_doubles(a, n);
+    }
+    if (multi) {
+        // ONE walk for all detectors needs one emission law and one set of tables: same limb flag and wavelength everywhere,
+        // star source over a black surface (the thermal / surface peel-offs keep their per-detector launches)
+        bool same = true;
+        for (int k = 1; k < n; ++k) same = same && Ls[k].limb_emission == L0.limb_emission && Ls[k].wl_index == L0.wl_index;
+        if (!same) return fail(ctx, -1, "run_multi: the detectors of one walk must share limb_emission and wl_index");
+        if (!(batched && L0.photon_source == 1 && !(L0.surface_albedo > 0.0)))
+            return run_batch_impl(ctx, Ls, n, det_sum, flux, err_hist, stats, false);      // independent walks: same expectation values
     }
     if (stats) std::memset(stats, 0, sizeof(*stats));
     if (err_hist) std::memset(err_hist, 0, ARTES_ERR_SLOTS * sizeof(uint64_t));
@@ -748,7 +761,7 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         g[7] = Ls[k].limb_emission ? 1.0 : 0.0; g[8] = t.det_sph_theta; g[9] = t.det_sph_phi;
         g[10] = (double)ctx->wl_depth[Ls[k].wl_index]; g[11] = (double)Ls[k].wl_index;
     }
-    const unsigned long long total = P * (unsigned long long)n;
+    const unsigned long long total = multi ? P : P * (unsigned long long)n;
     unsigned long long per = total / ndev, rem = total % ndev, off = 0;
     for (int i = 0; i < ndev; ++i) {
         DeviceState& d = ctx->devs[i];
@@ -769,7 +782,9 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         fill_launch(L0, a.L);
         a.L.n_photons = per + ((unsigned long long)i < rem ? 1 : 0);
         a.L.id_base = L0.photon_id_base + off;
-        a.L.n_batch = n; a.L.per_launch = P; a.L.batch_base = L0.photon_id_base; a.L.geo = d.geo; a.L.wl_batch = wl_batch ? 1 : 0;
+        a.L.n_batch = n; a.L.per_launch = P; a.L.batch_base = L0.photon_id_base; a.L.geo = d.geo; a.L.wl_batch = (wl_batch && !multi) ? 1 : 0;
+        a.L.multi = multi ? 1 : 0; a.L.sdet_doubles = sdet_doubles;
+        if (multi) a.T = tables_of(ctx, d, L0.wl_index);
         off += a.L.n_photons;
         d.n_photons = a.L.n_photons;
         a.O.det = d.out_d;
@@ -829,6 +844,7 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         }
         if (flux) { flux[2 * k] = h[(size_t)n * 10 * npx + 2 * k]; flux[2 * k + 1] = h[(size_t)n * 10 * npx + 2 * k + 1]; }
     }
+    if (hu[ARTES_ERR_SLOTS - 1]) return fail(ctx, -5, "transport kernel stopped by its watchdog (no scheduling progress): results discarded");
     if (err_hist) for (int c = 0; c < ARTES_ERR_SLOTS; ++c) err_hist[c] = hu[c];
     if (stats) {
         const unsigned long long* u = hu.data() + ARTES_ERR_SLOTS;
@@ -840,6 +856,17 @@ int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, dou
         stats->kernel_ms = kernel_ms; stats->reduce_ms = reduce_ms; stats->h2d_ms = ctx->last_h2d_ms; stats->d2h_ms = d2h;
     }
     return 0;
+}
+
+int artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, double* det_sum, double* flux,
+                        uint64_t* err_hist, artes_stats_t* stats) {
+    return run_batch_impl(ctx, Ls, n, det_sum, flux, err_hist, stats, false);
+}
+
+// ONE random walk of n_photons packets observed by all n detectors (see include/artes_gpu.h)
+int artes_gpu_run_multi(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, double* det_sum, double* flux,
+                        uint64_t* err_hist, artes_stats_t* stats) {
+    return run_batch_impl(ctx, Ls, n, det_sum, flux, err_hist, stats, true);
 }
 
 int artes_gpu_nccl_unique_id(void* id_out) {

@@ -1021,7 +1021,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     __syncthreads();
     for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; X.I(I_INFO, i) = 0; }   // every slot starts by asking for a photon
     if (tid < 16) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
-    if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; }
+    if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; X.misc[3] = 0; X.misc[4] = 0; }
     __syncthreads();
 }
 
@@ -1041,16 +1041,36 @@ __constant__ signed char c_list[4][8] = {
 struct Marcher {
     int slot, c0, dr, cell12, info;
     double t, acc, tr, tt, tp, hbn, D0, iq, lim, kap, ds;
+    double kapn;                 // opacity of the NEXT radial layer in the direction of motion, loaded one step ahead: the load's
+                                 // latency (an L2 round trip on the large grids) overlaps a whole step instead of ending it
     const double* kb;            // kext + nr*(c1 + nt*c2): the opacity row of the ray's (theta, phi) column
     int nr, nt, depth;           // launch invariants kept in registers (the kernel parameters live in constant memory)
     const double* kext;
+    unsigned r2s;                // shared-space byte address of the squared radii: ld.shared with a 32-bit address instead of a generic
+                                 // pointer (the compiler rebuilt the generic shared base with S2R + LEA in every step)
     int tl; unsigned long long th, pid;   // walk recorder (trace hook only; dead code otherwise)
     double s0w;                           // Stokes I of the photon (latitudinal flow counters only)
 
     __device__ __forceinline__ void init(const DevTables& T) {
         slot = -1; c0 = cell12 = info = 0; dr = 1;
-        t = acc = tr = tt = tp = hbn = D0 = iq = lim = kap = 0.0; ds = 1.0;
-        nr = T.nr; nt = T.nt; depth = T.cell_depth; kext = T.kext; kb = T.kext;
+        t = acc = tr = tt = tp = hbn = D0 = iq = lim = kap = kapn = 0.0; ds = 1.0;
+        nr = T.nr; nt = T.nt; depth = T.cell_depth; kext = T.kext; kb = T.kext; r2s = 0u;
+    }
+    template <class Sh>
+    __device__ __forceinline__ void bind(const Sh& X) {
+        unsigned long long sh;      // volatile: converted ONCE and kept, not rematerialised (S2UR + ULEA) at every use
+        asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(sh) : "l"((unsigned long long)X.r2));
+        r2s = (unsigned)sh;
+    }
+    // opacity of layer c0 and, ahead of time, of its neighbour in the direction of motion (index clamped to the column)
+    __device__ __forceinline__ void load_kap() {
+        kap = __ldg(kb + c0);
+        kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
+    }
+    __device__ __forceinline__ double r2_at(int i) const {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(r2s + 8u * (unsigned)i));
+        return v;
     }
 
     template <class Sh>
@@ -1069,7 +1089,7 @@ struct Marcher {
             kb += (size_t)wl_of(X, A, kbi) * A.T.cells;
             depth = depth_of(X, A, kbi);
         }
-        kap = __ldg(kb + c0);
+        load_kap();
         if (Sh::TRACE) {
             tl = X.I(I_TLEN, s);
             th = (unsigned long long)(unsigned)X.I(I_THLO, s) | ((unsigned long long)(unsigned)X.I(I_THHI, s) << 32);
@@ -1104,16 +1124,19 @@ struct Marcher {
         const int f = c0 + up;
         if (Sh::GEN && A.L.flow_theta && (info & 3) == K_WALK)      // add_flow :5016-5047, radial crossings (:730-735)
             atomicAdd(A.O.flow4 + (size_t)4 * ((kb - kext) + c0) + (up ? 0 : 1), s0w);
-        if (f == nr) return O_EXIT;
-        if (f == depth) return O_SURF;
+        // outward the ray can only leave through the top face, inward only reach the surface face: one comparison.  The surface
+        // face of a plain launch is read from the constant bank (as a register it was spilled and reloaded in every step).
+        const int dep = (Sh::BATCH && A.L.wl_batch) ? depth : A.T.cell_depth;
+        if (f == (up ? nr : dep)) return up ? O_EXIT : O_SURF;
         c0 += dr;
-        kap = __ldg(kb + c0);     // (measured: reading four layers at once with one 256-bit load and selecting is slower)
+        kap = kapn;               // loaded one step ago (measured: reading four layers at once with one 256-bit load and selecting is slower)
         // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
-        double disc = fma(X.r2[c0 + up], iq, D0);
+        double disc = fma(r2_at(c0 + up), iq, D0);
         if (disc < 0.0) {
-            if (dr < 0) { dr = 1; ds = 1.0; disc = fma(X.r2[c0 + 1], iq, D0); }
-            if (disc < 0.0) { tr = RAY_NONE; return O_NONE; }
+            if (dr < 0) { dr = 1; ds = 1.0; disc = fma(r2_at(c0 + 1), iq, D0); }
+            if (disc < 0.0) { tr = RAY_NONE; kapn = kap; return O_NONE; }
         }
+        kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
         tr = fma(ds, fsqrt(disc), hbn);
         return O_NONE;
     }
@@ -1341,7 +1364,7 @@ __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, 
             // ---- the walk to the detector (:4739-4761), in the lane; stops once tau >= 50 (the reference drops those, :4765)
             if (pix >= 0) {
                 Marcher M;
-                M.init(T);
+                M.init(T); M.bind(X);
                 RayK Kc;
                 double hbn, D0, iq;
                 ray_consts(T, px, py, pz, G.d0, G.d1, G.d2, Kc, hbn, D0, iq);
@@ -1354,7 +1377,7 @@ __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, 
                 M.info = K_PEEL | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
                 M.dr = inward ? -1 : 1; M.ds = inward ? -1.0 : 1.0;
                 M.kb = M.kext + T.nr * (c1 + T.nt * c2);
-                M.kap = kap_c;
+                M.load_kap();
                 M.slot = sp;
                 unsigned n_step = 0;
                 int out;
@@ -1377,7 +1400,7 @@ __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, 
                     }
                     M.cell12 = (cc1 << 10) | (cc2 << 20);
                     M.kb = M.kext + T.nr * (cc1 + T.nt * cc2);
-                    M.kap = __ldg(M.kb + M.c0);
+                    M.load_kap();
                 }
                 C.n_cf += n_step;
                 if (out == O_ERR) { err_count(A, 31); err_count(A, 43); ++C.n_err; }
@@ -1417,6 +1440,22 @@ __device__ __forceinline__ bool run_event(const Sh& X, const KernelArgs& A, int 
     return push;
 }
 
+// multi-detector walks: the event of list l for a batch of n slots; returns the list the lane's slot goes on next (-1: none)
+template <class Sh>
+__device__ __forceinline__ int run_event_md(const Sh& X, const KernelArgs& A, int l, int n, bool valid, int s, Cnt& C) {
+    RaySpec rs;
+    rs.make = false;
+    int tgt;
+    if (l == L_FAN) { ev_fan(X, A, n, s, C); tgt = valid ? L_SC : -1; }
+    else if (l == L_SC) tgt = ev_scatter_md(X, A, valid, s, C, rs);
+    else if (l == L_H) tgt = ev_survive(X, A, valid, s, C);
+    else if (l == L_RES) tgt = ev_resolve(X, A, valid, s) ? L_RDY : -1;
+    else if (l == L_PRE) tgt = ev_pre(X, A, valid, s, C, rs) ? L_RDY : -1;
+    else tgt = ev_emit(X, A, valid, s, C, rs) ? L_RDY : -1;
+    if (rs.make) ray_setup(X, A.T, s, rs.x, rs.y, rs.z, rs.n0, rs.n1, rs.n2, rs.c0, rs.c1, rs.c2, rs.sface, rs.kind, rs.lim, rs.acc0, rs.pk);
+    return tgt;
+}
+
 __device__ __forceinline__ void flush_counters(const KernelArgs& A, const Cnt& C) {
     const int lane = threadIdx.x & 31;
     unsigned long long v[7] = {C.n_emit, C.n_cf, C.n_sc, C.n_peel, C.n_surf, C.n_draw, C.n_err};
@@ -1446,7 +1485,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
     Marcher M[NRAY];              // NRAY independent rays per lane: their dependency chains interleave (ILP)
 #pragma unroll
-    for (int j = 0; j < NRAY; ++j) M[j].init(T);
+    for (int j = 0; j < NRAY; ++j) { M[j].init(T); M[j].bind(X); }
     volatile int* vhead = X.head;
     volatile int* vtail = X.tail;
 
@@ -1561,32 +1600,47 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
 // id to appear, clears the cell and fences before touching the slot.  A warp with (almost) nothing to march
 // and no ready ray to claim also takes partial batches, which is what drains the lists at the end.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ring_take(volatile short* e) {
+// Watchdog.  A list cell is published by exactly one producer and a consumer may wait for it; if the scheduling logic were ever
+// wrong such a wait (or a block whose warps all find nothing to do) would hang the GPU.  Waits therefore count their polls:
+// after ~10 s without progress a warp raises the launch's abort word (error slot 63), every loop that sees it leaves, and the host
+// returns an error instead of a hung device.  The polls of a healthy launch end within microseconds, the counter costs nothing.
+constexpr int ERR_WATCHDOG = 63;
+__device__ __forceinline__ bool spin_expired(unsigned& spin, unsigned long long* abort_word) {
+    if ((++spin & 0xfffffu) != 0u) return false;
+    if (*(volatile unsigned long long*)abort_word) return true;
+    if (spin >= (400u << 20)) { atomicExch(abort_word, 1ull); return true; }
+    return false;
+}
+__device__ __forceinline__ int ring_take(volatile short* e, unsigned long long* abort_word) {
     short v;
-    do { v = *e; } while (v < 0);
+    unsigned spin = 0;
+    do { v = *e; if (v < 0 && spin_expired(spin, abort_word)) return 0; } while (v < 0);
     *e = (short)-1;
     return (int)v;
 }
-__device__ __forceinline__ void ring_put(volatile short* e, int s) {
-    while (*e >= 0) { }
+__device__ __forceinline__ void ring_put(volatile short* e, int s, unsigned long long* abort_word) {
+    unsigned spin = 0;
+    while (*e >= 0) { if (spin_expired(spin, abort_word)) return; }
     *e = (short)s;
 }
 
-template <int NT, int NP, int MINB, bool TR, bool GN, bool BT = false>
+template <int NT, int NP, int MINB, bool TR, bool GN, bool BT = false, bool MD = false>
 __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ double smraw[];
     const DevTables& T = A.T;
-    using Sh = ShT<NP, TR, GN, BT>;
+    using Sh = ShT<NP, TR, GN, BT, MD>;
     Sh X;
-    block_setup<NT, NP, TR, GN, BT>(A, smraw, X, true);
+    block_setup<NT, NP, TR, GN, BT, MD>(A, smraw, X, true);
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     Cnt C; C.n_cf = 0; C.n_emit = C.n_sc = C.n_peel = C.n_surf = C.n_err = C.n_draw = 0;
-    Marcher M; M.init(T);
+    Marcher M; M.init(T); M.bind(X);
     volatile int* vhead = X.head;
     volatile int* vtail = X.tail;
     volatile int* vmisc = X.misc;
     const int starve = 8;                                        // take partial batches when fewer lanes than this march
+    unsigned idle_turns = 0;                                     // consecutive turns of the loop below without a ray or an event (watchdog)
+    int seen_progress = 0;
     // (Measured and dropped: soft warp specialisation -- the last warps of a block only run events, the others only march --
     // to shrink the code each warp loops over: 5-10 % slower on every workload, the event warps idle too often.)
 #ifdef E2_STATS
@@ -1600,6 +1654,20 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         // every slot retired: the block is done.  One lane reads, so that the whole warp leaves together (a volatile read per lane
         // is not warp-uniform by construction, and a warp that splits here would wait for its exited lanes in the ballots below)
         if (__shfl_sync(FULL, (int)vmisc[0], 0) >= NP) break;
+        // watchdog: this warp found neither a ray to step nor an event to run for 65 536 turns.  If no other warp of the block
+        // made progress either (misc[4] counts their busy turns) for ~1e8 of this warp's turns (seconds), or another warp raised
+        // the abort word, leave.  (The drain of a launch is NOT idle in this sense: the warps that finish the last photons keep counting.)
+        if (idle_turns && (idle_turns & 0xffffu) == 0u) {
+            int stop = 0;
+            if (lane == 0) {
+                const int prog = vmisc[4];
+                if (prog != seen_progress) { seen_progress = prog; idle_turns = 0u; }
+                stop = *(volatile unsigned long long*)(A.O.err + ERR_WATCHDOG) != 0ull;
+                if (!stop && idle_turns >= (1u << 27)) { atomicExch(A.O.err + ERR_WATCHDOG, 1ull); stop = 1; }
+            }
+            idle_turns = __shfl_sync(FULL, idle_turns, 0);
+            if (__shfl_sync(FULL, stop, 0)) break;
+        }
         // ---- free lanes claim ready rays
         const unsigned fm = __ballot_sync(FULL, M.slot < 0);
 #ifdef E2_STATS
@@ -1624,7 +1692,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             rdy_empty = n < __popc(fm);
             const int rank = __popc(fm & lt);
             if (M.slot < 0 && rank < n) {
-                const int s = ring_take(&X.Q(L_RDY, base + rank));
+                const int s = ring_take(&X.Q(L_RDY, base + rank), A.O.err + ERR_WATCHDOG);
                 __threadfence_block();
                 M.load(X, A, s);
             }
@@ -1658,7 +1726,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             int base = 0;
             if (lane == leader && lst >= 0) base = atomicAdd(X.tail + lst, __popc(g));
             base = __shfl_sync(FULL, base, leader);
-            if (lst >= 0) { ring_put(&X.Q(lst, base + __popc(g & lt)), M.slot); M.slot = -1; }
+            if (lst >= 0) { ring_put(&X.Q(lst, base + __popc(g & lt)), M.slot, A.O.err + ERR_WATCHDOG); M.slot = -1; }
         }
         // ---- events: a full batch if there is one; a partial one if this warp has little else to do
         int av = 0;
@@ -1667,8 +1735,20 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
         int l = -1;
+        if (nactive == 0 && !anym) ++idle_turns;
+        else { idle_turns = 0u; if (lane == 0) vmisc[4] = vmisc[4] + 1; }      // busy turn: tell the idle warps of the block
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
-        if (fullm)
+        if (Sh::MULTI) {
+            // multi-detector walks: a FAN event is a full warp's work for ONE photon, so any waiting photon is taken (a few at a
+            // time: the event is long); the others as usual
+            if (anym & (1u << L_FAN)) l = L_FAN;
+            else if (fullm)
+                l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_H)) ? L_H : (fullm & (1u << L_SC)) ? L_SC
+                    : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
+            else if (anym && rdy_empty && nactive < starve)
+                l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_H)) ? L_H : (anym & (1u << L_SC)) ? L_SC
+                    : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
+        } else if (fullm)
             l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
                 : (fullm & (1u << L_SURF)) ? L_SURF : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
         else if (anym && rdy_empty && nactive < starve)
@@ -1678,30 +1758,49 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             int base = 0, n = 0;
             if (lane == 0) {
                 const int h = vhead[l];
-                n = min(32, vtail[l] - h);
+                n = min((Sh::MULTI && l == L_FAN) ? 4 : 32, vtail[l] - h);
                 if (n > 0 && atomicCAS(X.head + l, h, h + n) == h) base = h; else n = 0;
             }
             base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
             if (n > 0) {
                 const bool valid = lane < n;
                 int s = 0;
-                if (valid) s = ring_take(&X.Q(l, base + lane));
+                if (valid) s = ring_take(&X.Q(l, base + lane), A.O.err + ERR_WATCHDOG);
                 __threadfence_block();
 #ifdef E2_STATS
                 st_evb++; st_evl += n;
 #endif
-                const bool push = run_event(X, A, l, valid, s, C);
-                __threadfence_block();
-                const unsigned pm = __ballot_sync(FULL, push);
-                if (pm) {
-                    const int leader = __ffs(pm) - 1;
-                    int pb = 0;
-                    if (lane == leader) pb = atomicAdd(X.tail + L_RDY, __popc(pm));
-                    pb = __shfl_sync(FULL, pb, leader);
-                    if (push) ring_put(&X.Q(L_RDY, pb + __popc(pm & lt)), s);
+                if (Sh::MULTI) {
+                    const int tgt = run_event_md(X, A, l, n, valid, s, C);
+                    __threadfence_block();
+                    if (__any_sync(FULL, tgt >= 0)) {
+                        const unsigned g = __match_any_sync(FULL, tgt);
+                        const int leader = __ffs(g) - 1;
+                        int pb = 0;
+                        if (lane == leader && tgt >= 0) pb = atomicAdd(X.tail + tgt, __popc(g));
+                        pb = __shfl_sync(FULL, pb, leader);
+                        if (tgt >= 0) ring_put(&X.Q(tgt, pb + __popc(g & lt)), s, A.O.err + ERR_WATCHDOG);
+                    }
+                } else {
+                    const bool push = run_event(X, A, l, valid, s, C);
+                    __threadfence_block();
+                    const unsigned pm = __ballot_sync(FULL, push);
+                    if (pm) {
+                        const int leader = __ffs(pm) - 1;
+                        int pb = 0;
+                        if (lane == leader) pb = atomicAdd(X.tail + L_RDY, __popc(pm));
+                        pb = __shfl_sync(FULL, pb, leader);
+                        if (push) ring_put(&X.Q(L_RDY, pb + __popc(pm & lt)), s, A.O.err + ERR_WATCHDOG);
+                    }
                 }
             }
         }
+    }
+    // block-private detector image -> the global one (every warp leaves the loop only when all slots are retired, i.e. after
+    // the last deposit of the block)
+    if (X.sdet) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < A.L.sdet_doubles; i += NT) { const double v = X.sdet[i]; if (v != 0.0) atomicAdd(A.O.det + i, v); }
     }
 #ifdef E2_STATS
     if (lane == 0) {

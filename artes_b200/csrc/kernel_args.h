@@ -57,6 +57,8 @@ struct LaunchArgs {
     const double* geo;
     int n_batch;
     int wl_batch;                    // 1: the launches of the batch use different wavelengths: kext / cellrec are [n_wl][cells], geo[k][10..11] = cell_depth, wavelength index
+    int multi;                       // 1: ONE walk of n_photons packets peels off towards all n_batch detectors of geo (artes_gpu_run_multi)
+    int sdet_doubles;                // > 0: the detector images ([n_batch][10][ny][nx] doubles) are accumulated per block in shared memory and added to det at the end
 };
 
 // Device accumulators of one launch.

@@ -23,7 +23,7 @@ _up = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "artes_gpu_create", "artes_gpu_destroy", "artes_gpu_last_error", "artes_gpu_abi_version",
     "artes_gpu_set_grid", "artes_gpu_set_wavelength", "artes_gpu_set_wavelength_dense", "artes_gpu_set_wavelength_dense_wl",
-    "artes_gpu_set_wavelengths", "artes_gpu_run", "artes_gpu_run_batch", "artes_gpu_run_async", "artes_gpu_wait", "artes_gpu_nccl_unique_id",
+    "artes_gpu_set_wavelengths", "artes_gpu_run", "artes_gpu_run_batch", "artes_gpu_run_multi", "artes_gpu_run_async", "artes_gpu_wait", "artes_gpu_nccl_unique_id",
     "artes_gpu_nccl_init_rank", "artes_gpu_trace", "artes_gpu_cell_face", "artes_gpu_device_info",
     "artes_gpu_fma_peak", "artes_gpu_last_engine",
 ]
@@ -58,6 +58,7 @@ def load():
     lib.artes_gpu_run.argtypes = [C.c_void_p, C.POINTER(Launch), _dp, _dp, C.c_void_p, C.c_void_p, _up, C.POINTER(Stats)]
     lib.artes_gpu_run_async.argtypes = [C.c_void_p, C.POINTER(Launch)]
     lib.artes_gpu_run_batch.argtypes = [C.c_void_p, C.POINTER(Launch), C.c_int, _dp, _dp, _up, C.POINTER(Stats)]
+    lib.artes_gpu_run_multi.argtypes = [C.c_void_p, C.POINTER(Launch), C.c_int, _dp, _dp, _up, C.POINTER(Stats)]
     lib.artes_gpu_wait.argtypes = [C.c_void_p, _dp, _dp, C.c_void_p, C.c_void_p, _up, C.POINTER(Stats)]
     lib.artes_gpu_nccl_unique_id.argtypes = [C.c_void_p]
     lib.artes_gpu_nccl_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -218,7 +219,11 @@ class GpuTransport:
                                            err, C.byref(st)), "artes_gpu_run")
         return self._result(launch, det, flux, err, f4, f3, st)
 
-    def run_batch(self, launches):
+    def run_multi(self, launches):
+        """ONE walk observed by all detectors of `launches` (include/artes_gpu.h: artes_gpu_run_multi)."""
+        return self.run_batch(launches, multi=True)
+
+    def run_batch(self, launches, multi=False):
         """Launches that differ only in the detector direction, as one kernel launch (include/artes_gpu.h)."""
         n = len(launches)
         arr = (Launch * n)(*launches)
@@ -227,7 +232,8 @@ class GpuTransport:
         flux = np.zeros(2 * n)
         err = np.zeros(ERR_SLOTS, dtype=np.uint64)
         st = Stats()
-        self._check(self.lib.artes_gpu_run_batch(self.h, arr, n, det, flux, err, C.byref(st)), "artes_gpu_run_batch")
+        fn = self.lib.artes_gpu_run_multi if multi else self.lib.artes_gpu_run_batch
+        self._check(fn(self.h, arr, n, det, flux, err, C.byref(st)), "artes_gpu_run_multi" if multi else "artes_gpu_run_batch")
         return dict(det=det.reshape(n, 3, 4, L0.ny, L0.nx), flux=flux.reshape(n, 2), err=err, stats=st.as_dict())
 
     def run_async(self, launch):

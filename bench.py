@@ -155,6 +155,9 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "faithful"])
     ap.add_argument("--batch", type=int, default=0, help="N > 1: every step is ONE batched launch (artes_gpu_run_batch) of N launches x --photons "
                                                          "packets whose det_phi sweeps 0..180 deg like the phase-curve loop src/ARTES.f90:215-245")
+    ap.add_argument("--multi", type=int, default=0, help="N > 1: every step is ONE walk of --photons packets observed by N detectors "
+                                                         "(artes_gpu_run_multi; det_phi = 0 .. 167.5 deg like the non-limb angles of a phase curve); "
+                                                         "value counts N x photons detector-packets, i.e. what a per-detector loop would have to walk")
     ap.add_argument("--cpu-sample", type=float, default=300000, help="photons of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -166,7 +169,9 @@ def main():
     from tools import atmospheres as A
     builder, wl_kw, default_p = WORKLOADS[args.workload]
     wl_kw = dict(wl_kw)
-    multi_wl = bool(wl_kw.pop("multi_wl", False)) and args.batch <= 1 and args.mode == "fast"
+    multi_wl = bool(wl_kw.pop("multi_wl", False)) and args.batch <= 1 and args.multi <= 1 and args.mode == "fast"
+    if args.multi > 1:
+        args.batch = args.multi
     atm = getattr(A, builder)()
     P = int(args.photons) if args.photons else (1_000_000 if args.batch > 1 else default_p)
     NB = args.batch if args.batch > 1 else (len(atm.wavelengths) if multi_wl else 1)
@@ -176,7 +181,10 @@ def main():
               "l2": "tables (<= few MB) are L2-resident by design; 256 MiB memset flushes L2 between steps"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
-    if multi_wl:
+    if args.multi > 1:
+        config["batch"] = (f"ONE walk of {P} packets per step observed by {NB} detectors (artes_gpu_run_multi), det_phi = 0..167.5 deg; "
+                           f"value = {NB} x packets / s (detector-packets: the packets a per-detector loop walks for the same curve)")
+    elif multi_wl:
         config["batch"] = f"{NB} wavelengths x {P} packets per step as one kernel (artes_gpu_set_wavelengths + artes_gpu_run_batch)"
     elif NB > 1:
         config["batch"] = f"{NB} launches x {P} packets per step as one kernel (artes_gpu_run_batch), det_phi = 0..180 deg"
@@ -242,12 +250,17 @@ def main():
     def launches(tr, packets, base):
         if multi_wl:
             return [tr.launch_struct(packets, seed=4, photon_id_base=base, wl_index=k) for k in range(NB)]
+        if args.multi > 1:
+            return [tr.launch_struct(packets, seed=4, photon_id_base=base, det_phi=max(math.radians(2.5 * k), 1e-3)) for k in range(NB)]
         return [tr.launch_struct(packets, seed=4, photon_id_base=base, det_phi=math.pi * k / (NB - 1)) for k in range(NB)]
+
+    def run_many(tr, ls):
+        return tr.gpu.run_multi(ls) if args.multi > 1 else tr.gpu.run_batch(ls)
 
     def step(i):
         base = adist.step_base(i, world, rank, P * NB)   # disjoint photon ids for every step and rank
         if NB > 1:
-            return t.gpu.run_batch(launches(t, P, base))
+            return run_many(t, launches(t, P, base))
         L = t.launch_struct(P, seed=4, photon_id_base=base)
         return t.gpu.run(L)
 
@@ -315,12 +328,12 @@ def main():
     shards = world if world > 1 else 2          # one GPU: two half-launches on the same device added on the host
     base0 = 1 << 40                             # ids no timed step used
     if world > 1:
-        rs = t.gpu.run_batch(launches(t, pc, base0 + rank * pc * NB)) if NB > 1 else t.gpu.run(t.launch_struct(pc, seed=4, photon_id_base=base0 + rank * pc))
+        rs = run_many(t, launches(t, pc, base0 + rank * pc * NB)) if NB > 1 else t.gpu.run(t.launch_struct(pc, seed=4, photon_id_base=base0 + rank * pc))
         det_n = rs["det"]
     else:
         det_n = None
         for r_ in range(shards):
-            rs = t.gpu.run_batch(launches(t, pc, base0 + r_ * pc * NB)) if NB > 1 else t.gpu.run(t.launch_struct(pc, seed=4, photon_id_base=base0 + r_ * pc))
+            rs = run_many(t, launches(t, pc, base0 + r_ * pc * NB)) if NB > 1 else t.gpu.run(t.launch_struct(pc, seed=4, photon_id_base=base0 + r_ * pc))
             det_n = rs["det"].copy() if det_n is None else det_n + rs["det"]
     shard_check = None
     if rank == 0:
@@ -329,7 +342,7 @@ def main():
         if NB > 1:       # launch k of shard r walks ids base0 + r*pc*NB + k*pc + [0, pc): the same ids, shard by shard
             det_1 = None
             for r_ in range(shards):
-                rr = t1.gpu.run_batch(launches(t1, pc, base0 + r_ * pc * NB))
+                rr = run_many(t1, launches(t1, pc, base0 + r_ * pc * NB))
                 det_1 = rr["det"].copy() if det_1 is None else det_1 + rr["det"]
         else:
             det_1 = t1.gpu.run(t1.launch_struct(pc * shards, seed=4, photon_id_base=base0))["det"]

@@ -181,6 +181,20 @@ int  artes_gpu_wait(artes_gpu_ctx* ctx, double* det_sum, double* flux, double* f
 int  artes_gpu_run_batch(artes_gpu_ctx* ctx, const artes_launch_t* launches, int n,
                          double* det_sum, double* flux, uint64_t* err_hist, artes_stats_t* stats);
 
+/* ONE random walk observed by n detectors.  The reference repeats the whole walk for every detector azimuth of a
+ * phase curve (src/ARTES.f90:215-245); peel-off (peel_photon :4710-4990) is a next-event estimate that does not disturb
+ * the walk, so a single walk of launches[0].n_photons packets can peel off towards ALL n detector directions at every
+ * scattering.  Every detector receives exactly the deposits the reference's run with that det_theta / det_phi would make
+ * along this walk: image k has the expectation value and the per-image noise of artes_gpu_run with launches[k] and the
+ * same n_photons, but the n images share the walks, i.e. their noise is CORRELATED between detectors instead of
+ * independent (a phase curve comes out smooth; error bars per point stay valid, chi^2 over points does not).
+ * The launches may differ in det_theta / det_phi only; limb_emission (a different emission law, :1041-1055) and wl_index
+ * must be equal, so a phase curve takes two calls: the angles below 170 deg and the limb-biased ones.
+ * Same outputs as artes_gpu_run_batch.  Star source over a black surface in fast mode; anything else (thermal source,
+ * reflecting surface, faithful mode, oblate planet) runs as artes_gpu_run_batch, i.e. with independent walks. */
+int  artes_gpu_run_multi(artes_gpu_ctx* ctx, const artes_launch_t* launches, int n,
+                         double* det_sum, double* flux, uint64_t* err_hist, artes_stats_t* stats);
+
 /* ---- multi-process NCCL (one process per GPU, e.g. under torchrun / MPI) ---------------------- */
 
 #define ARTES_NCCL_ID_BYTES 128

@@ -66,41 +66,116 @@ def _points_as_image(dets):
     return np.concatenate(dets, axis=-1)
 
 
-def test_phase_curve_all_73_angles(atmospheres, oracle_factory, gpu_factory):
-    """C2: the full phase curve of `run` (:215-245; 73 detector azimuths, limb-biased emission from 170 deg on) as batched
-    launches on the GPU against the oracle's 73 separate launches: I, Q, U and P of every angle through the gate."""
-    atm = atmospheres("c2_hg_deck")
-    o, _ = oracle_factory(atm)
-    g, _ = gpu_factory(atm)
-    xm = 1.3 * atm.rfront[-1]
+def _phase_angles():
+    """det_phi of the 73 calls of `run` (:215-245), clamped 1e-3 rad off 0 and pi like :492-493, and their limb flags (:1041)."""
     phis = [1.e-5 * math.pi / 180.0, 2.5 * math.pi / 180.0]
     while len(phis) < 72:
         phis.append(phis[-1] + 2.5 * math.pi / 180.0)
     phis.append((180.0 - 1e-5) * math.pi / 180.0)
-    assert len(phis) == 73
-    # the reference keeps det_phi 1e-3 rad away from 0 and pi (:492-493)
-    phis_c = [min(max(p, 1.e-3), math.pi - 1.e-3) for p in phis]
-    K, n = 32, 1500
-    kw = dict(x_max=xm, y_max=xm, nx=1, ny=1)
     limb = [int(p * 180.0 / math.pi >= 170.0) for p in phis]
-    assert sum(limb) == 5
+    return [min(max(p, 1.e-3), math.pi - 1.e-3) for p in phis], limb
+
+
+PHASE_K, PHASE_N = 32, 1500
+
+
+@pytest.fixture(scope="module")
+def phase_oracle_batches(atmospheres, oracle_factory):
+    """The oracle's phase curve of C2: 32 independent batches of 73 separate launches (its own generator)."""
     import oracle_lib
-    ba, bb = [], []
-    for i in range(K):
-        ba.append(_points_as_image([o.run(make_launch(n_photons=n, seed=20000 + 73 * i + a, det_phi=phis_c[a], limb_emission=limb[a], **kw),
-                                          rng=oracle_lib.RNG_MZ)["det"] for a in range(73)]))
-        Ls = [make_launch(mode=abi.MODE_FAST, n_photons=n, seed=9, photon_id_base=i * 73 * n, det_phi=phis_c[a], limb_emission=limb[a], **kw)
-              for a in range(73)]
-        r = g.run_batch(Ls)
-        assert r["stats"]["reserved"] == 1 and g.last_engine() == 2           # ONE kernel for the 73 angles
-        bb.append(_points_as_image(list(r["det"])))
+    atm = atmospheres("c2_hg_deck")
+    o, _ = oracle_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    phis, limb = _phase_angles()
+    assert len(phis) == 73 and sum(limb) == 5
+    kw = dict(x_max=xm, y_max=xm, nx=1, ny=1)
+    return [_points_as_image([o.run(make_launch(n_photons=PHASE_N, seed=20000 + 73 * i + a, det_phi=phis[a], limb_emission=limb[a], **kw),
+                                    rng=oracle_lib.RNG_MZ)["det"] for a in range(73)]) for i in range(PHASE_K)]
+
+
+def _check_phase_curve(ba, bb, what):
     rep = stat_gate.z_report(ba, bb)
-    stat_gate.assert_gate(rep, names=("I", "Q", "U", "P"), min_valid=60, what="c2 phase curve")
+    stat_gate.assert_gate(rep, names=("I", "Q", "U", "P"), min_valid=60, what=what)
     # the curve itself: bright at full phase, faint towards new phase, polarised in between
     tot = np.sum(bb, axis=0)
     assert tot[0, 0, 0, 0] > 5 * tot[0, 0, 0, 60]
     p = np.hypot(tot[0, 1, 0], tot[0, 2, 0]) / tot[0, 0, 0]
     assert p[36] > 3 * p[1]
+
+
+def test_phase_curve_all_73_angles(atmospheres, gpu_factory, phase_oracle_batches):
+    """C2: the full phase curve of `run` (:215-245; 73 detector azimuths, limb-biased emission from 170 deg on) as batched
+    launches on the GPU (independent walks per angle) against the oracle's 73 separate launches: I, Q, U and P of every
+    angle through the gate."""
+    atm = atmospheres("c2_hg_deck")
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    phis, limb = _phase_angles()
+    kw = dict(x_max=xm, y_max=xm, nx=1, ny=1)
+    bb = []
+    for i in range(PHASE_K):
+        Ls = [make_launch(mode=abi.MODE_FAST, n_photons=PHASE_N, seed=9, photon_id_base=i * 73 * PHASE_N, det_phi=phis[a], limb_emission=limb[a], **kw)
+              for a in range(73)]
+        r = g.run_batch(Ls)
+        assert r["stats"]["reserved"] == 1 and g.last_engine() == 2           # ONE kernel for the 73 angles
+        bb.append(_points_as_image(list(r["det"])))
+    _check_phase_curve(phase_oracle_batches, bb, "c2 phase curve, batched launches")
+
+
+def test_phase_curve_single_walk_multi_detector(atmospheres, gpu_factory, phase_oracle_batches):
+    """The same phase curve from ONE walk per packet observed by all detectors (artes_gpu_run_multi; the angles below
+    170 deg in one call, the five limb-biased ones in a second): every angle through the same gate against the oracle's
+    per-angle runs.  Batches are independent walks, so the batch variance is the photon noise of each angle."""
+    atm = atmospheres("c2_hg_deck")
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    phis, limb = _phase_angles()
+    kw = dict(x_max=xm, y_max=xm, nx=1, ny=1)
+    bb = []
+    for i in range(PHASE_K):
+        dets = [None] * 73
+        for flag in (0, 1):
+            idx = [a for a in range(73) if limb[a] == flag]
+            Ls = [make_launch(mode=abi.MODE_FAST, n_photons=PHASE_N, seed=19, photon_id_base=(2 * i + flag) * PHASE_N, det_phi=phis[a],
+                              limb_emission=flag, **kw) for a in idx]
+            r = g.run_multi(Ls)
+            assert r["stats"]["reserved"] == 1 and g.last_engine() == 2
+            assert r["stats"]["n_emit"] == PHASE_N                              # ONE walk per packet, whatever the number of detectors
+            for j, a in enumerate(idx):
+                dets[a] = r["det"][j]
+        bb.append(_points_as_image(dets))
+    _check_phase_curve(phase_oracle_batches, bb, "c2 phase curve, single walk")
+
+
+@pytest.mark.parametrize("name,extra", [("c2_hg_deck", dict(nx=1, ny=1)), ("c4_mie_patches", dict(nx=2, ny=2)), ("c5_scale", dict(nx=40, ny=40))])
+def test_single_walk_detectors_equal_the_launches_that_share_its_photon_ids(atmospheres, gpu_factory, name, extra):
+    """Peel-off does not disturb the walk and consumes no random numbers, so detector k of a multi-detector walk must equal
+    the plain launch with det_phi_k over the SAME photon ids: identical count planes, Stokes sums to rounding.  (1 x 1 and
+    2 x 2 pixels: block-private images in shared memory; 40 x 40: global atomics.)"""
+    atm = atmospheres(name)
+    g, _ = gpu_factory(atm)
+    xm = 1.3 * atm.rfront[-1]
+    P = 20000
+    angles = [1.e-3, 0.4, 1.0, math.pi / 2, 2.0, 2.6] + [0.05 + 0.0713 * k for k in range(35)]        # 41 detectors: two rounds of lanes
+    kw = dict(mode=abi.MODE_FAST, x_max=xm, y_max=xm, seed=77, n_photons=P, photon_id_base=5000, **extra)
+    Ls = [make_launch(det_phi=a, det_theta=math.pi / 2 if k % 3 else 1.2, **kw) for k, a in enumerate(angles)]
+    m = g.run_multi(Ls)
+    assert g.last_engine() == 2 and m["stats"]["reserved"] == 1 and m["stats"]["n_emit"] == P
+    for k in (0, 3, 7, 31, 32, 40):
+        one = g.run(Ls[k])
+        np.testing.assert_array_equal(m["det"][k][2], one["det"][2])
+        scale = np.abs(one["det"][0]).max()
+        np.testing.assert_allclose(m["det"][k][0], one["det"][0], rtol=1e-7, atol=1e-10 * scale)
+        np.testing.assert_allclose(m["det"][k][1], one["det"][1], rtol=1e-7, atol=1e-10 * scale * scale)
+    assert m["stats"]["n_scatter"] == one["stats"]["n_scatter"]          # one walk: as many scatterings as ONE launch
+    assert m["stats"]["n_peel"] == len(Ls) * one["stats"]["n_peel"]
+    assert int(m["err"].sum()) <= len(Ls) * (int(one["err"].sum()) + 2)
+    # fallbacks keep the contract (independent walks): faithful mode, reflecting surface
+    Lf = [make_launch(det_phi=a, **dict(kw, mode=abi.MODE_FAITHFUL, n_photons=2000)) for a in angles[:3]]
+    f = g.run_multi(Lf)
+    assert f["stats"]["n_emit"] == 3 * 2000 and f["det"].shape[0] == 3
+    with pytest.raises(Exception):
+        g.run_multi([make_launch(det_phi=1.0, **kw), make_launch(det_phi=3.1, limb_emission=1, **kw)])
 
 
 def test_spectrum_all_wavelengths(atmospheres, gpu_factory):
