@@ -55,6 +55,17 @@ namespace e2 {
 
 #include "fastmath.cuh"
 
+// measurement switches (tools/build_variants.sh builds the library with single optimisations turned off)
+#ifndef E2_OPT_KAPN
+#define E2_OPT_KAPN 1      // opacity of the next radial layer loaded one step ahead
+#endif
+#ifndef E2_OPT_R2S
+#define E2_OPT_R2S 1       // squared radii through ld.shared with a 32-bit address
+#endif
+#ifndef E2_WATCHDOG
+#define E2_WATCHDOG 1      // bounded waits (see ring_take)
+#endif
+
 // A block has NT marcher lanes and NP >= NT photon slots: with more photons than lanes a lane whose ray
 // ended finds another ready ray at once, and a round collects enough events to keep every warp busy in
 // the event phase.  RC = ring capacity of the lists (power of two >= NP).
@@ -1046,6 +1057,7 @@ struct Marcher {
     const double* kb;            // kext + nr*(c1 + nt*c2): the opacity row of the ray's (theta, phi) column
     int nr, nt, depth;           // launch invariants kept in registers (the kernel parameters live in constant memory)
     const double* kext;
+    const double* r2g;           // (the generic pointer: measurement variant without E2_OPT_R2S)
     unsigned r2s;                // shared-space byte address of the squared radii: ld.shared with a 32-bit address instead of a generic
                                  // pointer (the compiler rebuilt the generic shared base with S2R + LEA in every step)
     int tl; unsigned long long th, pid;   // walk recorder (trace hook only; dead code otherwise)
@@ -1058,6 +1070,7 @@ struct Marcher {
     }
     template <class Sh>
     __device__ __forceinline__ void bind(const Sh& X) {
+        r2g = X.r2;
         unsigned long long sh;      // volatile: converted ONCE and kept, not rematerialised (S2UR + ULEA) at every use
         asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(sh) : "l"((unsigned long long)X.r2));
         r2s = (unsigned)sh;
@@ -1065,11 +1078,12 @@ struct Marcher {
     // opacity of layer c0 and, ahead of time, of its neighbour in the direction of motion (index clamped to the column)
     __device__ __forceinline__ void load_kap() {
         kap = __ldg(kb + c0);
-        kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
+        if (E2_OPT_KAPN) kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
     }
     __device__ __forceinline__ double r2_at(int i) const {
+        if (!E2_OPT_R2S) return r2g[i];
         double v;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(r2s + 8u * (unsigned)i));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(r2s + 8u * (unsigned)i));
         return v;
     }
 
@@ -1129,14 +1143,15 @@ struct Marcher {
         const int dep = (Sh::BATCH && A.L.wl_batch) ? depth : A.T.cell_depth;
         if (f == (up ? nr : dep)) return up ? O_EXIT : O_SURF;
         c0 += dr;
-        kap = kapn;               // loaded one step ago (measured: reading four layers at once with one 256-bit load and selecting is slower)
+        if (E2_OPT_KAPN) kap = kapn;               // loaded one step ago (measured: reading four layers at once with one 256-bit load and selecting is slower)
+        else kap = __ldg(kb + c0);
         // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
         double disc = fma(r2_at(c0 + up), iq, D0);
         if (disc < 0.0) {
             if (dr < 0) { dr = 1; ds = 1.0; disc = fma(r2_at(c0 + 1), iq, D0); }
             if (disc < 0.0) { tr = RAY_NONE; kapn = kap; return O_NONE; }
         }
-        kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
+        if (E2_OPT_KAPN) kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
         tr = fma(ds, fsqrt(disc), hbn);
         return O_NONE;
     }
@@ -1606,6 +1621,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
 // returns an error instead of a hung device.  The polls of a healthy launch end within microseconds, the counter costs nothing.
 constexpr int ERR_WATCHDOG = 63;
 __device__ __forceinline__ bool spin_expired(unsigned& spin, unsigned long long* abort_word) {
+    if (!E2_WATCHDOG) return false;
     if ((++spin & 0xfffffu) != 0u) return false;
     if (*(volatile unsigned long long*)abort_word) return true;
     if (spin >= (400u << 20)) { atomicExch(abort_word, 1ull); return true; }
@@ -1657,7 +1673,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         // watchdog: this warp found neither a ray to step nor an event to run for 65 536 turns.  If no other warp of the block
         // made progress either (misc[4] counts their busy turns) for ~1e8 of this warp's turns (seconds), or another warp raised
         // the abort word, leave.  (The drain of a launch is NOT idle in this sense: the warps that finish the last photons keep counting.)
-        if (idle_turns && (idle_turns & 0xffffu) == 0u) {
+        if (E2_WATCHDOG && idle_turns && (idle_turns & 0xffffu) == 0u) {
             int stop = 0;
             if (lane == 0) {
                 const int prog = vmisc[4];
@@ -1735,8 +1751,10 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
         int l = -1;
-        if (nactive == 0 && !anym) ++idle_turns;
-        else { idle_turns = 0u; if (lane == 0) vmisc[4] = vmisc[4] + 1; }      // busy turn: tell the idle warps of the block
+        if (E2_WATCHDOG) {
+            if (nactive == 0 && !anym) ++idle_turns;
+            else { idle_turns = 0u; if (lane == 0) vmisc[4] = vmisc[4] + 1; }      // busy turn: tell the idle warps of the block
+        }
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
         if (Sh::MULTI) {
             // multi-detector walks: a FAN event is a full warp's work for ONE photon, so any waiting photon is taken (a few at a

@@ -33,6 +33,7 @@
 
 #include "../../include/artes_gpu.h"
 #include "fits_min.h"
+#include "list_directed.h"
 
 namespace fs = std::filesystem;
 using artes_host::FitsImage;
@@ -279,17 +280,8 @@ void thermal_tables(const Atmosphere& a, const Config& c, int l, int depth, doub
     t.total = total;
 }
 
-// list-directed real output of gfortran: 17 significant digits, 3-digit exponent
-std::string fnum(double v) {
-    char buf[64];
-    if (v == 0.0) return "   0.0000000000000000     ";
-    const double av = std::fabs(v);
-    if (av >= 0.1 && av < 1.e16) {
-        const int digits_before = (int)std::floor(std::log10(av)) + 1;
-        std::snprintf(buf, sizeof(buf), "%25.*f", std::max(0, 17 - std::max(digits_before, 1)), v);
-    } else std::snprintf(buf, sizeof(buf), "%25.16E", v);
-    return std::string(buf);
-}
+// list-directed real output of gfortran (list_directed.h): separator blank + G25.17E3 field
+std::string fnum(double v) { return artes_host::ld_real(v); }
 
 struct Run {
     Config c;
@@ -646,8 +638,7 @@ int main(int argc, char** argv) {
                         fnum(wavelength) + fnum(flux[0] * e_pack * 1.e-6) + fnum(flux[1] * e_pack * 1.e-6) + fnum(flux[1]));
         }
         if (c.imaging_mono || c.spectrum) {
-            char b[32]; std::snprintf(b, sizeof(b), "%12d", depth);
-            append_line(out + "cell_depth.dat", " # Wavelength [micron] - Cell depth", fnum(wavelength * 1.e6) + b);
+            append_line(out + "cell_depth.dat", " # Wavelength [micron] - Cell depth", fnum(wavelength * 1.e6) + artes_host::ld_int(depth));
         }
         if (c.flow_global) {   // unit vectors :3715-3738
             std::vector<double> tr(flow3.size(), 0.0);

@@ -67,9 +67,10 @@ void convert(const unsigned char* raw, size_t n, int bitpix, double* out) {
 
 size_t elem_bytes(int bitpix) { return (size_t)(bitpix < 0 ? -bitpix : bitpix) / 8; }
 
-std::string card(const char* key, const std::string& value, bool quoted = false) {
-    char buf[96];
-    if (quoted) std::snprintf(buf, sizeof(buf), "%-8s= '%-8s'", key, value.c_str());
+// one 80-character card: value right-justified to column 30, then " / comment" (the layout ftphpr writes)
+std::string card(const char* key, const std::string& value, const char* comment = nullptr) {
+    char buf[160];
+    if (comment) std::snprintf(buf, sizeof(buf), "%-8s= %20s / %s", key, value.c_str(), comment);
     else std::snprintf(buf, sizeof(buf), "%-8s= %20s", key, value.c_str());
     std::string s(buf);
     s.resize(80, ' ');
@@ -171,16 +172,25 @@ bool fits_read_hdu_chunked(const std::string& path, int hdu_index, size_t chunk_
 bool fits_write_image(const std::string& path, const std::vector<long>& naxes, const double* data, std::string& err) {
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) { err = "cannot create " + path; return false; }
+    // byte for byte the primary header the reference's calls produce (write_fits_3D/4D, src/ARTES.f90:3774-3841:
+    // ftphpr(unit, simple=T, bitpix=-64, naxis, naxes, pcount=0, gcount=1, extend=T) of the vendored CFITSIO 3.34),
+    // checked against lib/libcfitsio.so.3 in tests/test_output_stage.py
     std::string hdr;
-    hdr += card("SIMPLE", "T");
-    hdr += card("BITPIX", "-64");
-    hdr += card("NAXIS", std::to_string(naxes.size()));
+    hdr += card("SIMPLE", "T", "file does conform to FITS standard");
+    hdr += card("BITPIX", "-64", "number of bits per data pixel");
+    hdr += card("NAXIS", std::to_string(naxes.size()), "number of data axes");
     size_t n = naxes.empty() ? 0 : 1;
     for (size_t i = 0; i < naxes.size(); ++i) {
-        hdr += card(("NAXIS" + std::to_string(i + 1)).c_str(), std::to_string(naxes[i]));
+        hdr += card(("NAXIS" + std::to_string(i + 1)).c_str(), std::to_string(naxes[i]), ("length of data axis " + std::to_string(i + 1)).c_str());
         n *= (size_t)naxes[i];
     }
-    hdr += card("EXTEND", "T");
+    hdr += card("EXTEND", "T", "FITS dataset may contain extensions");
+    {
+        std::string c1 = "COMMENT   FITS (Flexible Image Transport System) format is defined in 'Astronomy";
+        std::string c2 = "COMMENT   and Astrophysics', volume 376, page 359; bibcode: 2001A&A...376..359H";
+        c1.resize(80, ' '); c2.resize(80, ' ');
+        hdr += c1 + c2;
+    }
     std::string end = "END";
     end.resize(80, ' ');
     hdr += end;

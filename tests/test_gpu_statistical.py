@@ -87,7 +87,7 @@ def phase_oracle_batches(atmospheres, oracle_factory):
     o, _ = oracle_factory(atm)
     xm = 1.3 * atm.rfront[-1]
     phis, limb = _phase_angles()
-    assert len(phis) == 73 and sum(limb) == 5
+    assert len(phis) == 73 and sum(limb) in (4, 5)      # 170 deg itself: the accumulated 68 x 2.5 deg falls an ulp short, as in the reference's loop
     kw = dict(x_max=xm, y_max=xm, nx=1, ny=1)
     return [_points_as_image([o.run(make_launch(n_photons=PHASE_N, seed=20000 + 73 * i + a, det_phi=phis[a], limb_emission=limb[a], **kw),
                                     rng=oracle_lib.RNG_MZ)["det"] for a in range(73)]) for i in range(PHASE_K)]
