@@ -57,7 +57,7 @@ namespace e2 {
 
 // measurement switches (tools/build_variants.sh builds the library with single optimisations turned off)
 #ifndef E2_OPT_KAPN
-#define E2_OPT_KAPN 1      // opacity of the next radial layer loaded one step ahead
+#define E2_OPT_KAPN 0      // opacity of the next radial layer loaded one step ahead (measured: 2-6 % SLOWER, profiles/r02_c_*; kept as a switch)
 #endif
 #ifndef E2_OPT_R2S
 #define E2_OPT_R2S 1       // squared radii through ld.shared with a 32-bit address
@@ -1032,7 +1032,7 @@ __device__ __forceinline__ void block_setup(const KernelArgs& A, double* sm, ShT
     __syncthreads();
     for (int i = tid; i < NP; i += NT) { X.Q(L_EMIT, i) = (short)i; X.I(I_ND, i) = 0; X.I(I_INFO, i) = 0; }   // every slot starts by asking for a photon
     if (tid < 16) { X.head[tid] = 0; X.tail[tid] = (tid == L_EMIT) ? NP : 0; }
-    if (tid == 0) { X.misc[0] = 0; X.misc[1] = 0; X.misc[2] = 0; X.misc[3] = 0; X.misc[4] = 0; }
+    if (tid < 32) X.misc[tid] = 0;      // [0] retired slots, [1], [2] bulk-synchronous kernel, [8..31] watchdog words of the (<= 8) warps
     __syncthreads();
 }
 
@@ -1655,8 +1655,6 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     volatile int* vtail = X.tail;
     volatile int* vmisc = X.misc;
     const int starve = 8;                                        // take partial batches when fewer lanes than this march
-    unsigned idle_turns = 0;                                     // consecutive turns of the loop below without a ray or an event (watchdog)
-    int seen_progress = 0;
     // (Measured and dropped: soft warp specialisation -- the last warps of a block only run events, the others only march --
     // to shrink the code each warp loops over: 5-10 % slower on every workload, the event warps idle too often.)
 #ifdef E2_STATS
@@ -1670,20 +1668,6 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         // every slot retired: the block is done.  One lane reads, so that the whole warp leaves together (a volatile read per lane
         // is not warp-uniform by construction, and a warp that splits here would wait for its exited lanes in the ballots below)
         if (__shfl_sync(FULL, (int)vmisc[0], 0) >= NP) break;
-        // watchdog: this warp found neither a ray to step nor an event to run for 65 536 turns.  If no other warp of the block
-        // made progress either (misc[4] counts their busy turns) for ~1e8 of this warp's turns (seconds), or another warp raised
-        // the abort word, leave.  (The drain of a launch is NOT idle in this sense: the warps that finish the last photons keep counting.)
-        if (E2_WATCHDOG && idle_turns && (idle_turns & 0xffffu) == 0u) {
-            int stop = 0;
-            if (lane == 0) {
-                const int prog = vmisc[4];
-                if (prog != seen_progress) { seen_progress = prog; idle_turns = 0u; }
-                stop = *(volatile unsigned long long*)(A.O.err + ERR_WATCHDOG) != 0ull;
-                if (!stop && idle_turns >= (1u << 27)) { atomicExch(A.O.err + ERR_WATCHDOG, 1ull); stop = 1; }
-            }
-            idle_turns = __shfl_sync(FULL, idle_turns, 0);
-            if (__shfl_sync(FULL, stop, 0)) break;
-        }
         // ---- free lanes claim ready rays
         const unsigned fm = __ballot_sync(FULL, M.slot < 0);
 #ifdef E2_STATS
@@ -1751,9 +1735,25 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
         int l = -1;
-        if (E2_WATCHDOG) {
-            if (nactive == 0 && !anym) ++idle_turns;
-            else { idle_turns = 0u; if (lane == 0) vmisc[4] = vmisc[4] + 1; }      // busy turn: tell the idle warps of the block
+        // Watchdog for the turns in which this warp found neither a ray nor an event.  It costs the busy path nothing: the idle
+        // turns are counted in shared memory (misc[8 + warp]); every 65 536 of them the warp looks whether ANY list of the block
+        // moved (sum of the list tails) and, after ~1e8 idle turns (seconds) without a single push anywhere in the block, raises
+        // the abort word.  The drain of a launch is not idle in this sense: the warps finishing the last photons keep pushing.
+        if (E2_WATCHDOG && nactive == 0 && !anym) {
+            const int w = threadIdx.x >> 5;
+            int stop = 0, c = 0;
+            if (lane == 0) { c = vmisc[8 + w] + 1; vmisc[8 + w] = c; }
+            c = __shfl_sync(FULL, c, 0);
+            if ((c & 0xffff) == 0) {
+                int sig = (lane < N_LISTS) ? vtail[lane] : 0;
+                for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(FULL, sig, o);
+                if (lane == 0) {
+                    if (sig != vmisc[16 + w]) { vmisc[16 + w] = sig; vmisc[24 + w] = c; }
+                    else if (c - vmisc[24 + w] >= (1 << 27)) atomicExch(A.O.err + ERR_WATCHDOG, 1ull);
+                    stop = *(volatile unsigned long long*)(A.O.err + ERR_WATCHDOG) != 0ull;
+                }
+                if (__shfl_sync(FULL, stop, 0)) break;
+            }
         }
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
         if (Sh::MULTI) {
