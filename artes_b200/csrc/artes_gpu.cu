@@ -41,6 +41,8 @@ cudaError_t launch_transport2(const KernelArgs& a, int sm_count, cudaStream_t st
 cudaError_t launch_transport2_trace(const KernelArgs& a, int sm_count, cudaStream_t stream);
 }  // namespace fast
 cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
+cudaError_t ingest_cell_tables(const double* k_sca, const double* k_abs, const int* c2u, size_t n, double* kext, double* albedo,
+                               double* cellrec, cudaStream_t stream);
 cudaError_t ingest_dedup_device(const double* src, size_t cells, size_t plane_stride, cudaStream_t stream,
                                 std::vector<double>& uniq, std::vector<int32_t>& c2u, int* exact, double* copy_ms, double* kernel_ms);
 }  // namespace artes
@@ -157,7 +159,7 @@ int upload_wl(artes_gpu_ctx* ctx, DeviceState& d, const Tp* host, size_t n, cons
         CU(cudaMalloc(&d.wl_allocs[i], bytes));
         d.wl_caps[i] = bytes;
     }
-    if (n) CU(cudaMemcpyAsync(d.wl_allocs[i], host, n * sizeof(Tp), cudaMemcpyHostToDevice, d.stream));
+    if (n && host) CU(cudaMemcpyAsync(d.wl_allocs[i], host, n * sizeof(Tp), cudaMemcpyHostToDevice, d.stream));      // host == null: device-built table
     *out = static_cast<const Tp*>(d.wl_allocs[i]);
     return 0;
 }
@@ -404,18 +406,8 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
     if ((long long)ctx->cells * n_wl > 2000000000LL) return fail(ctx, -1, "too many cells x wavelengths for one table set");
     const int n = ctx->cells * n_wl;
     for (int i = 0; i < n; ++i) if (cell_to_uniq[i] < 0 || cell_to_uniq[i] >= n_uniq) return fail(ctx, -1, "cell_to_uniq out of range");
-    std::vector<double> kext(n), albedo(n, 0.0);
-    for (int i = 0; i < n; ++i) {  // :2178-2188
-        kext[i] = k_sca[i] + k_abs[i];
-        if (kext[i] > 0.0) albedo[i] = k_sca[i] / kext[i];
-        if (albedo[i] < 1.e-20) albedo[i] = 1.e-20;
-    }
-    std::vector<double> cellrec((size_t)4 * n, 0.0);
-    for (int i = 0; i < n; ++i) {
-        cellrec[4 * (size_t)i] = kext[i]; cellrec[4 * (size_t)i + 1] = albedo[i];
-        const long long ub = cell_to_uniq[i];
-        std::memcpy(&cellrec[4 * (size_t)i + 2], &ub, 8);
-    }
+    // cell_opacity, cell_albedo (:2178-2188) and the per-cell record are derived ON THE DEVICE from the uploaded k_sca, k_abs and
+    // cell_to_uniq (ingest.cu): a third of the host-to-device bytes and no host pass over the cells
     std::vector<double> p1k((size_t)n_uniq * 4, 0.0), mrow((size_t)n_uniq * 720), cdfP((size_t)n_uniq * 181 * 4, 0.0);
     for (int u = 0; u < n_uniq; ++u) {
         for (int a = 0; a < 180; ++a)
@@ -448,10 +440,19 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
         const cudaEvent_t e0 = d.ev[0], e1 = d.ev[1];      // the device's own timing events (no launch is pending: the stream was just drained)
         CU(cudaEventRecord(e0, d.stream));
         int rc = 0;
-        rc |= upload_wl(ctx, d, kext.data(), kext.size(), &T.kext);
-        rc |= upload_wl(ctx, d, cellrec.data(), cellrec.size(), &T.cellrec);
-        rc |= upload_wl(ctx, d, albedo.data(), albedo.size(), &T.albedo);
+        const double *d_sca = nullptr, *d_abs = nullptr;
+        rc |= upload_wl(ctx, d, (const double*)nullptr, (size_t)n, &T.kext);
+        rc |= upload_wl(ctx, d, (const double*)nullptr, (size_t)4 * n, &T.cellrec);
+        rc |= upload_wl(ctx, d, (const double*)nullptr, (size_t)n, &T.albedo);
         rc |= upload_wl(ctx, d, cell_to_uniq, (size_t)n, &T.c2u);
+        rc |= upload_wl(ctx, d, k_sca, (size_t)n, &d_sca);
+        rc |= upload_wl(ctx, d, k_abs, (size_t)n, &d_abs);
+        if (rc) return rc;
+        {
+            cudaError_t ce = ingest_cell_tables(d_sca, d_abs, T.c2u, (size_t)n, const_cast<double*>(T.kext), const_cast<double*>(T.albedo),
+                                                const_cast<double*>(T.cellrec), d.stream);
+            if (ce != cudaSuccess) return fail(ctx, -2, std::string("cell tables: ") + cudaGetErrorString(ce));
+        }
         rc |= upload_wl(ctx, d, uniq_matrix, (size_t)n_uniq * 2880, &T.M);
         rc |= upload_wl(ctx, d, mrow.data(), mrow.size(), &T.Mrow);
         rc |= upload_wl(ctx, d, p1k.data(), p1k.size(), &T.p1k);
@@ -600,6 +601,7 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
                 ctx->last_engine = 2;
                 if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
                 a.O.scratch = d.scratch;
+                a.L.sdet_doubles = fast::engine2_sdet_doubles(a, 1);      // small detectors: block-private image in shared memory
                 e = fast::launch_transport2(a, d.sm_count, d.stream);
             }
             else e = fast::launch_transport(a, false, d.sm_count, d.stream);
@@ -717,7 +719,7 @@ static int run_batch_impl(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, d
         fill_launch(L0, a.L);
         // a launch table too large for shared memory or an image stack whose pixel offsets leave 32 bits: one launch after the other
         batched = fast::engine2_supports(a) && fast::engine2_batch_fits(a, n);
-        if (multi) sdet_doubles = fast::engine2_sdet_doubles(a, n);
+        sdet_doubles = fast::engine2_sdet_doubles(a, n);      // small detectors: block-private images in shared memory
     }
     if (multi) {
         // ONE walk for all detectors needs one emission law and one set of tables: same limb flag and wavelength everywhere,

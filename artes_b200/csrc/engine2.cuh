@@ -895,8 +895,10 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
             v[4] = v[0] * v[0]; v[5] = v[1] * v[1]; v[6] = v[2] * v[2]; v[7] = v[3] * v[3];
         }
         const size_t npx = (size_t)L.nx * L.ny;
+        // the block-private image in shared memory when the launch has one (small detectors: launchers.inc), else the global one
+        double* const detbase = X.sdet ? X.sdet : A.O.det;
         if (Sh::GEN && dep && pk != PK_SCATTER) {   // :4583-4585 / :4691-4693: Stokes I only
-            double* d = A.O.det + pix;
+            double* d = detbase + pix;
             atomicAdd(d, w_i); atomicAdd(d + 4 * npx, w_i * w_i); atomicAdd(d + 8 * npx, 1.0);
         }
         // Lanes that hit the same pixel are summed in the warp first (up to four pixel groups per batch: a batched
@@ -917,13 +919,13 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
                 if (lane == k) x = r;
             }
-            double* d = A.O.det + pixg;
+            double* d = detbase + pixg;
             if (lane < 8) atomicAdd(d + (size_t)lane * npx, x);
             else if (lane < 10) atomicAdd(d + (size_t)lane * npx, (double)__popc(grp));
         }
         left |= rem;
         if ((left >> lane) & 1u) {
-            double* d = A.O.det + pix;
+            double* d = detbase + pix;
 #pragma unroll
             for (int k = 0; k < 8; ++k) atomicAdd(d + (size_t)k * npx, v[k]);
             atomicAdd(d + 8 * npx, 1.0); atomicAdd(d + 9 * npx, 1.0);
@@ -1620,24 +1622,53 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
 // after ~10 s without progress a warp raises the launch's abort word (error slot 63), every loop that sees it leaves, and the host
 // returns an error instead of a hung device.  The polls of a healthy launch end within microseconds, the counter costs nothing.
 constexpr int ERR_WATCHDOG = 63;
-__device__ __forceinline__ bool spin_expired(unsigned& spin, unsigned long long* abort_word) {
-    if (!E2_WATCHDOG) return false;
-    if ((++spin & 0xfffffu) != 0u) return false;
-    if (*(volatile unsigned long long*)abort_word) return true;
-    if (spin >= (400u << 20)) { atomicExch(abort_word, 1ull); return true; }
-    return false;
+// the waits themselves are out of line: the common case (the cell is already published / free) costs one load and no register
+__device__ __noinline__ int ring_wait_take(volatile short* e, unsigned long long* abort_word) {
+    unsigned spin = 0;
+    for (;;) {
+        const short v = *e;
+        if (v >= 0) return (int)v;
+        if (!E2_WATCHDOG || (++spin & 0xfffffu) != 0u) continue;
+        if (*(volatile unsigned long long*)abort_word) return 0;
+        if (spin >= (400u << 20)) { atomicExch(abort_word, 1ull); return 0; }
+    }
+}
+__device__ __noinline__ void ring_wait_put(volatile short* e, unsigned long long* abort_word) {
+    unsigned spin = 0;
+    while (*e >= 0) {
+        if (!E2_WATCHDOG || (++spin & 0xfffffu) != 0u) continue;
+        if (*(volatile unsigned long long*)abort_word) return;
+        if (spin >= (400u << 20)) { atomicExch(abort_word, 1ull); return; }
+    }
 }
 __device__ __forceinline__ int ring_take(volatile short* e, unsigned long long* abort_word) {
-    short v;
-    unsigned spin = 0;
-    do { v = *e; if (v < 0 && spin_expired(spin, abort_word)) return 0; } while (v < 0);
+    int v = *e;
+    if (v < 0) v = ring_wait_take(e, abort_word);
     *e = (short)-1;
-    return (int)v;
+    return v;
 }
 __device__ __forceinline__ void ring_put(volatile short* e, int s, unsigned long long* abort_word) {
-    unsigned spin = 0;
-    while (*e >= 0) { if (spin_expired(spin, abort_word)) return; }
+    if (*e >= 0) ring_wait_put(e, abort_word);
     *e = (short)s;
+}
+// Watchdog for the turns in which a warp found neither a ray nor an event.  It costs the busy path nothing: the idle turns are
+// counted in shared memory (misc[8 + warp]); every 65 536 of them the warp looks whether ANY list of the block moved (sum of the
+// list tails) and, after ~1e8 idle turns (seconds) without a single push anywhere in the block, raises the abort word.  The
+// drain of a launch is not idle in this sense: the warps finishing the last photons keep pushing.  Returns true to leave.
+__device__ __noinline__ bool watchdog_idle_turn(volatile int* vmisc, volatile int* vtail, unsigned long long* abort_word) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int stop = 0, c = 0;
+    if (lane == 0) { c = vmisc[8 + w] + 1; vmisc[8 + w] = c; }
+    c = __shfl_sync(FULL, c, 0);
+    if ((c & 0xffff) != 0) return false;
+    int sig = (lane < N_LISTS) ? vtail[lane] : 0;
+    for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(FULL, sig, o);
+    if (lane == 0) {
+        if (sig != vmisc[16 + w]) { vmisc[16 + w] = sig; vmisc[24 + w] = c; }
+        else if (c - vmisc[24 + w] >= (1 << 27)) atomicExch(abort_word, 1ull);
+        stop = *(volatile unsigned long long*)abort_word != 0ull;
+    }
+    return __shfl_sync(FULL, stop, 0) != 0;
 }
 
 template <int NT, int NP, int MINB, bool TR, bool GN, bool BT = false, bool MD = false>
@@ -1735,26 +1766,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
         int l = -1;
-        // Watchdog for the turns in which this warp found neither a ray nor an event.  It costs the busy path nothing: the idle
-        // turns are counted in shared memory (misc[8 + warp]); every 65 536 of them the warp looks whether ANY list of the block
-        // moved (sum of the list tails) and, after ~1e8 idle turns (seconds) without a single push anywhere in the block, raises
-        // the abort word.  The drain of a launch is not idle in this sense: the warps finishing the last photons keep pushing.
-        if (E2_WATCHDOG && nactive == 0 && !anym) {
-            const int w = threadIdx.x >> 5;
-            int stop = 0, c = 0;
-            if (lane == 0) { c = vmisc[8 + w] + 1; vmisc[8 + w] = c; }
-            c = __shfl_sync(FULL, c, 0);
-            if ((c & 0xffff) == 0) {
-                int sig = (lane < N_LISTS) ? vtail[lane] : 0;
-                for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(FULL, sig, o);
-                if (lane == 0) {
-                    if (sig != vmisc[16 + w]) { vmisc[16 + w] = sig; vmisc[24 + w] = c; }
-                    else if (c - vmisc[24 + w] >= (1 << 27)) atomicExch(A.O.err + ERR_WATCHDOG, 1ull);
-                    stop = *(volatile unsigned long long*)(A.O.err + ERR_WATCHDOG) != 0ull;
-                }
-                if (__shfl_sync(FULL, stop, 0)) break;
-            }
-        }
+        if (E2_WATCHDOG && nactive == 0 && !anym && watchdog_idle_turn(vmisc, vtail, A.O.err + ERR_WATCHDOG)) break;
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
         if (Sh::MULTI) {
             // multi-detector walks: a FAN event is a full warp's work for ONE photon, so any waiting photon is taken (a few at a

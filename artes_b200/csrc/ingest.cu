@@ -57,7 +57,32 @@ __global__ void ingest_verify_kernel(const double* __restrict__ planes, size_t c
 
 struct Free { std::vector<void*> p; ~Free() { for (void* q : p) cudaFree(q); } };
 
+// derived per-cell tables of grid_initialize / get_atmosphere (src/ARTES.f90:2172-2188): cell_opacity = k_sca + k_abs,
+// cell_albedo = k_sca / cell_opacity floored at 1e-20, and the 32-byte record {opacity, albedo, matrix block, 0} the
+// interaction event reads with one 256-bit load
+__global__ void ingest_cell_tables_kernel(const double* __restrict__ k_sca, const double* __restrict__ k_abs, const int* __restrict__ c2u,
+                                          size_t n, double* __restrict__ kext, double* __restrict__ albedo, double* __restrict__ cellrec) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ks = k_sca[i], ke = ks + k_abs[i];
+    double al = 0.0;
+    if (ke > 0.0) al = ks / ke;
+    if (al < 1.e-20) al = 1.e-20;
+    kext[i] = ke;
+    albedo[i] = al;
+    double4 r;
+    r.x = ke; r.y = al; r.z = __longlong_as_double((long long)c2u[i]); r.w = 0.0;
+    reinterpret_cast<double4*>(cellrec)[i] = r;
+}
+
 }  // namespace
+
+cudaError_t ingest_cell_tables(const double* k_sca, const double* k_abs, const int* c2u, size_t n, double* kext, double* albedo,
+                               double* cellrec, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    ingest_cell_tables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(k_sca, k_abs, c2u, n, kext, albedo, cellrec);
+    return cudaGetLastError();
+}
 
 // src: plane (e, a) of the wavelength = `cells` contiguous doubles at src + plane_stride * (e + 16 a).
 // Returns the blocks in order of first appearance (cell index), like the host path.  *exact = 0 if a hash group failed the

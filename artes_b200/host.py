@@ -196,6 +196,7 @@ class Transport:
         self.wl_index = None
         self.depth = 0
         self.emis_total = 0.0
+        self._depth_cache = {}       # grid_initialize(2) is done once per wavelength of a run (:209, :141), not once per launch
 
     def close(self):
         self.gpu.close()
@@ -203,7 +204,7 @@ class Transport:
     def set_wavelength(self, l=0):
         """grid_initialize(2) for wavelength index l, then the table upload."""
         a, p = self.atm, self.p
-        self.depth = cell_depth(a.rfront, a.k_sca[l], a.k_abs[l], a.nr, a.ntheta, a.nphi, p.photon_source, p.ring)
+        self.depth = self._cell_depth(l)
         cw = cdf = None
         if p.photon_source == 2:
             vol = cell_volume(a.rfront, a.thetafront(), a.phifront(), self.oblate)
@@ -212,6 +213,12 @@ class Transport:
             self.emis_total = float(cdf.reshape(a.nphi, a.ntheta, a.nr)[-1, -1, -1])
         self.gpu.set_wavelength(a.k_sca[l], a.k_abs[l], a.uniq[l], a.cell_to_uniq[l], self.depth, cw, cdf)
         self.wl_index = l
+
+    def _cell_depth(self, l):
+        if l not in self._depth_cache:
+            a, p = self.atm, self.p
+            self._depth_cache[l] = cell_depth(a.rfront, a.k_sca[l], a.k_abs[l], a.nr, a.ntheta, a.nphi, p.photon_source, p.ring)
+        return self._depth_cache[l]
 
     def set_all_wavelengths(self, wls=None):
         """grid_initialize(2) for every wavelength of the atmosphere, uploaded as ONE stacked table set
@@ -222,9 +229,10 @@ class Transport:
         uniq, c2u, off = [], [], 0
         for l in wls:
             uniq.append(a.uniq[l]); c2u.append(np.asarray(a.cell_to_uniq[l]) + off); off += a.uniq[l].shape[0]
-        self.depths = [cell_depth(a.rfront, a.k_sca[l], a.k_abs[l], a.nr, a.ntheta, a.nphi, p.photon_source, p.ring) for l in wls]
-        self.gpu.set_wavelengths(np.stack([a.k_sca[l] for l in wls]), np.stack([a.k_abs[l] for l in wls]), np.concatenate(uniq),
-                                 np.stack(c2u), self.depths)
+        self.depths = [self._cell_depth(l) for l in wls]
+        whole = wls == list(range(len(a.wavelengths)))      # the atmosphere's own (n_wl, cells) arrays: no copy
+        self.gpu.set_wavelengths(a.k_sca if whole else np.stack([a.k_sca[l] for l in wls]),
+                                 a.k_abs if whole else np.stack([a.k_abs[l] for l in wls]), np.concatenate(uniq), np.stack(c2u), self.depths)
         self.wl_index = wls[0]
         self.depth = self.depths[0]
         return wls

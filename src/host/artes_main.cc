@@ -12,6 +12,9 @@
 //
 // Extra keywords (optional; reference inputs run unchanged):
 //   gpu:devices=N      number of GPUs of this node to shard the photons over (default 1)
+//   gpu:phase_walks=single|independent   phase curves (detector:type=phase): `single` (default) walks every photon packet ONCE and
+//                      peels off towards all detector azimuths (artes_gpu_run_multi: the 68 angles below 170 deg in one call, the
+//                      limb-biased angles in a second); `independent` repeats the walk for every azimuth like the reference
 //   gpu:seed=S         Philox key (default 1; the reference seeds from the clock, :4175-4195)
 //   gpu:mode=fast|faithful   arithmetic mode of the library (default fast)
 // Environment: ARTES_DRYRUN=1 parses everything, prints the run configuration and stops before touching a GPU.
@@ -68,6 +71,7 @@ struct Config {   // defaults of initialize :283-314
     int devices = 1;
     uint64_t seed = 1;
     int mode = ARTES_MODE_FAST;
+    bool phase_single_walk = true;   // phase curves: ONE walk per packet observed from all detector azimuths (gpu:phase_walks=independent: one walk per azimuth like the reference)
 };
 
 [[noreturn]] void die(const std::string& msg) {
@@ -125,6 +129,7 @@ void input_parameters(Config& c, const std::string& key, const std::string& valu
     else if (key == "gpu:devices") c.devices = std::max(1, std::atoi(value.c_str()));
     else if (key == "gpu:seed") c.seed = std::strtoull(value.c_str(), nullptr, 10);
     else if (key == "gpu:mode") c.mode = (value == "faithful") ? ARTES_MODE_FAITHFUL : ARTES_MODE_FAST;
+    else if (key == "gpu:phase_walks") c.phase_single_walk = (value != "independent");
     else die(" Wrong keyword found in input file: " + key);
 }
 
@@ -715,20 +720,55 @@ int main(int argc, char** argv) {
                     else phis[i - 1] = phis[i - 2] + 2.5 * PI / 180.0;
                 }
                 if (!c.flow_global && !c.flow_theta) {
-                    // the 73 calls of radiative_transfer as ONE batched launch (artes_gpu_run_batch): angle k walks the
-                    // photon ids k*packages + [0, packages), so the points are statistically independent like the
-                    // reference's clock-seeded runs
+                    // the 73 calls of radiative_transfer (:215-245) on the GPU:
+                    //  - gpu:phase_walks=single (default): every packet is walked ONCE and observed from all azimuths (peel-off does
+                    //    not disturb the walk): one artes_gpu_run_multi call for the angles below 170 deg, one for the limb-biased
+                    //    angles (a different emission law, :1041-1055).  Each angle has the expectation value and the noise of the
+                    //    reference's run with `packages` packets; the angles share their walks, so their noise is correlated.
+                    //  - gpu:phase_walks=independent: ONE batched launch of 73 independent walks (artes_gpu_run_batch): angle k walks
+                    //    the photon ids k*packages + [0, packages), statistically independent like the reference's runs.
                     std::vector<artes_launch_t> Ls;
                     for (double phi : phis) Ls.push_back(make_launch(phi));
                     std::vector<double> det_all((size_t)73 * 12 * npx), flux_all(2 * 73);
                     artes_stats_t st;
-                    std::fprintf(stdout, "Phase angles: 73, one batched launch\n"); std::fflush(stdout);
-                    if (artes_gpu_run_batch(ctx, Ls.data(), 73, det_all.data(), flux_all.data(), err_hist, &st) != 0) {
-                        std::fprintf(stderr, "ARTES: artes_gpu_run_batch: %s\n", artes_gpu_last_error(ctx));
+                    std::memset(&st, 0, sizeof(st));
+                    uint64_t walked = 0;
+                    bool failed = false;
+                    if (c.phase_single_walk) {
+                        std::fprintf(stdout, "Phase angles: 73, one walk per packet observed from all azimuths (two launches)\n"); std::fflush(stdout);
+                        for (int flag = 0; flag < 2 && !failed; ++flag) {
+                            std::vector<artes_launch_t> grp;
+                            std::vector<int> idx;
+                            for (int i = 0; i < 73; ++i) if (Ls[i].limb_emission == flag) { grp.push_back(Ls[i]); idx.push_back(i); }
+                            if (grp.empty()) continue;
+                            for (auto& g : grp) g.photon_id_base = (uint64_t)flag * packages;
+                            std::vector<double> det_g(grp.size() * 12 * npx), flux_g(2 * grp.size());
+                            artes_stats_t sg;
+                            uint64_t eh[ARTES_ERR_SLOTS];
+                            if (artes_gpu_run_multi(ctx, grp.data(), (int)grp.size(), det_g.data(), flux_g.data(), eh, &sg) != 0) {
+                                std::fprintf(stderr, "ARTES: artes_gpu_run_multi: %s\n", artes_gpu_last_error(ctx));
+                                failed = true;
+                                break;
+                            }
+                            for (size_t j = 0; j < idx.size(); ++j) {
+                                std::copy(det_g.begin() + j * 12 * npx, det_g.begin() + (j + 1) * 12 * npx, det_all.begin() + (size_t)idx[j] * 12 * npx);
+                                flux_all[2 * idx[j]] = flux_g[2 * j]; flux_all[2 * idx[j] + 1] = flux_g[2 * j + 1];
+                            }
+                            for (int k = 0; k < ARTES_ERR_SLOTS; ++k) err_hist[k] = (flag == 0 ? 0 : err_hist[k]) + eh[k];
+                            st.kernel_ms += sg.kernel_ms; st.reduce_ms += sg.reduce_ms;
+                            walked += sg.n_emit;
+                        }
+                    } else {
+                        std::fprintf(stdout, "Phase angles: 73, one batched launch\n"); std::fflush(stdout);
+                        failed = artes_gpu_run_batch(ctx, Ls.data(), 73, det_all.data(), flux_all.data(), err_hist, &st) != 0;
+                        if (failed) std::fprintf(stderr, "ARTES: artes_gpu_run_batch: %s\n", artes_gpu_last_error(ctx));
+                        walked = 73 * packages;
+                    }
+                    if (failed) {
                         rc = 1;
                     } else {
                         for (int k = 0; k < ARTES_ERR_SLOTS; ++k) if (err_hist[k]) R.errors[k] += err_hist[k];
-                        R.packets_done += 73 * packages; R.gpu_ms += st.kernel_ms + st.reduce_ms;
+                        R.packets_done += walked; R.gpu_ms += st.kernel_ms + st.reduce_ms;
                         for (int i = 0; i < 73; ++i) {
                             std::copy(det_all.begin() + (size_t)i * 12 * npx, det_all.begin() + (size_t)(i + 1) * 12 * npx, det_sum.begin());
                             flux[0] = flux_all[2 * i]; flux[1] = flux_all[2 * i + 1];

@@ -128,6 +128,27 @@ def test_driver_phase_curve_and_spectrum(driver, tmp_path, atmospheres):
     assert ph.shape == (73, 9) and ph[0, 0] == 0.0 and ph[-1, 0] == 180.0 and abs(ph[1, 0] - 2.5) < 1e-9     # :215-245
     assert (ph[:, 1] > 0).all() and ph[0, 1] > 5 * ph[-1, 1]          # bright at full phase, faint near new phase
     assert len(_read_table(tmp_path / "output" / "ph" / "output" / "normalization.dat")) == 1                # only at phase 0 (:3631)
+    # default: ONE walk per packet observed from all azimuths (artes_gpu_run_multi); gpu:phase_walks=independent repeats the walk
+    # per azimuth like the reference (one batched launch).  Same curve within the photon noise; the single-walk curve equals the
+    # library call made directly (angles below 170 deg: photon ids [0, packages)).
+    assert "one walk per packet" in r.stdout
+    r2 = run(driver, tmp_path, "c2", "20000", "-o", "ph2", "-k", "detector:type=phase", "-k", "gpu:phase_walks=independent")
+    assert r2.returncode == 0 and "one batched launch" in r2.stdout
+    ph2 = _read_table(tmp_path / "output" / "ph2" / "output" / "phase.dat")
+    assert ph2.shape == (73, 9)
+    np.testing.assert_allclose(ph[:56, 1], ph2[:56, 1], rtol=0.12)
+    atm2 = atmospheres("c2_hg_deck")
+    t = host.Transport(atm2, host.Params(nx=1, ny=1, phase_curve=True), mode=abi.MODE_FAST)
+    t.set_wavelength(0)
+    phis = [1.e-5 * math.pi / 180.0, 2.5 * math.pi / 180.0]
+    while len(phis) < 72:
+        phis.append(phis[-1] + 2.5 * math.pi / 180.0)
+    for k in (10, 40, 67):       # a detector's image depends on the walk (ids [0, packages), seed 1) and its own direction only
+        m = t.gpu.run_multi([t.launch_struct(20000, seed=1, det_phi=phis[k])])
+        e_k = host.package_energy(t.p, atm2.rfront, atm2.wavelengths[0] * 1e-6, 20000)
+        np.testing.assert_allclose(ph[k, 1], 1e-6 * e_k * m["det"][0][0, 0, 0, 0], rtol=1e-7)
+        assert abs(ph[k, 0] - 2.5 * k) < 1e-9
+    t.close()
     atm3 = A.c3_molecular(nr=30, nl=4)
     write_input(atm3, "c3", root=str(tmp_path))
     r = run(driver, tmp_path, "c3", "20000", "-o", "sp", "-k", "detector:type=spectrum")
