@@ -601,7 +601,6 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
                 ctx->last_engine = 2;
                 if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
                 a.O.scratch = d.scratch;
-                a.L.sdet_doubles = fast::engine2_sdet_doubles(a, 1);      // small detectors: block-private image in shared memory
                 e = fast::launch_transport2(a, d.sm_count, d.stream);
             }
             else e = fast::launch_transport(a, false, d.sm_count, d.stream);
@@ -719,7 +718,10 @@ static int run_batch_impl(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, d
         fill_launch(L0, a.L);
         // a launch table too large for shared memory or an image stack whose pixel offsets leave 32 bits: one launch after the other
         batched = fast::engine2_supports(a) && fast::engine2_batch_fits(a, n);
-        sdet_doubles = fast::engine2_sdet_doubles(a, n);      // small detectors: block-private images in shared memory
+        // block-private detector images in shared memory: multi-detector walks only.  Measured (profiles/r02_e_*): behind the
+        // warp-aggregated deposits of the single-detector kernels a private image gains nothing (1 x 1 detectors: -0.3 .. -1.7 %)
+        // and a 50 KB image (25 x 25) costs 18 % through the L1 it takes away.
+        if (multi) sdet_doubles = fast::engine2_sdet_doubles(a, n);
     }
     if (multi) {
         // ONE walk for all detectors needs one emission law and one set of tables: same limb flag and wavelength everywhere,

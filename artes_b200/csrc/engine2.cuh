@@ -63,8 +63,8 @@ namespace e2 {
 #define E2_OPT_R2S 1       // squared radii through ld.shared with a 32-bit address
 #endif
 #ifndef E2_WATCHDOG
-#define E2_WATCHDOG 1      // bounded waits (see ring_take)
-#endif
+#define E2_WATCHDOG 1      // 1: bounded waits on list cells (see ring_take); 2: also the idle-turn watchdog of the scheduling loop
+#endif                     //    (measured 4-5 % on C4, profiles/r02_g_*: debug / stress builds only, tools/gpu_stress.py)
 
 // A block has NT marcher lanes and NP >= NT photon slots: with more photons than lanes a lane whose ray
 // ended finds another ready ray at once, and a round collects enough events to keep every warp busy in
@@ -1651,24 +1651,18 @@ __device__ __forceinline__ void ring_put(volatile short* e, int s, unsigned long
     if (*e >= 0) ring_wait_put(e, abort_word);
     *e = (short)s;
 }
-// Watchdog for the turns in which a warp found neither a ray nor an event.  It costs the busy path nothing: the idle turns are
-// counted in shared memory (misc[8 + warp]); every 65 536 of them the warp looks whether ANY list of the block moved (sum of the
-// list tails) and, after ~1e8 idle turns (seconds) without a single push anywhere in the block, raises the abort word.  The
-// drain of a launch is not idle in this sense: the warps finishing the last photons keep pushing.  Returns true to leave.
-__device__ __noinline__ bool watchdog_idle_turn(volatile int* vmisc, volatile int* vtail, unsigned long long* abort_word) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int stop = 0, c = 0;
-    if (lane == 0) { c = vmisc[8 + w] + 1; vmisc[8 + w] = c; }
-    c = __shfl_sync(FULL, c, 0);
-    if ((c & 0xffff) != 0) return false;
-    int sig = (lane < N_LISTS) ? vtail[lane] : 0;
-    for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(FULL, sig, o);
-    if (lane == 0) {
-        if (sig != vmisc[16 + w]) { vmisc[16 + w] = sig; vmisc[24 + w] = c; }
-        else if (c - vmisc[24 + w] >= (1 << 27)) atomicExch(abort_word, 1ull);
-        stop = *(volatile unsigned long long*)abort_word != 0ull;
-    }
-    return __shfl_sync(FULL, stop, 0) != 0;
+// Watchdog for the turns in which a warp found neither a ray nor an event.  It must not slow the polling of an idle warp (which is
+// what picks up the next event): lane 0 alone counts the idle turns in shared memory (misc[8 + warp]: one load and one store);
+// every 65 536 of them it looks whether ANY list of the block moved (sum of the list tails) and, after ~1e8 idle turns (seconds)
+// without a single push anywhere in the block, raises the abort word and retires the block (misc[0] = NP: every warp leaves at
+// the top of its next turn).  The drain of a launch is not idle in this sense: the warps finishing the last photons keep pushing.
+__device__ __noinline__ void watchdog_check(volatile int* vmisc, volatile int* vtail, int c, int np_slots, unsigned long long* abort_word) {
+    const int w = threadIdx.x >> 5;
+    int sig = 0;
+    for (int l = 0; l < N_LISTS; ++l) sig += vtail[l];
+    if (sig != vmisc[16 + w]) { vmisc[16 + w] = sig; vmisc[24 + w] = c; }
+    else if (c - vmisc[24 + w] >= (1 << 27)) atomicExch(abort_word, 1ull);
+    if (*(volatile unsigned long long*)abort_word != 0ull) atomicMax((int*)vmisc, np_slots);
 }
 
 template <int NT, int NP, int MINB, bool TR, bool GN, bool BT = false, bool MD = false>
@@ -1685,7 +1679,13 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     volatile int* vhead = X.head;
     volatile int* vtail = X.tail;
     volatile int* vmisc = X.misc;
-    const int starve = 8;                                        // take partial batches when fewer lanes than this march
+#ifndef E2_STARVE
+#define E2_STARVE 8
+#endif
+#ifndef E2_INNER_SCALE
+#define E2_INNER_SCALE 2       // steps per pass = nr / E2_INNER_SCALE + 2, within [6, 16]
+#endif
+    const int starve = E2_STARVE;                                // take partial batches when fewer lanes than this march
     // (Measured and dropped: soft warp specialisation -- the last warps of a block only run events, the others only march --
     // to shrink the code each warp loops over: 5-10 % slower on every workload, the event warps idle too often.)
 #ifdef E2_STATS
@@ -1693,7 +1693,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     bool rdy_empty = false;
 #endif
     // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100)
-    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / 2 + 2));
+    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / E2_INNER_SCALE + 2));
 
     for (;;) {
         // every slot retired: the block is done.  One lane reads, so that the whole warp leaves together (a volatile read per lane
@@ -1766,7 +1766,11 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
         int l = -1;
-        if (E2_WATCHDOG && nactive == 0 && !anym && watchdog_idle_turn(vmisc, vtail, A.O.err + ERR_WATCHDOG)) break;
+        if (E2_WATCHDOG >= 2 && nactive == 0 && !anym && lane == 0) {
+            const int c = vmisc[8 + (threadIdx.x >> 5)] + 1;
+            vmisc[8 + (threadIdx.x >> 5)] = c;
+            if ((c & 0xffff) == 0) watchdog_check(vmisc, vtail, c, NP, A.O.err + ERR_WATCHDOG);
+        }
         // priority: re-solves and deposits first (cheap, they hand rays straight back), then interactions
         if (Sh::MULTI) {
             // multi-detector walks: a FAN event is a full warp's work for ONE photon, so any waiting photon is taken (a few at a
