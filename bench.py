@@ -378,10 +378,13 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-        traffic = None
+        traffic = traffic_at = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-            traffic = tr["dram_bytes_per_launch"] * P * NB / tr["photons_per_launch"] if tr else None   # scaled to this launch size
+            # as captured (the DRAM traffic of this kernel is mostly launch-constant: tables once, the L2-resident photon records
+            # as they are evicted, the image; 56 MB at 8e6 and 61 MB at 4e6 packets on C4), not scaled to this launch size
+            traffic = tr["dram_bytes_per_launch"] if tr else None
+            traffic_at = tr["photons_per_launch"] if tr else None
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -393,7 +396,7 @@ def main():
                 "rank_times": rank_times,
                 "shard_check": shard_check,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
-                             "frac": achieved / peaks["fp64_tflops"], "traffic": traffic,
+                             "frac": achieved / peaks["fp64_tflops"], "traffic": traffic, "traffic_captured_at_packets_per_launch": traffic_at,
                              "note": "dominant kernel transport3_kernel (ray/event engine, asynchronous scheduling); this path is FP64-issue / latency bound, "
                                      "not HBM or tensor bound: algorithmic FP64 flop = exact event counters x SURVEY 8d "
                                      "per-event figures; peak = FP64 FMA rate measured in this run by artes_gpu_fma_peak "
