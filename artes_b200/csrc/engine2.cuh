@@ -362,6 +362,46 @@ __device__ __forceinline__ int polrot_f(double c2a, double s2a, bool flip, doubl
     return 0;
 }
 
+// polrot_f with the scattering matrix taken straight from the table: F(deg) is interpolated between the two bracketing matrix
+// rows (matrix_at_deg_f) and multiplied with the rotated Stokes vector ROW BY ROW, so that only eight table values are live at a
+// time instead of F[16] and the two 16-value table rows (96 registers): the interaction event is what sets the kernel's
+// register budget.  Same arithmetic as matrix_at_deg_f + polrot_f.
+__device__ __forceinline__ int polrot_deg_f(const DevTables& T, int u, double deg, double c2a, double s2a, bool flip, double nc2,
+                                            const double Sin[4], double Sout[4], bool peeling, int& soft) {
+    if (!(fabs(nc2) < 1.00001)) return 11;
+    nc2 = fmin(fmax(nc2, -1.0), 1.0);
+    const double r0 = Sin[0], r1 = c2a * Sin[1] + s2a * Sin[2], r2 = c2a * Sin[2] - s2a * Sin[1], r3 = Sin[3];
+    int lo, up;
+    const double fl = floor(deg);
+    if (deg - fl > 0.5) { up = (int)fl + 2; lo = (int)fl + 1; }
+    else { up = (int)fl + 1; lo = (int)fl; }
+    const double* base = T.M + (size_t)u * (180 * 16);
+    const bool edge = (up <= 1 || lo >= 180);
+    const double* m0 = base + (edge ? (up <= 1 ? 0 : 179) : (lo - 1)) * 16;
+    const double* m1 = edge ? m0 : base + (up - 1) * 16;
+    const double w = edge ? 0.0 : deg - ((double)lo - 0.5);
+    double s[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double a0, a1, a2, a3, b0, b1, b2, b3;
+        ldg256_nc(m0 + 4 * r, a0, a1, a2, a3);
+        ldg256_nc(m1 + 4 * r, b0, b1, b2, b3);
+        s[r] = ((b0 - a0) * w + a0) * r0 + ((b1 - a1) * w + a1) * r1 + ((b2 - a2) * w + a2) * r2 + ((b3 - a3) * w + a3) * r3;
+    }
+    if (!peeling) {
+        if (s[0] > 0.0) { const double nrm = fdiv(r0, s[0]); s[0] = r0; s[1] *= nrm; s[2] *= nrm; s[3] *= nrm; }
+        else soft = 12;
+    }
+    const double c2 = 2.0 * nc2 * nc2 - 1.0;
+    double s2 = 2.0 * nc2 * fsqrt(fmax(1.0 - nc2 * nc2, 0.0));
+    if (flip) s2 = -s2;
+    Sout[0] = s[0];
+    Sout[1] = c2 * s[1] + s2 * s[2];
+    Sout[2] = c2 * s[2] - s2 * s[1];
+    Sout[3] = s[3];
+    return 0;
+}
+
 // Inversion of a 180-bin cumulative table: returns the bin lo with cum(lo) < samp <= cum(lo + 1) and the two
 // table values.  Three 6-ary rounds (steps 30, 5, 1; independent probes each) instead of eight dependent
 // binary-search steps: the same number of table reads, a third of the load round trips.  The last round reads
@@ -766,8 +806,6 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     int pix = -1;
     double W[4] = {0.0, 0.0, 0.0, 0.0};
     {
-        double F[16];
-        matrix_at_deg_f(T, u, peel_deg, F);
         if (!(fabs(dz) < 1.0)) err_count(A, 45);
         else {
             const double smu = fsqrt(1.0 - mu * mu);
@@ -782,7 +820,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
                 if (flip) s2a = -s2a;
                 const double nc2 = fdiv(dz - G.d2 * mu, smu * fsqrt(1.0 - G.d2 * G.d2));
                 int soft = 0;
-                const int e = (fabs(G.d2) < 1.0) ? polrot_f(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
+                const int e = (fabs(G.d2) < 1.0) ? polrot_deg_f(T, u, peel_deg, c2a, s2a, flip, nc2, S, W, true, soft) : 16;
                 if (e) err_count(A, e);
                 else if (!(W[0] > 0.0 && W[0] < 1.e100)) err_count(A, 53);
                 else {
@@ -823,11 +861,10 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
             }
         }
         if (!e) {
-            double F[16], Sn[4];
-            matrix_at_deg_f(T, u, g.deg, F);
+            double Sn[4];
             const double nc2 = fdiv(dz - e2 * g.alpha, g.sT * fsqrt(1.0 - e2 * e2));
             int soft = 0;
-            e = polrot_f(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
+            e = polrot_deg_f(T, u, g.deg, g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, Sn, false, soft);
             if (soft) err_count(A, soft);
             if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
         }
@@ -895,8 +932,9 @@ __device__ __forceinline__ bool ev_deposit(const Sh& X, const KernelArgs& A, boo
             v[4] = v[0] * v[0]; v[5] = v[1] * v[1]; v[6] = v[2] * v[2]; v[7] = v[3] * v[3];
         }
         const size_t npx = (size_t)L.nx * L.ny;
-        // the block-private image in shared memory when the launch has one (small detectors: launchers.inc), else the global one
-        double* const detbase = X.sdet ? X.sdet : A.O.det;
+        // always the global image here: a pointer that may be shared OR global would turn the reductions below into generic-address
+        // atomics.  (Block-private images are used by the multi-detector walks only, ev_fan; measured: profiles/r02_ab_variants.txt.)
+        double* const detbase = A.O.det;
         if (Sh::GEN && dep && pk != PK_SCATTER) {   // :4583-4585 / :4691-4693: Stokes I only
             double* d = detbase + pix;
             atomicAdd(d, w_i); atomicAdd(d + 4 * npx, w_i * w_i); atomicAdd(d + 8 * npx, 1.0);
@@ -1289,11 +1327,10 @@ __device__ __forceinline__ int ev_scatter_md(const Sh& X, const KernelArgs& A, b
         }
     }
     if (!e) {
-        double F[16], Sn[4];
-        matrix_at_deg_f(T, u, g.deg, F);
+        double Sn[4];
         const double nc2 = fdiv(dz - e2 * g.alpha, g.sT * fsqrt(1.0 - e2 * e2));
         int soft = 0;
-        e = polrot_f(g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, F, Sn, false, soft);
+        e = polrot_deg_f(T, u, g.deg, g.cb * g.cb - g.sb * g.sb, 2.0 * g.sb * g.cb, g.flip, nc2, S, Sn, false, soft);
         if (soft) err_count(A, soft);
         if (!e) { S[0] = Sn[0]; S[1] = Sn[1]; S[2] = Sn[2]; S[3] = Sn[3]; dx = e0; dy = e1; dz = e2; }
     }
@@ -1348,8 +1385,6 @@ __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, 
                 double mu = dx * G.d0 + dy * G.d1 + dz * G.d2;
                 if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
                 const double peel_deg = fm_acos(mu) * (180.0 / PI);
-                double F[16];
-                matrix_at_deg_f(T, u, peel_deg, F);
                 if (!dz_ok) err_count(A, 45);
                 else {
                     const double smu = fsqrt(1.0 - mu * mu);
@@ -1364,7 +1399,7 @@ __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, 
                         if (flip) s2a = -s2a;
                         const double nc2 = fdiv(dz - G.d2 * mu, smu * fsqrt(1.0 - G.d2 * G.d2));
                         int soft = 0;
-                        const int e = (fabs(G.d2) < 1.0) ? polrot_f(c2a, s2a, flip, nc2, S, F, W, true, soft) : 16;
+                        const int e = (fabs(G.d2) < 1.0) ? polrot_deg_f(T, u, peel_deg, c2a, s2a, flip, nc2, S, W, true, soft) : 16;
                         if (e) err_count(A, e);
                         else if (!(W[0] > 0.0 && W[0] < 1.e100)) err_count(A, 53);
                         else {
