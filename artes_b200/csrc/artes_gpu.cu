@@ -25,12 +25,16 @@ namespace artes {
 namespace faithful {
 size_t smem_bytes(int nr, int nt, int np);
 cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+cudaError_t launch_transport4(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+size_t engine3_scratch_bytes(int sm_count);
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
 }  // namespace faithful
 namespace fast {
 size_t smem_bytes(int nr, int nt, int np);
 cudaError_t launch_transport(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+cudaError_t launch_transport4(const KernelArgs& a, bool trace, int sm_count, cudaStream_t stream);
+size_t engine3_scratch_bytes(int sm_count);
 cudaError_t launch_cell_face(const DevTables& T, unsigned long long n, const double* pos, const double* dir,
                              const int* face, const int* cell, int* out_i, double* out_d, cudaStream_t stream);
 bool engine2_supports(const KernelArgs& a);
@@ -182,6 +186,11 @@ int ensure_outputs(artes_gpu_ctx* ctx, DeviceState& d, size_t n_d) {
 
 // Scheduling parameters are compile-time choices of the product library; the environment overrides exist only in a
 // tuning build (make TUNING=1 -> -DARTES_TUNING), which tools/gpu_tune.py uses for the measurements quoted in DESIGN.md.
+// photon records of the event-list engines (L2-resident working set): large enough for every engine
+size_t scratch_bytes(int sm_count) {
+    return std::max(fast::engine2_scratch_bytes(sm_count), std::max(fast::engine3_scratch_bytes(sm_count), faithful::engine3_scratch_bytes(sm_count)));
+}
+
 int env_int(const char* name, int dflt) {
 #ifdef ARTES_TUNING
     const char* v = std::getenv(name);
@@ -596,10 +605,19 @@ int artes_gpu_run_async(artes_gpu_ctx* ctx, const artes_launch_t* L) {
             static const int engine = env_int("ARTES_ENGINE", 2);
             cudaError_t e;
             ctx->last_engine = 1;
-            if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, false, d.sm_count, d.stream);
+            if (engine != 1 && !(engine == 2 && L->mode == ARTES_MODE_FAST && fast::engine2_supports(a))) {
+                // the event-list engine around the reference-order event bodies (engine3.cuh): the faithful mode, and what the
+                // ray/event engine leaves out in fast mode (flow_global, oblate planets)
+                ctx->last_engine = 3;
+                if (!d.scratch) CU(cudaMalloc(&d.scratch, scratch_bytes(d.sm_count)));
+                a.O.scratch = d.scratch;
+                e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport4(a, false, d.sm_count, d.stream)
+                                                     : fast::launch_transport4(a, false, d.sm_count, d.stream);
+            }
+            else if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, false, d.sm_count, d.stream);
             else if (engine == 2 && fast::engine2_supports(a)) {
                 ctx->last_engine = 2;
-                if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
+                if (!d.scratch) CU(cudaMalloc(&d.scratch, scratch_bytes(d.sm_count)));
                 a.O.scratch = d.scratch;
                 e = fast::launch_transport2(a, d.sm_count, d.stream);
             }
@@ -800,7 +818,7 @@ static int run_batch_impl(artes_gpu_ctx* ctx, const artes_launch_t* Ls, int n, d
         CU(cudaEventRecord(d.ev[0], d.stream));
         d.launches = 0;
         if (a.L.n_photons > 0) {
-            if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
+            if (!d.scratch) CU(cudaMalloc(&d.scratch, scratch_bytes(d.sm_count)));
             a.O.scratch = d.scratch;
             cudaError_t e = fast::launch_transport2(a, d.sm_count, d.stream);
             if (e != cudaSuccess) return fail(ctx, -2, std::string("transport launch: ") + cudaGetErrorString(e));
@@ -934,10 +952,17 @@ int artes_gpu_trace(artes_gpu_ctx* ctx, const artes_launch_t* L, const double* x
     static const int engine = env_int("ARTES_ENGINE", 2);
     cudaError_t e;
     ctx->last_engine = 1;
-    if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, true, d.sm_count, d.stream);
+    if (engine != 1 && !(engine == 2 && L->mode == ARTES_MODE_FAST && fast::engine2_supports(a))) {
+        ctx->last_engine = 3;
+        if (!d.scratch) CU(cudaMalloc(&d.scratch, scratch_bytes(d.sm_count)));
+        a.O.scratch = d.scratch;
+        e = (L->mode == ARTES_MODE_FAITHFUL) ? faithful::launch_transport4(a, true, d.sm_count, d.stream)
+                                             : fast::launch_transport4(a, true, d.sm_count, d.stream);
+    }
+    else if (L->mode == ARTES_MODE_FAITHFUL) e = faithful::launch_transport(a, true, d.sm_count, d.stream);
     else if (engine == 2 && fast::engine2_supports(a)) {
         ctx->last_engine = 2;
-        if (!d.scratch) CU(cudaMalloc(&d.scratch, fast::engine2_scratch_bytes(d.sm_count)));
+        if (!d.scratch) CU(cudaMalloc(&d.scratch, scratch_bytes(d.sm_count)));
         a.O.scratch = d.scratch;
         e = fast::launch_transport2_trace(a, d.sm_count, d.stream);
     } else e = fast::launch_transport(a, true, d.sm_count, d.stream);

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NT, MINB) transport4_kernel(const __grid_const
     // push the slots of the warp's lanes on the lists their photons need next (lst < 0: nothing to push)
     auto push = [&](int lst, int s) {
         if (__any_sync(FULL, lst >= 0)) {
-            __threadfence();                              // the photon records (global memory) before the list cells
+            __threadfence_block();                        // the photon records (global memory, same block) before the list cells
             const unsigned g = __match_any_sync(FULL, lst);
             const int leader = __ffs(g) - 1;
             int base = 0;
@@ -147,14 +147,13 @@ __global__ void __launch_bounds__(NT, MINB) transport4_kernel(const __grid_const
         }
         base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
         if (lane < n) s = ring_take(Q(l, base + lane), abort_word);
-        if (n > 0) __threadfence();
+        if (n > 0) __threadfence_block();
         return n;
     };
 
     Photon P;
     for (;;) {
         if (__shfl_sync(FULL, (int)vmisc[0], 0) >= NP) break;
-        if (__shfl_sync(FULL, (int)(*(volatile unsigned long long*)abort_word != 0ull), 0)) break;
         // ---- a pass of the walk: claim ready photons, `inner` crossings in lock step, everything back to the pool
         int s = -1;
         const int nw = take(L_RDY, 32, s);
@@ -203,8 +202,6 @@ __global__ void __launch_bounds__(NT, MINB) transport4_kernel(const __grid_const
                     if (l == L_DEP) ev_peel_done<TRACE, GEN>(X, P, C);
                     else if (l == L_SC) ev_scatter<TRACE>(X, P, C);
                     else if (GEN) ev_lambert<TRACE>(X, P, C);
-                    // an event may leave the photon in a state one of the cheap follow-ups resolves (a retirement, ...)
-                    cheap_handlers<TRACE, GEN>(X, P, C);
                 }
                 int lst = -1;
                 if (valid) {
@@ -213,6 +210,9 @@ __global__ void __launch_bounds__(NT, MINB) transport4_kernel(const __grid_const
                 }
                 push(lst, se);
             }
+        } else if (nw == 0) {
+            // nothing to walk and no event: an idle turn; leave if a bounded wait somewhere raised the abort word
+            if (__shfl_sync(FULL, (int)(*(volatile unsigned long long*)abort_word != 0ull), 0)) break;
         }
     }
     C.flush(A.O.stats);

@@ -227,9 +227,9 @@ int  artes_gpu_cell_face(artes_gpu_ctx* ctx, int mode, uint64_t n, const double*
 int  artes_gpu_device_info(const artes_gpu_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
                            char* name, int name_len);
 
-/* Which transport engine the last run / trace of this context used: 1 = persistent-lane engine (faithful mode;
- * fast mode with flow_global or an oblate planet), 2 = ray/event engine (fast mode, everything else).  Lets tests
- * assert that the production path is the one that ran. */
+/* Which transport engine the last run / trace of this context used: 2 = ray/event engine (fast mode), 3 = event-list engine
+ * around the reference-order event bodies (faithful mode; fast mode with flow_global or an oblate planet), 1 = persistent-lane
+ * engine (tuning builds only).  Lets tests assert that the production path is the one that ran. */
 int  artes_gpu_last_engine(const artes_gpu_ctx* ctx);
 
 /* FP64 / FP32 FMA peak microbenchmark (roofline denominator): returns TFLOP/s. */

@@ -112,7 +112,7 @@ def test_crossing_sequences_bit_exact_vs_oracle(atmospheres, oracle_factory, gpu
     ro = o.trace(L, xi, max_rec=4)
     rg = g.trace(L, xi, max_rec=4)
     # fast mode walks the ray/event engine (the production path); the faithful mode the persistent-lane engine
-    assert g.last_engine() == (2 if mode == abi.MODE_FAST else 1)
+    assert g.last_engine() == (2 if mode == abi.MODE_FAST else 3)
     same = (ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])
     assert same.all(), f"{(~same).sum()} of {n} sequences differ"
     np.testing.assert_array_equal(ro["head"], rg["head"])
@@ -140,7 +140,7 @@ def test_trace_thermal_source(atmospheres, oracle_factory):
             L = make_launch(mode=mode, n_photons=n, x_max=xm, y_max=xm, fstop=0.03, photon_source=2,
                             photon_emission=emission, nx=1, ny=1)
             ro, rg = o.trace(L, xi), g.trace(L, xi)
-            assert g.last_engine() == (2 if mode == abi.MODE_FAST else 1)
+            assert g.last_engine() == (2 if mode == abi.MODE_FAST else 3)
             assert ((ro["hash"] == rg["hash"]) & (ro["len"] == rg["len"])).all()
         L = make_launch(mode=abi.MODE_FAST, n_photons=n, x_max=xm, y_max=xm, seed=3, photon_source=2,
                         photon_emission=emission, nx=1, ny=1)
@@ -271,7 +271,7 @@ def test_fast_mode_oblate_planet_same_stream(atmospheres):
     xm = 1.06 * 1.3 * atm.rfront[-1]
     L = make_launch(mode=abi.MODE_FAST, n_photons=40000, x_max=xm, y_max=xm, seed=9, nx=32, ny=32, det_phi=math.radians(100.0))
     a, b = o.run(L), g.run(L)
-    assert g.last_engine() == 1
+    assert g.last_engine() == 3
     assert abs(a["stats"]["n_cell_face"] - b["stats"]["n_cell_face"]) <= max(2, 2e-5 * a["stats"]["n_cell_face"])
     assert a["stats"]["n_scatter"] == b["stats"]["n_scatter"] or abs(a["stats"]["n_scatter"] - b["stats"]["n_scatter"]) <= 3
     np.testing.assert_allclose(b["det"][0].sum(axis=(1, 2)), a["det"][0].sum(axis=(1, 2)), rtol=2e-5, atol=1e-9)

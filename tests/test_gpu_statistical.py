@@ -49,7 +49,8 @@ def test_images_agree_within_photon_noise(atmospheres, oracle_factory, gpu_facto
 
 
 def test_faithful_mode_image_agrees_within_photon_noise(atmospheres, oracle_factory, gpu_factory):
-    """The faithful mode (persistent-lane engine) through the same gate, on the 3-D Mie configuration."""
+    """The faithful mode (reference-order arithmetic on the event-list engine, engine3.cuh) through the same gate, on the 3-D
+    Mie configuration."""
     atm = atmospheres("c4_mie_patches")
     o, _ = oracle_factory(atm)
     g, _ = gpu_factory(atm)
@@ -57,7 +58,7 @@ def test_faithful_mode_image_agrees_within_photon_noise(atmospheres, oracle_fact
     kw = dict(x_max=xm, y_max=xm, nx=64, ny=64, det_phi=math.radians(60.0))
     ba = _oracle_batches(o, 32, 12000, 3000, **kw)
     bb = _gpu_batches(g, 32, 12000, 11, mode=abi.MODE_FAITHFUL, **kw)
-    assert g.last_engine() == 1
+    assert g.last_engine() == 3
     stat_gate.assert_gate(stat_gate.z_report(ba, bb), names=("I", "Q", "U", "P"), min_valid=500, what="c4 faithful")
 
 
