@@ -410,28 +410,17 @@ __device__ __forceinline__ int sample_angles(const double* __restrict__ sm, cons
 #if ARTES_FAITHFUL
     const double* c2t = sm + lay.o_c2;
     const double* s2t = sm + lay.o_s2;
-    // The running sum of the first pass is remembered every 30 bins.  If no bin was negative the sums are non-decreasing, the
-    // first bin with prev <= samp <= cur lies after the last checkpoint strictly below samp, and the search pass resumes there
-    // with the checkpointed sum -- the same additions in the same order as the full scan, ~15 iterations instead of ~90.
     double cum = 0.0;
-    double ck[6];
-    bool mono = true;
-    for (int b = 0; b < 6; ++b) {
-        for (int i = 30 * b; i < 30 * b + 30; ++i) {
-            double v = p11 * S[0] + p12 * S[1] * c2t[i] + p12 * S[2] * s2t[i] - p13 * S[1] * s2t[i] + p13 * S[2] * c2t[i] + p14 * S[3];
-            if (v < 0.0) mono = false;
-            cum = cum + v;
-        }
-        ck[b] = cum;
+    for (int i = 0; i < 180; ++i) {
+        double v = p11 * S[0] + p12 * S[1] * c2t[i] + p12 * S[2] * s2t[i] - p13 * S[1] * s2t[i] + p13 * S[2] * c2t[i] + p14 * S[3];
+        cum = cum + v;
     }
     double xi = rng_next<TRACE>(rng, A);
     double samp = xi * cum;
     bool found = false;
     double prev = 0.0;
     beta = 0.0;
-    int i0 = 0;
-    if (mono) for (int b = 4; b >= 0; --b) if (ck[b] < samp) { i0 = 30 * b + 30; prev = ck[b]; break; }
-    for (int i = i0; i < 180; ++i) {
+    for (int i = 0; i < 180; ++i) {
         double v = p11 * S[0] + p12 * S[1] * c2t[i] + p12 * S[2] * s2t[i] - p13 * S[1] * s2t[i] + p13 * S[2] * c2t[i] + p14 * S[3];
         double cur = prev + v;
         if (samp >= prev && samp <= cur) {
@@ -478,25 +467,18 @@ __device__ __forceinline__ int sample_angles(const double* __restrict__ sm, cons
     const double* sbt = sm + lay.o_sb;
     const double2* row = reinterpret_cast<const double2*>(T.Mrow + (size_t)u * 720);
     cum = 0.0;
-    mono = true;
-    for (int b = 0; b < 6; ++b) {
-        for (int i = 30 * b; i < 30 * b + 30; ++i) {
-            double2 m01 = __ldg(row + 2 * i), m23 = __ldg(row + 2 * i + 1);
-            double v = m01.x * S[0] + m01.y * c2b * S[1] + m01.y * s2b * S[2] - m23.x * s2b * S[1] + m23.x * c2b * S[2] + m23.y * S[3];
-            v = v * sbt[i] * PI / 180.0;
-            if (v < 0.0) mono = false;
-            cum = cum + v;
-        }
-        ck[b] = cum;
+    for (int i = 0; i < 180; ++i) {
+        double2 m01 = __ldg(row + 2 * i), m23 = __ldg(row + 2 * i + 1);
+        double v = m01.x * S[0] + m01.y * c2b * S[1] + m01.y * s2b * S[2] - m23.x * s2b * S[1] + m23.x * c2b * S[2] + m23.y * S[3];
+        v = v * sbt[i] * PI / 180.0;
+        cum = cum + v;
     }
     xi = rng_next<TRACE>(rng, A);
     samp = xi * cum;
     found = false;
     prev = 0.0;
     alpha = 0.0;
-    i0 = 0;
-    if (mono) for (int b = 4; b >= 0; --b) if (ck[b] < samp) { i0 = 30 * b + 30; prev = ck[b]; break; }
-    for (int i = i0; i < 180; ++i) {
+    for (int i = 0; i < 180; ++i) {
         double2 m01 = __ldg(row + 2 * i), m23 = __ldg(row + 2 * i + 1);
         double v = m01.x * S[0] + m01.y * c2b * S[1] + m01.y * s2b * S[2] - m23.x * s2b * S[1] + m23.x * c2b * S[2] + m23.y * S[3];
         v = v * sbt[i] * PI / 180.0;
