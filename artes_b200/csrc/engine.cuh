@@ -564,6 +564,7 @@ __device__ __forceinline__ void ev_scatter(const Ctx& X, Photon& P, Counters& C)
     }
 }
 
+#ifdef ARTES_TUNING   // comparison kernel, tuning builds only: the product schedules these event bodies from engine3.cuh
 // =====================================================================================================
 // Engine 1: persistent lanes (one lane keeps one photon), events ballot-deferred
 // =====================================================================================================
@@ -636,3 +637,4 @@ __global__ void __launch_bounds__(128, 4) transport_kernel(const __grid_constant
     }
     C.flush(A.O.stats);
 }
+#endif  // ARTES_TUNING

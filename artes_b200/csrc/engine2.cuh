@@ -1346,40 +1346,44 @@ __device__ __forceinline__ int ev_scatter_md(const Sh& X, const KernelArgs& A, b
 }
 
 // FAN (multi): peel-off of the n photons of the batch (lane j holds slot s of photon j) towards every detector.
-// One photon at a time, lanes = detectors.  The photon's record is read with warp-uniform addresses (one transaction),
-// the matrix rows of the 32 detectors come from the same 23 KB block, and the walk to the detector runs in the lane.
+// The n x K (photon, detector) pairs are dealt to the lanes 32 at a time, so that a round is full whatever K is (68 detectors
+// as 32 + 32 + 4 lanes per photon wasted a third of the lanes).  A round touches at most two or three photons: their records
+// are read with one or two distinct addresses per instruction, the matrix rows of the detectors come from the same 23 KB
+// blocks, and the walk to the detector runs in the lane.
 template <class Sh>
 __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, int s_lane, Cnt& C) {
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
     const int lane = threadIdx.x & 31;
     const int K = L.n_batch;
+    const int total = n * K;
     const size_t npx = (size_t)L.nx * L.ny;
 #pragma unroll 1
-    for (int j = 0; j < n; ++j) {
-        const int sp = __shfl_sync(FULL, s_lane, j);
-        const double* rec = X.cold + (size_t)sp * REC;
-        double px, py, pz, dx, dy, dz, S[4], t0_, t1_;
-        ldg256(rec, px, py, pz, dx);
-        ldg256(rec + 4, dy, dz, S[0], S[1]);
-        ldg256(rec + 8, S[2], S[3], t0_, t1_);
-        (void)t0_; (void)t1_;
-        const int cell = X.I(I_HCELL, sp);
-        const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
-        const int ci = c0 + T.nr * (c1 + T.nt * c2);
-        double kap_c, alb_c, u_bits, pad_c;
-        ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
-        (void)alb_c; (void)pad_c;
-        const int u = (int)__double_as_longlong(u_bits);
-        const bool dz_ok = fabs(dz) < 1.0;
-        const double idz = dz_ok ? frcp(fsqrt(1.0 - dz * dz)) : 0.0;
-#pragma unroll 1
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int kd = k0 + lane;
-            const bool act = kd < K;
+    for (int it = 0; it < total; it += 32) {
+        {
+            const int item = it + lane;
+            const bool act = item < total;
+            const int j = act ? item / K : 0;
+            const int kd = act ? item - j * K : 0;
+            const int sp = __shfl_sync(FULL, s_lane, j);
+            const double* rec = X.cold + (size_t)sp * REC;
+            double px, py, pz, dx, dy, dz, S[4], t0_, t1_;
+            ldg256(rec, px, py, pz, dx);
+            ldg256(rec + 4, dy, dz, S[0], S[1]);
+            ldg256(rec + 8, S[2], S[3], t0_, t1_);
+            (void)t0_; (void)t1_;
+            const int cell = X.I(I_HCELL, sp);
+            const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+            const int ci = c0 + T.nr * (c1 + T.nt * c2);
+            double kap_c, alb_c, u_bits, pad_c;
+            ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
+            (void)alb_c; (void)pad_c; (void)kap_c;
+            const int u = (int)__double_as_longlong(u_bits);
+            const bool dz_ok = fabs(dz) < 1.0;
+            const double idz = dz_ok ? frcp(fsqrt(1.0 - dz * dz)) : 0.0;
             double W[4] = {0.0, 0.0, 0.0, 0.0};
             int pix = -1;
-            Geo G = geo_of(X, L, act ? kd : 0);
+            Geo G = geo_of(X, L, kd);
             if (act) {
                 ++C.n_peel;
                 double mu = dx * G.d0 + dy * G.d1 + dz * G.d2;
@@ -1827,7 +1831,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             int base = 0, n = 0;
             if (lane == 0) {
                 const int h = vhead[l];
-                n = min((Sh::MULTI && l == L_FAN) ? 4 : 32, vtail[l] - h);
+                n = min((Sh::MULTI && l == L_FAN) ? 8 : 32, vtail[l] - h);
                 if (n > 0 && atomicCAS(X.head + l, h, h + n) == h) base = h; else n = 0;
             }
             base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
