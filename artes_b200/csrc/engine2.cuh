@@ -62,6 +62,15 @@ namespace e2 {
 #ifndef E2_OPT_R2S
 #define E2_OPT_R2S 1       // squared radii through ld.shared with a 32-bit address
 #endif
+#ifndef E2_RELEASE
+#define E2_RELEASE 0       // 1: a warp keeps no ray across passes -- unfinished rays go back to the ready list, and a pass starts only
+#endif                     //    with at least E2_MARCH_MIN ready rays (or when there is no full event batch to run instead)
+#ifndef E2_MARCH_MIN
+#define E2_MARCH_MIN 24
+#endif
+#ifndef E2_EVENT_POLICY
+#define E2_EVENT_POLICY 1  // which event list a warp serves: 1 the one with the largest backlog, 0 a fixed priority order (RES, DEP, H, SURF, PRE, EMIT)
+#endif
 #ifndef E2_WATCHDOG
 #define E2_WATCHDOG 1      // 1: bounded waits on list cells (see ring_take); 2: also the idle-turn watchdog of the scheduling loop
 #endif                     //    (measured 4-5 % on C4, profiles/r02_g_*: debug / stress builds only, tools/gpu_stress.py)
@@ -1215,6 +1224,15 @@ struct Marcher {
         return c_list[kind][out];
     }
 
+    // the pass ended before the ray did: write back what a step changes, so that any lane can go on with it (E2_RELEASE)
+    template <class Sh>
+    __device__ __forceinline__ void release(const Sh& X) {
+        X.D(F_T, slot) = t; X.D(F_ACC, slot) = acc; X.D(F_TR, slot) = tr;
+        X.I(I_CELL, slot) = cell12 | c0;
+        X.I(I_INFO, slot) = (info & 0xff & ~B_INWARD) | (dr < 0 ? B_INWARD : 0);
+        if (Sh::TRACE) { X.I(I_TLEN, slot) = tl; X.I(I_THLO, slot) = (int)(unsigned)th; X.I(I_THHI, slot) = (int)(unsigned)(th >> 32); }
+    }
+
     template <class Sh>
     __device__ __forceinline__ int trip(const Sh& X, const KernelArgs& A, Cnt& C) {
         if ((info & 3) == K_DEAD) return finish(X, A, C, O_DEAD);
@@ -1753,6 +1771,11 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
                 for (;;) {
                     n = min(want, vtail[L_RDY] - h);
                     if (n <= 0) { n = 0; break; }
+                    if (E2_RELEASE && n < E2_MARCH_MIN) {      // a thin pass only if no event list holds a full batch to run instead
+                        bool full_event = false;
+                        for (int q = 0; q < N_EVENT_LISTS; ++q) full_event = full_event || (vtail[q] - vhead[q] >= 32);
+                        if (full_event) { n = 0; break; }
+                    }
                     const int old = atomicCAS(X.head + L_RDY, h, h + n);
                     if (old == h) { base = h; break; }
                     h = old;
@@ -1760,6 +1783,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             }
             base = __shfl_sync(FULL, base, 0); n = __shfl_sync(FULL, n, 0);
             rdy_empty = n < __popc(fm);
+            if (E2_RELEASE) rdy_empty = (n == 0);      // (no ray is kept across passes: "starving" = this turn marched nothing)
             const int rank = __popc(fm & lt);
             if (M.slot < 0 && rank < n) {
                 const int s = ring_take(&X.Q(L_RDY, base + rank), A.O.err + ERR_WATCHDOG);
@@ -1787,6 +1811,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             }
             C.n_cf += n_step;
             if (M.slot >= 0 && out != O_NONE) lst = M.finish(X, A, C, out);
+            else if (E2_RELEASE && M.slot >= 0) { M.release(X); lst = L_RDY; }
         }
         // ---- push ended rays on their event lists
         if (__any_sync(FULL, lst >= 0)) {
@@ -1821,6 +1846,14 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
             else if (anym && rdy_empty && nactive < starve)
                 l = (anym & (1u << L_RES)) ? L_RES : (anym & (1u << L_H)) ? L_H : (anym & (1u << L_SC)) ? L_SC
                     : (anym & (1u << L_PRE)) ? L_PRE : L_EMIT;
+        } else if (E2_EVENT_POLICY == 1) {
+            // the list with the largest backlog (full batches first; partial ones only when this warp is starving).  With a fixed
+            // priority order the lists at its end -- EMIT above all -- were served only when nothing else had a full batch: dead
+            // slots piled up there, the block walked a fraction of its 512 photons and the lanes ran short of rays
+            // (-DE2_STATS: 12.7 of 32 lanes held a ray at the start of a pass on C4, 61 % of the claims found the ready list empty).
+            const int mine = (lane < N_EVENT_LISTS) ? av : 0;
+            const int mx = __reduce_max_sync(FULL, mine);
+            if (mx >= 32 || (mx > 0 && rdy_empty && nactive < starve)) l = __ffs(__ballot_sync(FULL, lane < N_EVENT_LISTS && av == mx)) - 1;
         } else if (fullm)
             l = (fullm & (1u << L_RES)) ? L_RES : (fullm & (1u << L_DEP)) ? L_DEP : (fullm & (1u << L_H)) ? L_H
                 : (fullm & (1u << L_SURF)) ? L_SURF : (fullm & (1u << L_PRE)) ? L_PRE : L_EMIT;
