@@ -758,9 +758,17 @@ __device__ __forceinline__ bool ev_pre(const Sh& X, const KernelArgs& A, bool va
 
 // H: the transport walk reached its optical depth.  Survival :791-813, peel-off weight and pixel (peel_photon
 // :4763-4951; the e^-tau factor is applied by DEP once the peel ray has been walked), scattering :819-845.
+// (defined after the marcher, below)
 template <class Sh>
-__device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
-    if (!valid) return false;
+__device__ __forceinline__ int march_inline(const Sh& X, const KernelArgs& A, double px, double py, double pz, double n0, double n1, double n2,
+                                            int cell, int slot, double lim, double& acc_out, unsigned& n_step);
+__device__ __forceinline__ void deposit_scatter_warp(const KernelArgs& A, bool dep, int pix, const double v[8]);
+
+struct HOut { double px, py, pz, dx, dy, dz, tau, W[4]; int pix, cell, kb; };
+// returns 0: idle lane, 1: the photon died (survival test), 2: scattered -- `o` holds the peel-off weights and the new state
+template <class Sh>
+__device__ __forceinline__ int interact_core(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, HOut& o) {
+    if (!valid) return 0;
     const DevTables& T = A.T;
     const LaunchArgs& L = A.L;
     const int cell = X.I(I_CELL, s);
@@ -808,7 +816,7 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
             X.D(F_PX, s) = px; X.D(F_PY, s) = py; X.D(F_PZ, s) = pz;
             X.D(F_S0, s) = S[0]; X.D(F_S1, s) = S[1]; X.D(F_S2, s) = S[2]; X.D(F_S3, s) = S[3];
         }
-        return true;
+        return 1;
     }
     // ---- peel-off towards the detector: Stokes vector scattered into det, pixel
     ++C.n_peel;
@@ -888,8 +896,57 @@ __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bo
     if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, tau0, X.D(F_ACC, s), X.D(F_T, s));
 #endif
     X.I(I_ND, s) = (int)nd;
-    rs.set(px, py, pz, G.d0, G.d1, G.d2, c0, c1, c2, -1, K_PEEL, CUDART_INF);
-    return true;
+    o.px = px; o.py = py; o.pz = pz; o.dx = dx; o.dy = dy; o.dz = dz; o.tau = tau;
+    o.W[0] = W[0]; o.W[1] = W[1]; o.W[2] = W[2]; o.W[3] = W[3]; o.pix = pix; o.cell = cell; o.kb = kb;
+    return 2;
+}
+
+#ifndef E2_INLINE_PEEL
+#define E2_INLINE_PEEL 1   // 1: the peel-off walk of a scattering is marched inside the interaction event (no peel ray, no DEP event)
+#endif
+template <class Sh>
+__device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
+    HOut o;
+    const int st = interact_core(X, A, valid, s, C, o);
+    const LaunchArgs& L = A.L;
+    if (!E2_INLINE_PEEL) {
+        if (st == 2) {
+            const Geo G = geo_of(X, L, o.kb);
+            rs.set(o.px, o.py, o.pz, G.d0, G.d1, G.d2, o.cell & 1023, (o.cell >> 10) & 1023, (o.cell >> 20) & 1023, -1, K_PEEL, CUDART_INF);
+        }
+        return st != 0;
+    }
+    // ---- the walk to the detector in the lane (:4739-4761), e^-tau and the deposit (:4955-4972), then the transport ray of the
+    // scattered photon: what the peel ray and the DEP event did, without their trips through the lists and the photon record
+    bool dep = false, dead = false;
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (st == 2) {
+        const Geo G = geo_of(X, L, o.kb);
+        unsigned n_step = 0;
+        double acc = 0.0;
+        const int out = march_inline(X, A, o.px, o.py, o.pz, G.d0, G.d1, G.d2, o.cell, s, CUDART_INF, acc, n_step);
+        C.n_cf += n_step;
+        if (out == O_ERR) { err_count(A, 31); ++C.n_err; err_count(A, 43); dead = true; }      // (as Marcher::finish: the photon is dropped)
+        dep = (out == O_EXIT && acc < 50.0 && o.pix >= 0);
+        if (dep) {
+            const double w = fm_exp_neg(acc);
+            v[0] = w * o.W[0]; v[1] = -(w * o.W[1]); v[2] = w * o.W[2]; v[3] = w * o.W[3];
+            v[4] = v[0] * v[0]; v[5] = v[1] * v[1]; v[6] = v[2] * v[2]; v[7] = v[3] * v[3];
+            if (Sh::TRACE) {   // the reference's deposit point in the walk record: (100, ix, iy, 0, 0)
+                const unsigned long long pid = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+                int tl = X.I(I_TLEN, s);
+                unsigned long long th = (unsigned long long)(unsigned)X.I(I_THLO, s) | ((unsigned long long)(unsigned)X.I(I_THHI, s) << 32);
+                trace_tuple(A, pid, tl, th, 100, o.pix % L.nx + 1, o.pix / L.nx + 1, 0, 0);
+                X.I(I_TLEN, s) = tl; X.I(I_THLO, s) = (int)(unsigned)th; X.I(I_THHI, s) = (int)(unsigned)(th >> 32);
+            }
+        }
+    }
+    deposit_scatter_warp(A, dep, o.pix, v);
+    if (st == 2) {
+        if (dead || o.tau < 0.0) X.I(I_INFO, s) = K_DEAD;
+        else rs.set(o.px, o.py, o.pz, o.dx, o.dy, o.dz, o.cell & 1023, (o.cell >> 10) & 1023, (o.cell >> 20) & 1023, -1, K_WALK, o.tau);
+    }
+    return st != 0;
 }
 
 // DEP: the peel ray ended -> e^-tau, detector deposit :4955-4972; then the transport ray of the scattered photon
@@ -1245,6 +1302,113 @@ struct Marcher {
 
 
 // ---------------------------------------------------------------------------------------------------
+// A ray marched INSIDE an event, by the lane that owns the photon (multi-detector fan-out; peel-off walk of the interaction
+// event with E2_INLINE_PEEL): no slot, no list, no record traffic -- the ray state never leaves registers, polar / azimuthal
+// faces are re-solved inline.  Returns the outcome (O_EXIT, O_SURF, O_LIMIT, O_ERR) and the optical depth walked.
+// ---------------------------------------------------------------------------------------------------
+template <class Sh>
+__device__ __forceinline__ int march_inline(const Sh& X, const KernelArgs& A, double px, double py, double pz, double n0, double n1, double n2,
+                                            int cell, int slot, double lim, double& acc_out, unsigned& n_step) {
+    const DevTables& T = A.T;
+    const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
+    Marcher M;
+    M.init(T); M.bind(X);
+    int inward, upper = 0, up = 0;
+    {
+        RayK Kc;       // the quadric constants are needed for the first solves only; a polar / azimuthal crossing (rare) rebuilds them,
+        double hbn, D0, iq;      // so that they do not occupy 28 registers while the ray is marched
+        ray_consts(T, px, py, pz, n0, n1, n2, Kc, hbn, D0, iq);
+        M.tr = radial_first(X, c0, -1, hbn, D0, iq, inward);
+        M.tt = (T.nt > 1) ? theta_next(X, T.nt, c1, 0.0, Kc, upper) : RAY_NONE;
+        M.tp = phi_next(X, T.np, c2, 0.0, Kc, up);
+        M.hbn = hbn; M.D0 = D0; M.iq = iq;
+    }
+    M.t = 0.0; M.acc = 0.0; M.lim = lim;
+    M.c0 = c0; M.cell12 = cell & ~1023;
+    M.info = K_PEEL | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
+    M.dr = inward ? -1 : 1; M.ds = inward ? -1.0 : 1.0;
+    M.kb = M.kext + T.nr * (c1 + T.nt * c2);
+    if (Sh::BATCH && A.L.wl_batch) {       // wavelength batch: the opacity table and the surface layer of the photon's launch
+        const int kbi = X.I(I_BATCH, slot);
+        M.kb += (size_t)wl_of(X, A, kbi) * T.cells;
+        M.depth = depth_of(X, A, kbi);
+    }
+    M.load_kap();
+    M.slot = slot;
+    if (Sh::TRACE) {
+        M.tl = X.I(I_TLEN, slot);
+        M.th = (unsigned long long)(unsigned)X.I(I_THLO, slot) | ((unsigned long long)(unsigned)X.I(I_THHI, slot) << 32);
+        M.pid = (unsigned long long)(unsigned)X.I(I_IDLO, slot) | ((unsigned long long)(unsigned)X.I(I_IDHI, slot) << 32);
+    }
+    int out;
+#pragma unroll 1
+    for (;;) {
+        out = M.step(X, A, n_step);
+        if (out == O_NONE) continue;
+        if (out != O_REST && out != O_RESP) break;
+        // a polar or azimuthal face: move the cell index and re-solve that axis (the RES event, inline)
+        int cc1 = (M.cell12 >> 10) & 1023, cc2 = (M.cell12 >> 20) & 1023;
+        RayK Kc;
+        double h_, d_, i_;
+        ray_consts(T, px, py, pz, n0, n1, n2, Kc, h_, d_, i_);
+        if (out == O_REST) {
+            cc1 += (M.info & B_TUPPER) ? 1 : -1;
+            int up2;
+            M.tt = theta_next(X, T.nt, cc1, M.t, Kc, up2);
+            M.info = (M.info & ~B_TUPPER) | (up2 ? B_TUPPER : 0);
+        } else {
+            if (M.info & B_PUP) cc2 = (cc2 + 1 == T.np) ? 0 : cc2 + 1; else cc2 = (cc2 == 0) ? T.np - 1 : cc2 - 1;
+            int up2;
+            M.tp = phi_next(X, T.np, cc2, M.t, Kc, up2);
+        }
+        M.cell12 = (cc1 << 10) | (cc2 << 20);
+        const size_t wl_off = (size_t)(M.kb - M.kext) / (size_t)T.cells * (size_t)T.cells;      // (0 unless a wavelength batch)
+        M.kb = M.kext + wl_off + T.nr * (cc1 + T.nt * cc2);
+        M.load_kap();
+    }
+    if (Sh::TRACE) { X.I(I_TLEN, slot) = M.tl; X.I(I_THLO, slot) = (int)(unsigned)M.th; X.I(I_THHI, slot) = (int)(unsigned)(M.th >> 32); }
+    acc_out = M.acc;
+    return out;
+}
+
+// Deposit of a scattering peel-off (:4955-4972), called by the WHOLE warp: lanes that hit the same pixel are summed in the warp first
+// (up to four pixel groups: 1x1 detectors, launch boundaries of a batched launch); what is left goes lane by lane.  Always to the
+// global image: a pointer that may be shared OR global would turn these reductions into generic-address atomics.
+__device__ __forceinline__ void deposit_scatter_warp(const KernelArgs& A, bool dep, int pix, const double v[8]) {
+    const unsigned dm = __ballot_sync(FULL, dep);
+    if (!dm) return;
+    const LaunchArgs& L = A.L;
+    const size_t npx = (size_t)L.nx * L.ny;
+    unsigned rem = dm, left = 0u;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int it = 0; it < 4 && rem; ++it) {
+        const int pixg = __shfl_sync(FULL, pix, __ffs(rem) - 1);
+        const unsigned grp = __ballot_sync(FULL, ((rem >> lane) & 1u) && pix == pixg);
+        rem &= ~grp;
+        if (__popc(grp) <= 2) { left |= grp; continue; }
+        const bool in = (grp >> lane) & 1u;
+        double x = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double r = in ? v[k] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+            if (lane == k) x = r;
+        }
+        double* d = A.O.det + pixg;
+        if (lane < 8) atomicAdd(d + (size_t)lane * npx, x);
+        else if (lane < 10) atomicAdd(d + (size_t)lane * npx, (double)__popc(grp));
+    }
+    left |= rem;
+    if ((left >> lane) & 1u) {
+        double* d = A.O.det + pix;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(d + (size_t)k * npx, v[k]);
+        atomicAdd(d + 8 * npx, 1.0); atomicAdd(d + 9 * npx, 1.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Multi-detector walks (ShT::MULTI, artes_gpu_run_multi).  The reference runs the whole random walk once per detector
 // azimuth of a phase curve (src/ARTES.f90:215-245: 73 calls of radiative_transfer that differ in det_phi only).  Peel-off
 // is a next-event estimate: at every scattering the walk may be observed from ANY direction without disturbing it, so
@@ -1437,49 +1601,13 @@ __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, 
             }
             // ---- the walk to the detector (:4739-4761), in the lane; stops once tau >= 50 (the reference drops those, :4765)
             if (pix >= 0) {
-                Marcher M;
-                M.init(T); M.bind(X);
-                RayK Kc;
-                double hbn, D0, iq;
-                ray_consts(T, px, py, pz, G.d0, G.d1, G.d2, Kc, hbn, D0, iq);
-                int inward, upper = 0, up = 0;
-                M.tr = radial_first(X, c0, -1, hbn, D0, iq, inward);
-                M.tt = (T.nt > 1) ? theta_next(X, T.nt, c1, 0.0, Kc, upper) : RAY_NONE;
-                M.tp = phi_next(X, T.np, c2, 0.0, Kc, up);
-                M.t = 0.0; M.acc = 0.0; M.hbn = hbn; M.D0 = D0; M.iq = iq; M.lim = 50.0;
-                M.c0 = c0; M.cell12 = cell & ~1023;
-                M.info = K_PEEL | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
-                M.dr = inward ? -1 : 1; M.ds = inward ? -1.0 : 1.0;
-                M.kb = M.kext + T.nr * (c1 + T.nt * c2);
-                M.load_kap();
-                M.slot = sp;
                 unsigned n_step = 0;
-                int out;
-#pragma unroll 1
-                for (;;) {
-                    out = M.step(X, A, n_step);
-                    if (out == O_NONE) continue;
-                    if (out != O_REST && out != O_RESP) break;
-                    // a polar or azimuthal face: move the cell index and re-solve that axis (the RES event, inline)
-                    int cc1 = (M.cell12 >> 10) & 1023, cc2 = (M.cell12 >> 20) & 1023;
-                    if (out == O_REST) {
-                        cc1 += (M.info & B_TUPPER) ? 1 : -1;
-                        int up2;
-                        M.tt = theta_next(X, T.nt, cc1, M.t, Kc, up2);
-                        M.info = (M.info & ~B_TUPPER) | (up2 ? B_TUPPER : 0);
-                    } else {
-                        if (M.info & B_PUP) cc2 = (cc2 + 1 == T.np) ? 0 : cc2 + 1; else cc2 = (cc2 == 0) ? T.np - 1 : cc2 - 1;
-                        int up2;
-                        M.tp = phi_next(X, T.np, cc2, M.t, Kc, up2);
-                    }
-                    M.cell12 = (cc1 << 10) | (cc2 << 20);
-                    M.kb = M.kext + T.nr * (cc1 + T.nt * cc2);
-                    M.load_kap();
-                }
+                double acc_w = 0.0;
+                const int out = march_inline(X, A, px, py, pz, G.d0, G.d1, G.d2, cell, sp, 50.0, acc_w, n_step);
                 C.n_cf += n_step;
                 if (out == O_ERR) { err_count(A, 31); err_count(A, 43); ++C.n_err; }
-                if (out == O_EXIT && M.acc < 50.0) {        // reached the detector: e^-tau, deposit :4955-4972
-                    const double w = fm_exp_neg(M.acc);
+                if (out == O_EXIT && acc_w < 50.0) {        // reached the detector: e^-tau, deposit :4955-4972
+                    const double w = fm_exp_neg(acc_w);
                     const double v0 = w * W[0], v1 = -(w * W[1]), v2 = w * W[2], v3 = w * W[3];
                     if (X.sdet) {
                         double* d = X.sdet + pix;
