@@ -1627,8 +1627,29 @@ __device__ __forceinline__ void ev_fan(const Sh& X, const KernelArgs& A, int n, 
     }
 }
 
+#ifndef E2_HEAD_STEPS
+#define E2_HEAD_STEPS 0    // > 0: the event that sets up a transport ray also marches its first E2_HEAD_STEPS crossings; a ray that ends
+#endif                     //      within them goes straight to its event list, without the trip through the ready list and a marcher
+
+// the first crossings of the transport ray an event has just set up; returns the list the slot goes on (L_RDY: the ray goes on)
 template <class Sh>
-__device__ __forceinline__ bool run_event(const Sh& X, const KernelArgs& A, int l, bool valid, int s, Cnt& C) {
+__device__ __forceinline__ int head_march(const Sh& X, const KernelArgs& A, int s, Cnt& C) {
+    Marcher Mw;
+    Mw.init(A.T); Mw.bind(X);
+    Mw.load(X, A, s);
+    unsigned n_step = 0;
+    int out = O_NONE;
+#pragma unroll 1
+    for (int k = 0; k < E2_HEAD_STEPS && out == O_NONE; ++k) out = Mw.step(X, A, n_step);
+    C.n_cf += n_step;
+    if (out != O_NONE) return Mw.finish(X, A, C, out);
+    Mw.release(X);
+    return L_RDY;
+}
+
+// the event of list l; returns the list the lane's slot goes on next (-1: none)
+template <class Sh>
+__device__ __forceinline__ int run_event(const Sh& X, const KernelArgs& A, int l, bool valid, int s, Cnt& C) {
     RaySpec rs;
     rs.make = false;
     bool push;
@@ -1639,7 +1660,8 @@ __device__ __forceinline__ bool run_event(const Sh& X, const KernelArgs& A, int 
     else if (Sh::GEN && l == L_SURF) push = ev_surface(X, A, valid, s, C, rs);
     else push = ev_emit(X, A, valid, s, C, rs);
     if (rs.make) ray_setup(X, A.T, s, rs.x, rs.y, rs.z, rs.n0, rs.n1, rs.n2, rs.c0, rs.c1, rs.c2, rs.sface, rs.kind, rs.lim, rs.acc0, rs.pk);
-    return push;
+    if (E2_HEAD_STEPS > 0 && rs.make && rs.kind == K_WALK) return head_march(X, A, s, C);
+    return push ? L_RDY : -1;
 }
 
 // multi-detector walks: the event of list l for a batch of n slots; returns the list the lane's slot goes on next (-1: none)
@@ -1770,7 +1792,7 @@ __global__ void __launch_bounds__(NT, MINB) transport2_kernel(const __grid_const
                 const bool valid = idx < m[k];
                 const int l = order[k];
                 const int s = valid ? (int)X.Q(l, hd[k] + idx) : 0;
-                const bool push = run_event(X, A, l, valid, s, C);
+                const bool push = run_event(X, A, l, valid, s, C) >= 0;
                 const unsigned pm = __ballot_sync(FULL, push);
                 if (pm) {
                     const int leader = __ffs(pm) - 1;
@@ -2016,15 +2038,27 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
                         if (tgt >= 0) ring_put(&X.Q(tgt, pb + __popc(g & lt)), s, A.O.err + ERR_WATCHDOG);
                     }
                 } else {
-                    const bool push = run_event(X, A, l, valid, s, C);
+                    const int tgt = run_event(X, A, l, valid, s, C);
                     __threadfence_block();
-                    const unsigned pm = __ballot_sync(FULL, push);
-                    if (pm) {
-                        const int leader = __ffs(pm) - 1;
-                        int pb = 0;
-                        if (lane == leader) pb = atomicAdd(X.tail + L_RDY, __popc(pm));
-                        pb = __shfl_sync(FULL, pb, leader);
-                        if (push) ring_put(&X.Q(L_RDY, pb + __popc(pm & lt)), s, A.O.err + ERR_WATCHDOG);
+                    if (E2_HEAD_STEPS > 0) {       // a head-marched ray may have ended: any list
+                        if (__any_sync(FULL, tgt >= 0)) {
+                            const unsigned g = __match_any_sync(FULL, tgt);
+                            const int leader = __ffs(g) - 1;
+                            int pb = 0;
+                            if (lane == leader && tgt >= 0) pb = atomicAdd(X.tail + tgt, __popc(g));
+                            pb = __shfl_sync(FULL, pb, leader);
+                            if (tgt >= 0) ring_put(&X.Q(tgt, pb + __popc(g & lt)), s, A.O.err + ERR_WATCHDOG);
+                        }
+                    } else {
+                        const bool push = tgt >= 0;
+                        const unsigned pm = __ballot_sync(FULL, push);
+                        if (pm) {
+                            const int leader = __ffs(pm) - 1;
+                            int pb = 0;
+                            if (lane == leader) pb = atomicAdd(X.tail + L_RDY, __popc(pm));
+                            pb = __shfl_sync(FULL, pb, leader);
+                            if (push) ring_put(&X.Q(L_RDY, pb + __popc(pm & lt)), s, A.O.err + ERR_WATCHDOG);
+                        }
                     }
                 }
             }
