@@ -47,6 +47,7 @@ cudaError_t launch_transport2_trace(const KernelArgs& a, int sm_count, cudaStrea
 cudaError_t fma_peak(double* fp64_tflops, double* fp32_tflops, int sm_count, cudaStream_t stream);
 cudaError_t ingest_cell_tables(const double* k_sca, const double* k_abs, const int* c2u, size_t n, double* kext, double* albedo,
                                double* cellrec, cudaStream_t stream);
+void ingest_set_chunk_override(int planes);
 cudaError_t ingest_dedup_device(const double* src, size_t cells, size_t plane_stride, cudaStream_t stream,
                                 std::vector<double>& uniq, std::vector<int32_t>& c2u, int* exact, double* copy_ms, double* kernel_ms);
 }  // namespace artes
@@ -1002,6 +1003,8 @@ int artes_gpu_cell_face(artes_gpu_ctx* ctx, int mode, uint64_t n, const double* 
 }
 
 int artes_gpu_last_engine(const artes_gpu_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
+
+int artes_gpu_test_ingest_chunk(int planes) { ingest_set_chunk_override(planes); return 0; }
 
 int artes_gpu_fma_peak(artes_gpu_ctx* ctx, double* fp64_tflops, double* fp32_tflops) {
     if (!ctx) return fail(nullptr, -1, "null context");

@@ -84,6 +84,10 @@ cudaError_t ingest_cell_tables(const double* k_sca, const double* k_abs, const i
     return cudaGetLastError();
 }
 
+// test hook: > 0 forces the chunked two-pass path with that many planes per chunk (the resident path needs no more than HBM offers)
+static int g_chunk_override = 0;
+void ingest_set_chunk_override(int planes) { g_chunk_override = planes; }
+
 // src: plane (e, a) of the wavelength = `cells` contiguous doubles at src + plane_stride * (e + 16 a).
 // Returns the blocks in order of first appearance (cell index), like the host path.  *exact = 0 if a hash group failed the
 // element-wise check (the caller then de-duplicates on the host).
@@ -98,6 +102,7 @@ cudaError_t ingest_dedup_device(const double* src, size_t cells, size_t plane_st
     const size_t plane_bytes = cells * sizeof(double);
     size_t budget = free_b / 2;
     int chunk = (int)std::min<size_t>(NPL, budget / (plane_bytes ? plane_bytes : 1));
+    if (g_chunk_override > 0) chunk = std::min(chunk, g_chunk_override);
     if (chunk < 1) return cudaErrorMemoryAllocation;
     const bool resident = chunk == NPL;
     double* buf = nullptr;

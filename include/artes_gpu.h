@@ -232,6 +232,11 @@ int  artes_gpu_device_info(const artes_gpu_ctx* ctx, int* sm_count, int* cc_majo
  * engine (tuning builds only).  Lets tests assert that the production path is the one that ran. */
 int  artes_gpu_last_engine(const artes_gpu_ctx* ctx);
 
+/* Test hook for the dense-matrix ingest: planes > 0 makes artes_gpu_set_wavelength_dense[_wl] stream the 2880 (element, angle)
+ * planes in chunks of that many (two passes: hash, verify), the path taken when a wavelength's planes do not fit into free HBM;
+ * 0 restores the automatic choice (resident planes whenever they fit). */
+int  artes_gpu_test_ingest_chunk(int planes);
+
 /* FP64 / FP32 FMA peak microbenchmark (roofline denominator): returns TFLOP/s. */
 int  artes_gpu_fma_peak(artes_gpu_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
 

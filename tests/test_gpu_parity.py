@@ -322,7 +322,10 @@ def test_dense_whole_array_entry_picks_the_wavelength_and_dedups_on_the_device(a
         for g in (ga, gb):
             g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
         ga.set_wavelength(atm.k_sca[l], atm.k_abs[l], atm.uniq[l], atm.cell_to_uniq[l], depth)
+        # wavelength 0 through the resident path, wavelength 2 through the chunked two-pass path (planes that do not fit into HBM)
+        gb.lib.artes_gpu_test_ingest_chunk(0 if l == 0 else 97)
         gb.set_wavelength_dense_wl(atm.k_sca, atm.k_abs, dense_all, l, depth)
+        gb.lib.artes_gpu_test_ingest_chunk(0)
         L = make_launch(mode=abi.MODE_FAST, n_photons=30000, x_max=xm, y_max=xm, seed=4, nx=16, ny=16, det_phi=math.radians(50.0))
         a, b = ga.run(L), gb.run(L)
         np.testing.assert_array_equal(a["det"][2], b["det"][2])

@@ -2,7 +2,7 @@
 # round 2, call f2 (8 GPUs, final build): multi-GPU equality tests, C5 scale run, C4 weak / strong scaling at 8
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-( time timeout 600 python -m pytest tests/test_multirank_gpu.py tests/test_gpu_parity.py -m gpu -q -k "two_device or torchrun" ) > gpurun_out/r02_f2_pytest.log 2>&1
+( time timeout 600 python -m pytest tests/test_multirank_gpu.py tests/test_gpu_parity.py -m gpu -q -k "two_device or torchrun or dense" ) > gpurun_out/r02_f2_pytest.log 2>&1
 tail -3 gpurun_out/r02_f2_pytest.log
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r02_f2_c4_n1.json 2> gpurun_out/r02_f2_c4_n1.err
 timeout 600 $TR --nproc-per-node 8 --master-port 29711 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r02_f2_c4_weak_n8.json 2> gpurun_out/r02_f2_c4_weak_n8.err
