@@ -62,6 +62,9 @@ namespace e2 {
 #ifndef E2_OPT_R2S
 #define E2_OPT_R2S 1       // squared radii through ld.shared with a 32-bit address
 #endif
+#ifndef E2_EARLY_ROOT
+#define E2_EARLY_ROOT 0    // the radial root of the NEXT cell is computed at the top of a step, next to the min / optical-depth chain it does
+#endif                     // not depend on (two independent dependency chains per step instead of one long one); same operations, same results
 #ifndef E2_RELEASE
 #define E2_RELEASE 0       // 1: a warp keeps no ray across passes -- unfinished rays go back to the ready list, and a pass starts only
 #endif                     //    with at least E2_MARCH_MIN ready rays (or when there is no full event batch to run instead)
@@ -1220,6 +1223,21 @@ struct Marcher {
     // One step: advance to the next crossing.  Returns the outcome (O_NONE: the ray goes on).
     template <class Sh>
     __device__ __forceinline__ int step(const Sh& X, const KernelArgs& A, unsigned& n_cf) {
+        // (E2_EARLY_ROOT) the crossing after this one, should this one be radial: cell cn = c0 + dr, inner sphere while the ray still
+        // reaches it (inward), else the outer one.  Nothing here depends on which face is crossed now, so the square root's chain
+        // (MUFU seed + Newton step + residual, ~10 dependent FP64 operations) runs beside the min / accumulate / compare chain below
+        // instead of after it.  A step that ends on a polar / azimuthal face or on the optical-depth limit discards it.
+        double trn = 0.0;
+        bool inner = false;
+        if (E2_EARLY_ROOT) {
+            const int cn = min(max(c0 + dr, 0), nr - 1);
+            const double da = fma(r2_at(cn), iq, D0), db = fma(r2_at(cn + 1), iq, D0);
+            inner = (dr < 0) && !(da < 0.0);
+            const double disc = inner ? da : db;
+            trn = fma(inner ? -1.0 : 1.0, fsqrt(disc), hbn);
+            if (disc < 0.0) trn = RAY_NONE;
+            asm volatile("" : "+d"(trn));      // computed HERE, not sunk below the branches that follow
+        }
         double tn = tr;
         if (tt < tn) tn = tt;
         if (tp < tn) tn = tp;
@@ -1251,6 +1269,11 @@ struct Marcher {
         c0 += dr;
         if (E2_OPT_KAPN) kap = kapn;               // loaded one step ago (measured: reading four layers at once with one 256-bit load and selecting is slower)
         else kap = __ldg(kb + c0);
+        if (E2_EARLY_ROOT) {
+            if (dr < 0 && !inner) { dr = 1; ds = 1.0; }      // turning point passed: outward from here on
+            tr = trn;
+            return O_NONE;
+        }
         // inward: the inner sphere if the ray reaches it, else (turning point passed) the outer one
         double disc = fma(r2_at(c0 + up), iq, D0);
         if (disc < 0.0) {
@@ -1897,6 +1920,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     // to shrink the code each warp loops over: 5-10 % slower on every workload, the event warps idle too often.)
 #ifdef E2_STATS
     unsigned long long st_pass = 0, st_act0 = 0, st_rdy0 = 0, st_it = 0, st_lane = 0, st_ev = 0, st_rdy = 0, st_evb = 0, st_evl = 0;
+    unsigned long long st_av = 0, st_lb = 0, st_ll = 0;      // per lane = per list: backlog summed over the passes, batches run, lanes in them
     bool rdy_empty = false;
 #endif
     // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100)
@@ -1976,6 +2000,9 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         // ---- events: a full batch if there is one; a partial one if this warp has little else to do
         int av = 0;
         if (lane < N_EVENT_LISTS) av = vtail[lane] - vhead[lane];
+#ifdef E2_STATS
+        st_av += (lane < N_EVENT_LISTS) ? av : (lane == L_RDY ? max(vtail[L_RDY] - vhead[L_RDY], 0) : 0);
+#endif
         const unsigned fullm = __ballot_sync(FULL, av >= 32);
         const unsigned anym = __ballot_sync(FULL, av > 0);
         const int nactive = __popc(__ballot_sync(FULL, M.slot >= 0));
@@ -2025,6 +2052,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
                 __threadfence_block();
 #ifdef E2_STATS
                 st_evb++; st_evl += n;
+                if (lane == l) { st_lb++; st_ll += n; }
 #endif
                 if (Sh::MULTI) {
                     const int tgt = run_event_md(X, A, l, n, valid, s, C);
@@ -2076,6 +2104,7 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
         atomicAdd(A.O.err + 53, st_it); atomicAdd(A.O.err + 54, st_lane); atomicAdd(A.O.err + 55, st_ev);
         atomicAdd(A.O.err + 56, st_rdy); atomicAdd(A.O.err + 57, st_evb); atomicAdd(A.O.err + 58, st_evl);
     }
+    if (lane < N_LISTS) { atomicAdd(A.O.err + 4 + lane, st_av); atomicAdd(A.O.err + 13 + lane, st_lb); atomicAdd(A.O.err + 22 + lane, st_ll); }
 #endif
     flush_counters(A, C);
 }

@@ -22,4 +22,7 @@ for m in modes:
         e = [int(x) for x in r["err"][50:59]]
         print(f"  passes {e[0]:.3e} lanes@start {e[1]/max(e[0],1):.1f} rdy_empty {e[2]/max(e[0],1):.2f} step-iters/pass {e[3]/max(e[0],1):.1f} lanes/step {e[4]/max(e[3],1):.1f} "
               f"evlist(H+DEP+RES)/block {e[5]/max(e[0],1):.0f} rdy/block {e[6]/max(e[0],1):.0f} event batches {e[7]:.3e} lanes/batch {e[8]/max(e[7],1):.1f}")
+        names = ["EMIT", "PRE", "H", "DEP", "RES", "SURF", "FAN", "SC", "RDY"]
+        e = [int(x) for x in r["err"]]
+        print("  " + "  ".join(f"{nm}: backlog {e[4+i]/max(e[50],1):.1f} batches {e[13+i]:.2e} lanes {e[22+i]/max(e[13+i],1):.1f}" for i, nm in enumerate(names) if e[4+i] or e[13+i]))
     t.close()
