@@ -428,6 +428,21 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
                 cdfP[((size_t)u * 181 + a + 1) * 4 + k] = cdfP[((size_t)u * 181 + a) * 4 + k] + m * ctx->sinbeta[a] * PI / 180.0;
             }
     }
+    // Block-diagonal scattering matrices (F13 = F14 = F23 = F24 = F31 = F32 = F41 = F42 = 0 exactly, in every block and at every angle) get a
+    // second, half-size copy with the eight elements that can be non-zero: the interaction event then reads 2 x 64 bytes per angle
+    // instead of 2 x 128, and products with exact zeros add nothing, so the Stokes vectors are the same.
+    std::vector<double> mc;
+    {
+        static const int zero_at[8] = {2, 3, 6, 7, 8, 9, 12, 13}, keep[8] = {0, 1, 4, 5, 10, 11, 14, 15};
+        bool compact = std::getenv("ARTES_GPU_FULL_MATRIX") == nullptr;       // (test hook: forces the 16-element path)
+        for (size_t r = 0; compact && r < (size_t)n_uniq * 180; ++r)
+            for (int k = 0; k < 8; ++k) if (uniq_matrix[r * 16 + zero_at[k]] != 0.0) { compact = false; break; }
+        if (compact) {
+            mc.resize((size_t)n_uniq * 180 * 8);
+            for (size_t r = 0; r < (size_t)n_uniq * 180; ++r)
+                for (int k = 0; k < 8; ++k) mc[r * 8 + k] = uniq_matrix[r * 16 + keep[k]];
+        }
+    }
     std::vector<double> cdf_lin;
     ctx->thermal = (cell_weight && emis_cdf);
     if (ctx->thermal) {  // reorder emissivity_cumulative into its (i,j,k) construction order (:2425-2427); wavelength l at l * cells
@@ -467,6 +482,8 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
         rc |= upload_wl(ctx, d, mrow.data(), mrow.size(), &T.Mrow);
         rc |= upload_wl(ctx, d, p1k.data(), p1k.size(), &T.p1k);
         rc |= upload_wl(ctx, d, cdfP.data(), cdfP.size(), &T.cdfP);
+        rc |= upload_wl(ctx, d, mc.data(), mc.size(), &T.Mc);      // (always takes its pool slot, so that the slots of the tables after it do not move)
+        if (mc.empty()) T.Mc = nullptr;
         T.cell_weight = nullptr; T.emis_cdf = nullptr;
         if (ctx->thermal) {
             rc |= upload_wl(ctx, d, cell_weight, (size_t)n, &T.cell_weight);

@@ -95,7 +95,7 @@ enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16, PK_SHIFT = 5 };   // bits 5
 // lets a block hold several times more photons than lanes.
 enum : int { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_S0, F_S1, F_S2, F_S3, F_TAU, F_W0, F_W1, F_W2, F_W3, NF_COLD,
              F_T = NF_COLD, F_ACC, F_TR, F_TT, F_TP, F_HBN, F_D0, F_IQ, F_LIM, NF_D };
-enum : int { I_CELL = 0, I_INFO, NI_HOT, I_HCELL = NI_HOT, I_PIX, I_ND, I_IDLO, I_IDHI,
+enum : int { I_CELL = 0, I_INFO, I_ND, I_IDLO, I_IDHI, NI_HOT, I_HCELL = NI_HOT, I_PIX,
              I_TLEN, I_TNSC, I_THLO, I_THHI, I_FLAG, NF_I,
              I_BATCH = I_TLEN };   // launch index of the photon in a batched launch (the walk recorder never runs batched)     // I_T*: walk recorder of the trace hook; I_FLAG bit 0: injected stream used up
 constexpr int NF_HOT = NF_D - NF_COLD;
@@ -112,6 +112,9 @@ __host__ __device__ constexpr int fixed_doubles(int NP) {
 }
 constexpr int GEO = 12;     // doubles per launch in the launch table: det(3), sin_dt, cos_dt, sin_dp, cos_dp, limb_emission, det_sph_theta, det_sph_phi,
                             // cell_depth and wavelength index of the launch (batches over wavelengths: LaunchArgs::wl_batch)
+#ifndef E2_COMPACT_M
+#define E2_COMPACT_M 1     // block-diagonal scattering matrices are read from the eight-element copy (DevTables::Mc)
+#endif
 struct Lay {
     int o_r, o_r2, o_tf, o_tt, o_ps, o_pc, o_pf, o_tp, o_ca, o_geo, o_det, n_end;   // offsets in doubles
     size_t bytes;
@@ -387,18 +390,38 @@ __device__ __forceinline__ int polrot_deg_f(const DevTables& T, int u, double de
     const double fl = floor(deg);
     if (deg - fl > 0.5) { up = (int)fl + 2; lo = (int)fl + 1; }
     else { up = (int)fl + 1; lo = (int)fl; }
-    const double* base = T.M + (size_t)u * (180 * 16);
     const bool edge = (up <= 1 || lo >= 180);
-    const double* m0 = base + (edge ? (up <= 1 ? 0 : 179) : (lo - 1)) * 16;
-    const double* m1 = edge ? m0 : base + (up - 1) * 16;
+    const int row0 = edge ? (up <= 1 ? 0 : 179) : (lo - 1), row1 = edge ? row0 : (up - 1);
     const double w = edge ? 0.0 : deg - ((double)lo - 0.5);
     double s[4];
+    if (E2_COMPACT_M && T.Mc) {
+        // block-diagonal matrices (DevTables::Mc): rows 0, 1 act on (r0, r1), rows 2, 3 on (r2, r3); the terms left out are products
+        // with exact zeros.  Half the table bytes and half the 32-byte reads (one L1 wavefront per lane and read) of the general path.
+        const double* base = T.Mc + (size_t)u * (180 * 8);
+        const double* m0 = base + row0 * 8;
+        const double* m1 = base + row1 * 8;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        double a0, a1, a2, a3, b0, b1, b2, b3;
-        ldg256_nc(m0 + 4 * r, a0, a1, a2, a3);
-        ldg256_nc(m1 + 4 * r, b0, b1, b2, b3);
-        s[r] = ((b0 - a0) * w + a0) * r0 + ((b1 - a1) * w + a1) * r1 + ((b2 - a2) * w + a2) * r2 + ((b3 - a3) * w + a3) * r3;
+        for (int h = 0; h < 2; ++h) {
+            double a0, a1, a2, a3, b0, b1, b2, b3;
+            ldg256_nc(m0 + 4 * h, a0, a1, a2, a3);
+            ldg256_nc(m1 + 4 * h, b0, b1, b2, b3);
+            const double x = h ? r2 : r0, y = h ? r3 : r1;
+            // the operation order of the general path's contracted sum: fma(F_r3, r3, fma(F_r2, r2, fma(F_r0, r0, F_r1 * r1)))
+            const double f0 = (b0 - a0) * w + a0, f1 = (b1 - a1) * w + a1, f2 = (b2 - a2) * w + a2, f3 = (b3 - a3) * w + a3;
+            s[2 * h] = h ? fma(f1, y, f0 * x) : fma(f0, x, f1 * y);
+            s[2 * h + 1] = h ? fma(f3, y, f2 * x) : fma(f2, x, f3 * y);
+        }
+    } else {
+        const double* base = T.M + (size_t)u * (180 * 16);
+        const double* m0 = base + row0 * 16;
+        const double* m1 = base + row1 * 16;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double a0, a1, a2, a3, b0, b1, b2, b3;
+            ldg256_nc(m0 + 4 * r, a0, a1, a2, a3);
+            ldg256_nc(m1 + 4 * r, b0, b1, b2, b3);
+            s[r] = ((b0 - a0) * w + a0) * r0 + ((b1 - a1) * w + a1) * r1 + ((b2 - a2) * w + a2) * r2 + ((b3 - a3) * w + a3) * r3;
+        }
     }
     if (!peeling) {
         if (s[0] > 0.0) { const double nrm = fdiv(r0, s[0]); s[0] = r0; s[1] *= nrm; s[2] *= nrm; s[3] *= nrm; }
@@ -418,15 +441,36 @@ __device__ __forceinline__ int polrot_deg_f(const DevTables& T, int u, double de
 // table values.  Three 6-ary rounds (steps 30, 5, 1; independent probes each) instead of eight dependent
 // binary-search steps: the same number of table reads, a third of the load round trips.  The last round reads
 // the six entries lo .. lo+5, so the bracketing pair comes out of registers instead of a fourth round trip.
+#ifndef E2_BSEARCH
+#define E2_BSEARCH 3       // bit 0: polar CDF, bit 1: azimuth CDF inverted by binary search (8 dependent probes instead of 16 in three rounds)
+#endif
+// The same bin by bisection: 8 probes instead of 16.  y180 = cum(180) (the caller has it), cum(0) = 0 (prefix tables).
 template <class F>
-__device__ __forceinline__ int search6(F cum, double samp, double& ylo, double& yhi) {
+__device__ __forceinline__ int search2(F cum, double samp, double y180, double& ylo, double& yhi) {
+    int lo = 0, hi = 180;          // cum(lo) < samp (or lo = 0), cum(hi) >= samp (or hi = 180)
+    ylo = 0.0; yhi = y180;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int mid = (lo + hi) >> 1;
+        const double v = cum(mid);
+        const bool below = (v < samp) && (hi - lo > 1);
+        const bool above = !(v < samp) && (hi - lo > 1);
+        if (below) { lo = mid; ylo = v; }
+        if (above) { hi = mid; yhi = v; }
+    }
+    return lo;
+}
+
+// cum30(k) = cum(30 k) for k = 1..5: the first round's probes, which may come from a copy that is cheaper to read
+template <class F, class F30>
+__device__ __forceinline__ int search6(F cum, F30 cum30, double samp, double& ylo, double& yhi) {
     int lo = 0;
 #pragma unroll
     for (int round = 0; round < 2; ++round) {
         const int step = (round == 0) ? 30 : 5;
         double y[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) y[k] = cum(lo + (k + 1) * step);
+        for (int k = 0; k < 5; ++k) y[k] = (round == 0) ? cum30(k + 1) : cum(lo + (k + 1) * step);
         int c = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) c += (y[k] < samp) ? 1 : 0;
@@ -454,9 +498,11 @@ __device__ __forceinline__ int sample_angles_f(const Sh& X, const KernelArgs& A,
     ldg256_nc(T.p1k + 4 * u, p11, p12, p13, p14);
     const double Ac = p11 * S[0] + p14 * S[3], Bc = p12 * S[1] + p13 * S[2], Cc = p12 * S[2] - p13 * S[1];
     auto cumA = [&](int i) { const double2 q = X.cdfa[i]; return Ac * (double)i + Bc * q.x + Cc * q.y; };
-    double samp = xi1 * cumA(180);
+    const double a180 = cumA(180);
+    double samp = xi1 * a180;
     double ylo, yhi;
-    int lo = search6(cumA, samp, ylo, yhi);   // bin lo: cum(lo) < samp <= cum(lo + 1)
+    int lo = (E2_BSEARCH & 2) ? search2(cumA, samp, a180, ylo, yhi)
+                              : search6(cumA, [&](int k) { return cumA(30 * k); }, samp, ylo, yhi);   // bin lo: cum(lo) < samp <= cum(lo + 1)
     double fr = fdiv(samp - ylo, yhi - ylo);
     if (!(fr == fr)) return 6;
     fr = fmin(fmax(fr, 0.0), 1.0);
@@ -472,8 +518,10 @@ __device__ __forceinline__ int sample_angles_f(const Sh& X, const KernelArgs& A,
         ldg256_nc(tab + 4 * i, q0, q1, q2, q3);
         return w1 * q0 + w2 * q1 + w3 * q2 + w4 * q3;
     };
-    samp = xi3 * cumP(180);
-    lo = search6(cumP, samp, ylo, yhi);
+    // cumP(180) without reading the table: row 180 of cdfP is p1k, built by the same additions in the same order (artes_gpu.cu)
+    const double p180 = w1 * p11 + w2 * p12 + w3 * p13 + w4 * p14;
+    samp = xi3 * p180;
+    lo = (E2_BSEARCH & 1) ? search2(cumP, samp, p180, ylo, yhi) : search6(cumP, [&](int k) { return cumP(30 * k); }, samp, ylo, yhi);
     fr = fdiv(samp - ylo, yhi - ylo);
     if (!(fr == fr)) return 7;
     fr = fmin(fmax(fr, 0.0), 1.0);
@@ -767,6 +815,12 @@ __device__ __forceinline__ int march_inline(const Sh& X, const KernelArgs& A, do
                                             int cell, int slot, double lim, double& acc_out, unsigned& n_step);
 __device__ __forceinline__ void deposit_scatter_warp(const KernelArgs& A, bool dep, int pix, const double v[8]);
 
+#ifndef E2_INLINE_PEEL
+#define E2_INLINE_PEEL 1   // 1: the peel-off walk of a scattering is marched inside the interaction event (no peel ray, no DEP event)
+#endif
+#ifndef E2_KEEP_W
+#define E2_KEEP_W 0
+#endif
 struct HOut { double px, py, pz, dx, dy, dz, tau, W[4]; int pix, cell, kb; };
 // returns 0: idle lane, 1: the photon died (survival test), 2: scattered -- `o` holds the peel-off weights and the new state
 template <class Sh>
@@ -777,17 +831,16 @@ __device__ __forceinline__ int interact_core(const Sh& X, const KernelArgs& A, b
     const int cell = X.I(I_CELL, s);
     const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     const int ci = c0 + T.nr * (c1 + T.nt * c2);
-    // the cold record in 32-byte pieces: [px py pz dx] [dy dz S0 S1] [S2 S3 tau W0] [W1 W2 W3 hcell|pix] [nd|idlo idhi|tlen ...]
+    // the cold record in 32-byte pieces: [px py pz dx] [dy dz S0 S1] [S2 S3 tau W0] [W1 W2 W3 hcell|pix] [tlen|tnsc ...]; photon id and draw counter are hot ints
     double* rec = X.cold + (size_t)s * REC;
-    double hx, hy, hz, dx, dy, dz, S[4], tau0, w0_, i0_, i1_, i2_, i3_;
+    double hx, hy, hz, dx, dy, dz, S[4], tau0, w0_;
     ldg256(rec, hx, hy, hz, dx);
     ldg256(rec + 4, dy, dz, S[0], S[1]);
     ldg256(rec + 8, S[2], S[3], tau0, w0_);
-    ldg256(rec + 16, i0_, i1_, i2_, i3_);
-    (void)w0_; (void)i2_; (void)i3_;
+    (void)w0_;
     // per-cell record {cell_opacity, cell_albedo, unique-matrix index}: one 256-bit read instead of three scattered ones
     double kap_c, alb_c, u_bits, pad_c;
-    const int kb = Sh::BATCH ? (int)((unsigned long long)__double_as_longlong(i1_) >> 32) : 0;      // I_BATCH shares the word of I_IDHI
+    const int kb = Sh::BATCH ? X.I(I_BATCH, s) : 0;
     ldg256_nc(T.cellrec + (size_t)4 * ((size_t)ci + (size_t)wl_of(X, A, kb) * T.cells), kap_c, alb_c, u_bits, pad_c);
     (void)pad_c;
     const int u = (int)__double_as_longlong(u_bits);
@@ -798,10 +851,9 @@ __device__ __forceinline__ int interact_core(const Sh& X, const KernelArgs& A, b
     double mu = dx * G.d0 + dy * G.d1 + dz * G.d2;
     if (mu >= 1.0) mu = 1.0 - 1.e-10; else if (mu <= -1.0) mu = -1.0 + 1.e-10;
     const double peel_deg = fm_acos(mu) * (180.0 / PI);
-    // ints of the record: piece 4 = [nd | idlo] [idhi | tlen] ...
-    const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
-    const unsigned long long id = (w16 >> 32) | ((w17 & 0xffffffffull) << 32);
-    unsigned nd = (unsigned)w16;
+    // photon id and position in its random stream: hot fields (shared memory)
+    const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+    unsigned nd = (unsigned)X.I(I_ND, s);
     bool alive = L.photon_scattering != 0;
     if (Sh::TRACE && (X.I(I_FLAG, s) & 1)) alive = false;       // injected stream used up (test hook only)
     double xr[5];
@@ -894,7 +946,8 @@ __device__ __forceinline__ int interact_core(const Sh& X, const KernelArgs& A, b
     stg256(rec, px, py, pz, dx);
     stg256(rec + 4, dy, dz, S[0], S[1]);
     stg256(rec + 8, S[2], S[3], tau, W[0]);
-    stg256(rec + 12, W[1], W[2], W[3], __longlong_as_double((long long)((unsigned long long)(unsigned)cell | ((unsigned long long)(unsigned)pix << 32))));
+    // (the peel-off weights and the pixel are for a DEP event: with the walk inside this event nobody reads them)
+    if (!E2_INLINE_PEEL || E2_KEEP_W) stg256(rec + 12, W[1], W[2], W[3], __longlong_as_double((long long)((unsigned long long)(unsigned)cell | ((unsigned long long)(unsigned)pix << 32))));
 #ifdef E2_DEBUG
     if (!(W[0] < 1.e10) || !(S[0] < 1.e10)) printf("E2 interact: slot %d cell %d %d %d W %g %g %g %g S %g tpos %g tau %g acc %g t %g\n", s, c0, c1, c2, W[0], W[1], W[2], W[3], S[0], tpos, tau0, X.D(F_ACC, s), X.D(F_T, s));
 #endif
@@ -904,9 +957,6 @@ __device__ __forceinline__ int interact_core(const Sh& X, const KernelArgs& A, b
     return 2;
 }
 
-#ifndef E2_INLINE_PEEL
-#define E2_INLINE_PEEL 1   // 1: the peel-off walk of a scattering is marched inside the interaction event (no peel ray, no DEP event)
-#endif
 template <class Sh>
 __device__ __forceinline__ bool ev_interact(const Sh& X, const KernelArgs& A, bool valid, int s, Cnt& C, RaySpec& rs) {
     HOut o;
@@ -1456,20 +1506,18 @@ __device__ __forceinline__ int ev_survive(const Sh& X, const KernelArgs& A, bool
     const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     const int ci = c0 + T.nr * (c1 + T.nt * c2);
     double* rec = X.cold + (size_t)s * REC;
-    double hx, hy, hz, dx, dy, dz, S[4], tau0, w0_, i0_, i1_, i2_, i3_;
+    double hx, hy, hz, dx, dy, dz, S[4], tau0, w0_;
     ldg256(rec, hx, hy, hz, dx);
     ldg256(rec + 4, dy, dz, S[0], S[1]);
     ldg256(rec + 8, S[2], S[3], tau0, w0_);
-    ldg256(rec + 16, i0_, i1_, i2_, i3_);
-    (void)w0_; (void)i2_; (void)i3_;
+    (void)w0_;
     double kap_c, alb_c, u_bits, pad_c;
     ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
     (void)pad_c; (void)u_bits;
     const double tpos = X.D(F_T, s) - fdiv(X.D(F_ACC, s) - tau0, kap_c);      // step back by the overshoot (:705-720)
     const double px = hx + tpos * dx, py = hy + tpos * dy, pz = hz + tpos * dz;
-    const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
-    const unsigned long long id = (w16 >> 32) | ((w17 & 0xffffffffull) << 32);
-    unsigned nd = (unsigned)w16;
+    const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+    unsigned nd = (unsigned)X.I(I_ND, s);
     bool alive = L.photon_scattering != 0;
     if (alive) { double xi; draws(X, A, s, id, nd, 1, &xi); ++nd; if (xi < L.fstop) alive = false; }
     if (alive) {
@@ -1491,12 +1539,11 @@ __device__ __forceinline__ int ev_scatter_md(const Sh& X, const KernelArgs& A, b
     if (!valid) return -1;
     const DevTables& T = A.T;
     double* rec = X.cold + (size_t)s * REC;
-    double px, py, pz, dx, dy, dz, S[4], t0_, t1_, i0_, i1_, i2_, i3_;
+    double px, py, pz, dx, dy, dz, S[4], t0_, t1_;
     ldg256(rec, px, py, pz, dx);
     ldg256(rec + 4, dy, dz, S[0], S[1]);
     ldg256(rec + 8, S[2], S[3], t0_, t1_);
-    ldg256(rec + 16, i0_, i1_, i2_, i3_);
-    (void)t0_; (void)t1_; (void)i2_; (void)i3_;
+    (void)t0_; (void)t1_;
     const int cell = X.I(I_HCELL, s);
     const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = (cell >> 20) & 1023;
     const int ci = c0 + T.nr * (c1 + T.nt * c2);
@@ -1504,9 +1551,8 @@ __device__ __forceinline__ int ev_scatter_md(const Sh& X, const KernelArgs& A, b
     ldg256_nc(T.cellrec + (size_t)4 * ci, kap_c, alb_c, u_bits, pad_c);
     (void)kap_c; (void)alb_c; (void)pad_c;
     const int u = (int)__double_as_longlong(u_bits);
-    const unsigned long long w16 = (unsigned long long)__double_as_longlong(i0_), w17 = (unsigned long long)__double_as_longlong(i1_);
-    const unsigned long long id = (w16 >> 32) | ((w17 & 0xffffffffull) << 32);
-    unsigned nd = (unsigned)w16;
+    const unsigned long long id = (unsigned long long)(unsigned)X.I(I_IDLO, s) | ((unsigned long long)(unsigned)X.I(I_IDHI, s) << 32);
+    unsigned nd = (unsigned)X.I(I_ND, s);
     double xr[5];
     draws(X, A, s, id, nd, 4, xr);
     ++C.n_sc;

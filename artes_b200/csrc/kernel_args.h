@@ -24,6 +24,8 @@ struct DevTables {
     const int*    c2u;               // [cells] cell -> unique matrix block
     const double* M;                 // [n_uniq][180][16] cell_scatter_matrix, de-duplicated (:69)
     const double* Mrow;              // [n_uniq][180][4]  first matrix row, compact (polar CDF loop)
+    const double* Mc;                // [n_uniq][180][8]  {F11 F12 F21 F22 F33 F34 F43 F44} when EVERY block has exact zeros in the two off-diagonal
+                                     // 2x2 quarters (spheres, Rayleigh, Henyey-Greenstein: all the reference's opacity tools), else null
     const double* p1k;               // [n_uniq][4] cell_p11..p14_int (:72-75)
     const double* cdfA;              // fast mode: prefix sums of cos2beta | sin2beta, [2][181]
     const double* cdfA2;             // the same, interleaved [181][2] (staged in shared memory by the ray/event engine)
