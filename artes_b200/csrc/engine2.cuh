@@ -56,9 +56,6 @@ namespace e2 {
 #include "fastmath.cuh"
 
 // measurement switches (tools/build_variants.sh builds the library with single optimisations turned off)
-#ifndef E2_OPT_KAPN
-#define E2_OPT_KAPN 0      // opacity of the next radial layer loaded one step ahead (measured: 2-6 % SLOWER, profiles/r02_c_*; kept as a switch)
-#endif
 #ifndef E2_OPT_R2S
 #define E2_OPT_R2S 1       // squared radii through ld.shared with a 32-bit address
 #endif
@@ -1211,11 +1208,9 @@ __constant__ signed char c_list[4][8] = {
 struct Marcher {
     int slot, c0, dr, cell12, info;
     double t, acc, tr, tt, tp, hbn, D0, iq, lim, kap, ds;
-    double kapn;                 // opacity of the NEXT radial layer in the direction of motion, loaded one step ahead: the load's
-                                 // latency (an L2 round trip on the large grids) overlaps a whole step instead of ending it
-    const double* kb;            // kext + nr*(c1 + nt*c2): the opacity row of the ray's (theta, phi) column
+    const double* kb;            // kext + nr * col: the opacity row of the ray's (theta, phi) column
+    int col;                     // column index c1 + nt*c2 (+ nt*np * wavelength in a wavelength batch)
     int nr, nt, depth;           // launch invariants kept in registers (the kernel parameters live in constant memory)
-    const double* kext;
     const double* r2g;           // (the generic pointer: measurement variant without E2_OPT_R2S)
     unsigned r2s;                // shared-space byte address of the squared radii: ld.shared with a 32-bit address instead of a generic
                                  // pointer (the compiler rebuilt the generic shared base with S2R + LEA in every step)
@@ -1224,8 +1219,13 @@ struct Marcher {
 
     __device__ __forceinline__ void init(const DevTables& T) {
         slot = -1; c0 = cell12 = info = 0; dr = 1;
-        t = acc = tr = tt = tp = hbn = D0 = iq = lim = kap = kapn = 0.0; ds = 1.0;
-        nr = T.nr; nt = T.nt; depth = T.cell_depth; kext = T.kext; kb = T.kext; r2s = 0u;
+        t = acc = tr = tt = tp = hbn = D0 = iq = lim = kap = 0.0; ds = 1.0;
+        col = 0;
+        nr = T.nr; nt = T.nt; depth = T.cell_depth; kb = T.kext; r2s = 0u;
+    }
+    // the ray is in column `column` from now on
+    __device__ __forceinline__ void set_column(const DevTables& T, int column) {
+        col = column; kb = T.kext + (size_t)T.nr * (size_t)column;
     }
     template <class Sh>
     __device__ __forceinline__ void bind(const Sh& X) {
@@ -1234,11 +1234,9 @@ struct Marcher {
         asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(sh) : "l"((unsigned long long)X.r2));
         r2s = (unsigned)sh;
     }
-    // opacity of layer c0 and, ahead of time, of its neighbour in the direction of motion (index clamped to the column)
-    __device__ __forceinline__ void load_kap() {
-        kap = __ldg(kb + c0);
-        if (E2_OPT_KAPN) kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
-    }
+    // opacity of layer c0 (measured and dropped, twice: four layers per 256-bit load and a select -- the branch and the selects in
+    // the stepping loop cost 20-28 %, profiles/r02_ab_variants.txt; the next layer loaded one step ahead -- 2-6 %)
+    __device__ __forceinline__ void load_kap() { kap = __ldg(kb + c0); }
     __device__ __forceinline__ double r2_at(int i) const {
         if (!E2_OPT_R2S) return r2g[i];
         double v;
@@ -1256,12 +1254,13 @@ struct Marcher {
         info = X.I(I_INFO, s);
         c0 = cell & 1023; cell12 = cell & ~1023;
         dr = (info & B_INWARD) ? -1 : 1; ds = (info & B_INWARD) ? -1.0 : 1.0;
-        kb = kext + nr * (((cell >> 10) & 1023) + nt * ((cell >> 20) & 1023));
+        int column = ((cell >> 10) & 1023) + nt * ((cell >> 20) & 1023);
         if (Sh::BATCH && A.L.wl_batch) {       // wavelength batch: the opacity table and the surface layer of the photon's launch
             const int kbi = X.I(I_BATCH, s);
-            kb += (size_t)wl_of(X, A, kbi) * A.T.cells;
+            column += wl_of(X, A, kbi) * (A.T.nt * A.T.np);
             depth = depth_of(X, A, kbi);
         }
+        set_column(A.T, column);
         load_kap();
         if (Sh::TRACE) {
             tl = X.I(I_TLEN, s);
@@ -1311,14 +1310,13 @@ struct Marcher {
         const int up = (dr > 0) ? 1 : 0;
         const int f = c0 + up;
         if (Sh::GEN && A.L.flow_theta && (info & 3) == K_WALK)      // add_flow :5016-5047, radial crossings (:730-735)
-            atomicAdd(A.O.flow4 + (size_t)4 * ((kb - kext) + c0) + (up ? 0 : 1), s0w);
+            atomicAdd(A.O.flow4 + (size_t)4 * ((size_t)nr * col + c0) + (up ? 0 : 1), s0w);
         // outward the ray can only leave through the top face, inward only reach the surface face: one comparison.  The surface
         // face of a plain launch is read from the constant bank (as a register it was spilled and reloaded in every step).
         const int dep = (Sh::BATCH && A.L.wl_batch) ? depth : A.T.cell_depth;
         if (f == (up ? nr : dep)) return up ? O_EXIT : O_SURF;
         c0 += dr;
-        if (E2_OPT_KAPN) kap = kapn;               // loaded one step ago (measured: reading four layers at once with one 256-bit load and selecting is slower)
-        else kap = __ldg(kb + c0);
+        load_kap();
         if (E2_EARLY_ROOT) {
             if (dr < 0 && !inner) { dr = 1; ds = 1.0; }      // turning point passed: outward from here on
             tr = trn;
@@ -1328,9 +1326,8 @@ struct Marcher {
         double disc = fma(r2_at(c0 + up), iq, D0);
         if (disc < 0.0) {
             if (dr < 0) { dr = 1; ds = 1.0; disc = fma(r2_at(c0 + 1), iq, D0); }
-            if (disc < 0.0) { tr = RAY_NONE; kapn = kap; return O_NONE; }
+            if (disc < 0.0) { tr = RAY_NONE; return O_NONE; }
         }
-        if (E2_OPT_KAPN) kapn = __ldg(kb + min(max(c0 + dr, 0), nr - 1));
         tr = fma(ds, fsqrt(disc), hbn);
         return O_NONE;
     }
@@ -1400,12 +1397,13 @@ __device__ __forceinline__ int march_inline(const Sh& X, const KernelArgs& A, do
     M.c0 = c0; M.cell12 = cell & ~1023;
     M.info = K_PEEL | (inward ? B_INWARD : 0) | (upper ? B_TUPPER : 0) | (up ? B_PUP : 0);
     M.dr = inward ? -1 : 1; M.ds = inward ? -1.0 : 1.0;
-    M.kb = M.kext + T.nr * (c1 + T.nt * c2);
+    int wlcol = 0;                         // first column of the photon's wavelength (0 unless a wavelength batch)
     if (Sh::BATCH && A.L.wl_batch) {       // wavelength batch: the opacity table and the surface layer of the photon's launch
         const int kbi = X.I(I_BATCH, slot);
-        M.kb += (size_t)wl_of(X, A, kbi) * T.cells;
+        wlcol = wl_of(X, A, kbi) * (T.nt * T.np);
         M.depth = depth_of(X, A, kbi);
     }
+    M.set_column(T, wlcol + c1 + T.nt * c2);
     M.load_kap();
     M.slot = slot;
     if (Sh::TRACE) {
@@ -1435,8 +1433,7 @@ __device__ __forceinline__ int march_inline(const Sh& X, const KernelArgs& A, do
             M.tp = phi_next(X, T.np, cc2, M.t, Kc, up2);
         }
         M.cell12 = (cc1 << 10) | (cc2 << 20);
-        const size_t wl_off = (size_t)(M.kb - M.kext) / (size_t)T.cells * (size_t)T.cells;      // (0 unless a wavelength batch)
-        M.kb = M.kext + wl_off + T.nr * (cc1 + T.nt * cc2);
+        M.set_column(T, wlcol + cc1 + T.nt * cc2);
         M.load_kap();
     }
     if (Sh::TRACE) { X.I(I_TLEN, slot) = M.tl; X.I(I_THLO, slot) = (int)(unsigned)M.th; X.I(I_THHI, slot) = (int)(unsigned)(M.th >> 32); }
