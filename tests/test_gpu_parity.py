@@ -307,6 +307,38 @@ def test_dense_matrix_entry_equals_compact(atmospheres, gpu_factory):
     np.testing.assert_allclose(a["det"][0], b["det"][0], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("name,px", [("c1_template_rayleigh", 25), ("c4_mie_patches", 32)])
+def test_eight_element_matrix_table_equals_the_full_matrices(atmospheres, gpu_factory, name, px, monkeypatch):
+    """Block-diagonal scattering matrices (all the reference's opacity tools make them) are read from an eight-element copy
+    (DevTables::Mc, artes_gpu.cu); ARTES_GPU_FULL_MATRIX forces the 16-element path.  The terms the short path leaves out are
+    products with exact zeros: same photons, same pixels, sums equal up to the order of the detector's atomic additions.  A matrix
+    with one non-zero element outside the diagonal quarters must switch the short path off by itself."""
+    atm = atmospheres(name)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(mode=abi.MODE_FAST, n_photons=60000, x_max=xm, y_max=xm, nx=px, ny=px, seed=9)
+    g, depth = gpu_factory(atm)
+    a = g.run(L)
+    assert a["stats"]["n_scatter"] > 100000
+    monkeypatch.setenv("ARTES_GPU_FULL_MATRIX", "1")
+    g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth)
+    b = g.run(L)
+    monkeypatch.delenv("ARTES_GPU_FULL_MATRIX")
+    for k in ("n_emit", "n_cell_face", "n_scatter", "n_peel"):
+        assert a["stats"][k] == b["stats"][k]
+    np.testing.assert_array_equal(a["det"][2], b["det"][2])
+    np.testing.assert_allclose(a["det"][0], b["det"][0], rtol=1e-10, atol=1e-13 * np.abs(b["det"][0]).max())
+    # F13 != 0 somewhere: not block-diagonal any more -> the general path, and a different answer from the zero-F13 tables
+    uniq = np.array(atm.uniq[0], dtype=np.float64, copy=True).reshape(-1, 180, 16)
+    uniq[0, 40, 2] = 1e-3 * uniq[0, 40, 0]
+    g.set_wavelength(atm.k_sca[0], atm.k_abs[0], uniq.reshape(np.shape(atm.uniq[0])), atm.cell_to_uniq[0], depth)
+    c = g.run(L)
+    g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth)
+    d = g.run(L)
+    assert np.abs(c["det"][0] - b["det"][0]).max() > 0.0
+    np.testing.assert_array_equal(d["det"][2], a["det"][2])
+    np.testing.assert_allclose(d["det"][0], a["det"][0], rtol=1e-10, atol=1e-13 * np.abs(a["det"][0]).max())
+
+
 def test_dense_whole_array_entry_picks_the_wavelength_and_dedups_on_the_device(atmospheres):
     """artes_gpu_set_wavelength_dense_wl takes the reference's WHOLE arrays (cells, n_wl[, 16, 180]) as they sit in memory
     and picks one wavelength with strides (no Fortran slice copy); the (element, angle) planes are hashed and verified on
