@@ -92,9 +92,10 @@ enum : int { B_INWARD = 4, B_TUPPER = 8, B_PUP = 16, PK_SHIFT = 5 };   // bits 5
 // lets a block hold several times more photons than lanes.
 enum : int { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_S0, F_S1, F_S2, F_S3, F_TAU, F_W0, F_W1, F_W2, F_W3, NF_COLD,
              F_T = NF_COLD, F_ACC, F_TR, F_TT, F_TP, F_HBN, F_D0, F_IQ, F_LIM, NF_D };
-enum : int { I_CELL = 0, I_INFO, I_ND, I_IDLO, I_IDHI, NI_HOT, I_HCELL = NI_HOT, I_PIX,
-             I_TLEN, I_TNSC, I_THLO, I_THHI, I_FLAG, NF_I,
-             I_BATCH = I_TLEN };   // launch index of the photon in a batched launch (the walk recorder never runs batched)     // I_T*: walk recorder of the trace hook; I_FLAG bit 0: injected stream used up
+enum : int { I_CELL = 0, I_INFO, I_ND, I_IDLO, I_IDHI, I_BATCH, NI_HOT, I_HCELL = NI_HOT, I_PIX,
+             I_TLEN, I_TNSC, I_THLO, I_THHI, I_FLAG, NF_I };
+// I_ND draw counter, I_IDLO/HI photon id, I_BATCH launch index of the photon in a batched launch: hot (shared memory), every interaction
+// and every ray load of a wavelength batch reads them; I_T*: walk recorder of the trace hook; I_FLAG bit 0: injected stream used up
 constexpr int NF_HOT = NF_D - NF_COLD;
 constexpr int REC = 20;       // doubles per cold record: 15 doubles + 10 ints = 160 bytes
 
@@ -1966,8 +1967,10 @@ __global__ void __launch_bounds__(NT, MINB) transport3_kernel(const __grid_const
     unsigned long long st_av = 0, st_lb = 0, st_ll = 0;      // per lane = per list: backlog summed over the passes, batches run, lanes in them
     bool rdy_empty = false;
 #endif
-    // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100)
-    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / E2_INNER_SCALE + 2));
+    // steps per bookkeeping pass: rays are about as long as the grid has radial layers (measured best: 4-8 at nr = 2, 12 at nr = 20, 16 at nr = 100).
+    // Since the peel-off walks moved into the interaction event the marchers carry transport rays only, and on 3-D grids, where a ray also ends
+    // at the polar and azimuthal faces, shorter passes pay (nr = 20: 8 steps +2 % on C4, -1.7 % on the 2-D grid of C2; profiles/r02_ab_variants.txt)
+    const int inner = A.L.e2_inner > 0 ? A.L.e2_inner : min(16, max(6, T.nr / (T.np > 1 ? E2_INNER_SCALE + 1 : E2_INNER_SCALE) + 2));
 
     for (;;) {
         // every slot retired: the block is done.  One lane reads, so that the whole warp leaves together (a volatile read per lane
