@@ -402,6 +402,7 @@ int artes_gpu_set_grid(artes_gpu_ctx* ctx, int nr, int ntheta, int nphi, const d
 }  // extern "C"
 
 namespace {
+bool g_full_matrix = false;      // test hook, see artes_gpu_test_full_matrix
 // tables of n_wl wavelengths: the per-cell arrays are [n_wl][cells], cell_to_uniq indexes one common list of matrices
 int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, const double* k_abs, int n_uniq,
                           const double* uniq_matrix, const int32_t* cell_to_uniq, const int* cell_depths,
@@ -434,7 +435,7 @@ int set_wavelength_tables(artes_gpu_ctx* ctx, int n_wl, const double* k_sca, con
     std::vector<double> mc;
     {
         static const int zero_at[8] = {2, 3, 6, 7, 8, 9, 12, 13}, keep[8] = {0, 1, 4, 5, 10, 11, 14, 15};
-        bool compact = std::getenv("ARTES_GPU_FULL_MATRIX") == nullptr;       // (test hook: forces the 16-element path)
+        bool compact = !g_full_matrix;       // (artes_gpu_test_full_matrix: the test hook that forces the 16-element path)
         for (size_t r = 0; compact && r < (size_t)n_uniq * 180; ++r)
             for (int k = 0; k < 8; ++k) if (uniq_matrix[r * 16 + zero_at[k]] != 0.0) { compact = false; break; }
         if (compact) {
@@ -1022,6 +1023,8 @@ int artes_gpu_cell_face(artes_gpu_ctx* ctx, int mode, uint64_t n, const double* 
 int artes_gpu_last_engine(const artes_gpu_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
 
 int artes_gpu_test_ingest_chunk(int planes) { ingest_set_chunk_override(planes); return 0; }
+
+int artes_gpu_test_full_matrix(int on) { g_full_matrix = on != 0; return 0; }
 
 int artes_gpu_fma_peak(artes_gpu_ctx* ctx, double* fp64_tflops, double* fp32_tflops) {
     if (!ctx) return fail(nullptr, -1, "null context");

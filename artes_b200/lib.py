@@ -25,7 +25,7 @@ SYMBOLS = [
     "artes_gpu_set_grid", "artes_gpu_set_wavelength", "artes_gpu_set_wavelength_dense", "artes_gpu_set_wavelength_dense_wl",
     "artes_gpu_set_wavelengths", "artes_gpu_run", "artes_gpu_run_batch", "artes_gpu_run_multi", "artes_gpu_run_async", "artes_gpu_wait", "artes_gpu_nccl_unique_id",
     "artes_gpu_nccl_init_rank", "artes_gpu_trace", "artes_gpu_cell_face", "artes_gpu_device_info",
-    "artes_gpu_fma_peak", "artes_gpu_last_engine", "artes_gpu_test_ingest_chunk",
+    "artes_gpu_fma_peak", "artes_gpu_last_engine", "artes_gpu_test_ingest_chunk", "artes_gpu_test_full_matrix",
 ]
 
 
@@ -70,6 +70,7 @@ def load():
     lib.artes_gpu_fma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.artes_gpu_last_engine.argtypes = [C.c_void_p]
     lib.artes_gpu_test_ingest_chunk.argtypes = [C.c_int]
+    lib.artes_gpu_test_full_matrix.argtypes = [C.c_int]
     if lib.artes_gpu_abi_version() != ABI_VERSION:
         raise ArtesGpuError("libartes_gpu.so ABI version mismatch")
     _LIB = lib

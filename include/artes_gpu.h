@@ -237,6 +237,11 @@ int  artes_gpu_last_engine(const artes_gpu_ctx* ctx);
  * 0 restores the automatic choice (resident planes whenever they fit). */
 int  artes_gpu_test_ingest_chunk(int planes);
 
+/* Test hook for the scattering-matrix tables: block-diagonal matrices (exact zeros in the two off-diagonal 2x2 quarters of every
+ * block -- what python/opacity*.py write) are read by the interaction event from an eight-element copy; on != 0 makes the
+ * following artes_gpu_set_wavelength* calls keep the 16-element path for them as well, so that a test can compare the two. */
+int  artes_gpu_test_full_matrix(int on);
+
 /* FP64 / FP32 FMA peak microbenchmark (roofline denominator): returns TFLOP/s. */
 int  artes_gpu_fma_peak(artes_gpu_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
 

@@ -308,9 +308,9 @@ def test_dense_matrix_entry_equals_compact(atmospheres, gpu_factory):
 
 
 @pytest.mark.parametrize("name,px", [("c1_template_rayleigh", 25), ("c4_mie_patches", 32)])
-def test_eight_element_matrix_table_equals_the_full_matrices(atmospheres, gpu_factory, name, px, monkeypatch):
+def test_eight_element_matrix_table_equals_the_full_matrices(atmospheres, gpu_factory, name, px):
     """Block-diagonal scattering matrices (all the reference's opacity tools make them) are read from an eight-element copy
-    (DevTables::Mc, artes_gpu.cu); ARTES_GPU_FULL_MATRIX forces the 16-element path.  The terms the short path leaves out are
+    (DevTables::Mc, artes_gpu.cu); artes_gpu_test_full_matrix forces the 16-element path.  The terms the short path leaves out are
     products with exact zeros: same photons, same pixels, sums equal up to the order of the detector's atomic additions.  A matrix
     with one non-zero element outside the diagonal quarters must switch the short path off by itself."""
     atm = atmospheres(name)
@@ -319,10 +319,12 @@ def test_eight_element_matrix_table_equals_the_full_matrices(atmospheres, gpu_fa
     g, depth = gpu_factory(atm)
     a = g.run(L)
     assert a["stats"]["n_scatter"] > 100000
-    monkeypatch.setenv("ARTES_GPU_FULL_MATRIX", "1")
-    g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth)
-    b = g.run(L)
-    monkeypatch.delenv("ARTES_GPU_FULL_MATRIX")
+    g.lib.artes_gpu_test_full_matrix(1)
+    try:
+        g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], depth)
+        b = g.run(L)
+    finally:
+        g.lib.artes_gpu_test_full_matrix(0)
     for k in ("n_emit", "n_cell_face", "n_scatter", "n_peel"):
         assert a["stats"][k] == b["stats"][k]
     np.testing.assert_array_equal(a["det"][2], b["det"][2])

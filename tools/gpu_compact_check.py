@@ -6,6 +6,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np
     from tools import atmospheres as A
     from artes_b200 import abi, host
+    from artes_b200 import lib
+    lib.load().artes_gpu_test_full_matrix(1 if sys.argv[2] == "full" else 0)
     for name, builder, px in (("c1", "c1_template_rayleigh", 25), ("c2", "c2_hg_deck", 1), ("c4", "c4_mie_patches", 64)):
         t = host.Transport(getattr(A, builder)(), host.Params(nx=px, ny=px, det_phi=math.radians(60.0)), mode=abi.MODE_FAST)
         t.set_wavelength(0)
@@ -15,7 +17,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         t.close()
 else:
     import numpy as np
-    for tag, env in (("compact", {}), ("full", {"ARTES_GPU_FULL_MATRIX": "1"})):
+    for tag, env in (("compact", {}), ("full", {})):
         subprocess.check_call([sys.executable, __file__, "child", tag], env=dict(os.environ, **env))
     for name in ("c1", "c2", "c4"):
         a, b = np.load(f"/tmp/compact_{name}_compact.npy"), np.load(f"/tmp/compact_{name}_full.npy")
