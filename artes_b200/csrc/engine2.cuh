@@ -11,7 +11,7 @@
 //           :691-778 / :850-941, peel-off walk :4739-4761).  A lane ("marcher") owns one ray at a time and
 //           does nothing but step it radially in a tight loop; its whole state is ~30 registers.
 //   event   everything else.  A photon lives in a SLOT: the hot ray state in shared memory, the cold state
-//           (position, direction, Stokes vector, pending peel-off weights, stream position) in a 160-byte
+//           (position, direction, Stokes vector, optical depth; the photon id and its stream position are hot ints) in a 160-byte
 //           L2-resident record.  When its ray ends the marcher writes (t, tau) back to the slot and pushes
 //           the slot on the list of the event it needs; whenever a list holds 32 entries some warp takes
 //           them and runs the event fully converged.  Each event ends by setting up the slot's next ray
