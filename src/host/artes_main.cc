@@ -319,23 +319,14 @@ double package_energy(const Run& r, double wavelength, double det_phi, double pa
     return emis_total / (c.distance_planet * c.distance_planet * packages);
 }
 
-}  // namespace
-
-int main(int argc, char** argv) {
-    // ---- argument_input :4232-4258
-    if (argc <= 2) {
-        std::printf("How to run ARTES:\n./bin/ARTES [inputDirectory] [photons] -o [outputDirectory] -k [keyWord]=[value]\n");
-        return 0;
-    }
-    Run R;
+// ---- argument_input :4232-4258, artes.in (initialize :384-397), argument_keywords :4260-4309
+void read_inputs(int argc, char** argv, Run& R, bool dryrun, std::string& atmosphere_directory) {
     Config& c = R.c;
     R.atmosphere = argv[1];
     c.packages = std::floor(fortran_real(argv[2]));
-    const std::string atmosphere_directory = "input/" + R.atmosphere;
+    atmosphere_directory = "input/" + R.atmosphere;
     const std::string input_file = atmosphere_directory + "/artes.in";
     if (!fs::exists(input_file)) die("Input file does not exist!");
-
-    // ---- artes.in (initialize :384-397)
     {
         std::ifstream f(input_file);
         std::string line;
@@ -350,9 +341,6 @@ int main(int argc, char** argv) {
             input_parameters(c, key, value);
         }
     }
-    const bool dryrun = std::getenv("ARTES_DRYRUN") != nullptr;
-
-    // ---- argument_keywords :4260-4309
     for (int i = 1; i < argc; ++i) {
         const std::string arg = argv[i];
         if (arg == "-o" && i + 1 < argc) {
@@ -375,12 +363,12 @@ int main(int argc, char** argv) {
         }
     }
     if (R.output_name.empty()) die("No output directory given (-o [outputDirectory])");
+}
 
-    // ---- get_atmosphere
-    get_atmosphere(atmosphere_directory + "/atmosphere.fits", R.a);
+// ---- detector, oblateness, field of view (initialize :451-514); returns the observer's phase angle in degrees (0 for a phase curve)
+double derive_detector(Run& R) {
+    Config& c = R.c;
     const Atmosphere& a = R.a;
-
-    // ---- detector, oblateness, field of view (initialize :451-514)
     if (c.spectrum) { c.nx = 1; c.ny = 1; }
     else if (c.phase_curve) { c.nx = 1; c.ny = 1; c.det_theta = PI / 2.0; c.det_phi = 1.e-5; }
     R.ox = 1.0 / (1.0 - c.oblateness); R.oy = R.ox; R.oz = 1.0;
@@ -389,21 +377,77 @@ int main(int argc, char** argv) {
     R.pixel_scale = R.x_fov / c.nx;
     if (std::fabs(c.det_phi) < 1.e-3 || c.det_phi > 2.0 * PI - 1.e-3) c.det_phi = 1.e-3;
     if (c.det_phi > PI - 1.e-3 && c.det_phi < PI + 1.e-3) c.det_phi = PI - 1.e-3;
-    double phase_observer = 0.0;
-    if (!c.phase_curve)
-        phase_observer = std::acos(std::sin(c.theta_star) * std::cos(c.phi_star) * std::sin(c.det_theta) * std::cos(c.det_phi) +
-                                   std::sin(c.theta_star) * std::sin(c.phi_star) * std::sin(c.det_theta) * std::sin(c.det_phi) +
-                                   std::cos(c.theta_star) * std::cos(c.det_theta)) * 180.0 / PI;
+    if (c.phase_curve) return 0.0;
+    return std::acos(std::sin(c.theta_star) * std::cos(c.phi_star) * std::sin(c.det_theta) * std::cos(c.det_phi) +
+                     std::sin(c.theta_star) * std::sin(c.phi_star) * std::sin(c.det_theta) * std::sin(c.det_phi) +
+                     std::cos(c.theta_star) * std::cos(c.det_theta)) * 180.0 / PI;
+}
 
-    if (dryrun) {
-        std::printf("ARTES dry run\n atmosphere=%s output=%s photons=%.0f source=%d\n grid nr=%d ntheta=%d nphi=%d nlambda=%d\n"
-                    " detector type=%s theta=%.6f phi=%.6f pixels=%d\n fstop=%g minimum=%g albedo=%g oblateness=%g\n gpu devices=%d seed=%llu mode=%s\n",
-                    R.atmosphere.c_str(), R.output_name.c_str(), c.packages, c.photon_source, a.nr, a.nt, a.np, a.nl,
-                    c.phase_curve ? "phase" : c.spectrum ? "spectrum" : c.imaging_mono ? "imaging_mono" : c.imaging_broad ? "imaging_broad" : "none",
-                    c.det_theta, c.det_phi, c.nx, c.fstop, c.photon_minimum, c.surface_albedo, c.oblateness, c.devices,
-                    (unsigned long long)c.seed, c.mode == ARTES_MODE_FAST ? "fast" : "faithful");
+void print_dryrun(const Run& R) {
+    const Config& c = R.c;
+    const Atmosphere& a = R.a;
+    std::printf("ARTES dry run\n atmosphere=%s output=%s photons=%.0f source=%d\n grid nr=%d ntheta=%d nphi=%d nlambda=%d\n"
+                " detector type=%s theta=%.6f phi=%.6f pixels=%d\n fstop=%g minimum=%g albedo=%g oblateness=%g\n gpu devices=%d seed=%llu mode=%s\n",
+                R.atmosphere.c_str(), R.output_name.c_str(), c.packages, c.photon_source, a.nr, a.nt, a.np, a.nl,
+                c.phase_curve ? "phase" : c.spectrum ? "spectrum" : c.imaging_mono ? "imaging_mono" : c.imaging_broad ? "imaging_broad" : "none",
+                c.det_theta, c.det_phi, c.nx, c.fstop, c.photon_minimum, c.surface_albedo, c.oblateness, c.devices,
+                (unsigned long long)c.seed, c.mode == ARTES_MODE_FAST ? "fast" : "faithful");
+}
+
+}  // namespace
+
+// detector = thread sum x package energy (:959-975), photometry (:977-1004) and the Stokes errors of write_output (:3481-3519);
+// layout (ix, iy, stokes, l): sums / detector 12 planes of npx pixels, error 5 planes, photometry 11 numbers
+void finish_detector(size_t npx, const std::vector<double>& sums, double energy, std::vector<double>& detector, double* photometry,
+                     std::vector<double>& error) {
+    for (size_t i = 0; i < 4 * npx; ++i) {
+        detector[i] = sums[i] * energy; detector[4 * npx + i] = sums[4 * npx + i] * energy * energy; detector[8 * npx + i] = sums[8 * npx + i];
+    }
+    std::fill(photometry, photometry + 11, 0.0);
+    for (int s = 0; s < 4; ++s) {
+        double sum1 = 0, sum2 = 0, n = 0;
+        for (size_t i = 0; i < npx; ++i) { sum1 += detector[s * npx + i]; sum2 += detector[(4 + s) * npx + i]; n += detector[(8 + s) * npx + i]; }
+        photometry[2 * s] = sum1;
+        if (n > 0.0) { const double d = sum2 / n - (sum1 / n) * (sum1 / n); if (d > 0.0) photometry[2 * s + 1] = std::sqrt(d) * std::sqrt(n); }
+    }
+    photometry[8] = std::sqrt(photometry[2] * photometry[2] + photometry[4] * photometry[4]);
+    photometry[9] = photometry[0] != 0.0 ? photometry[8] / photometry[0] : 0.0;
+    // Stokes errors write_output :3481-3519
+    std::fill(error.begin(), error.end(), 0.0);
+    for (int s = 0; s < 4; ++s)
+        for (size_t i = 0; i < npx; ++i) {
+            const double n = detector[(8 + s) * npx + i];
+            if (n > 0.0) {
+                const double d = detector[(4 + s) * npx + i] / n - std::pow(detector[s * npx + i] / n, 2);
+                if (d > 0.0) error[s * npx + i] = std::sqrt(d) * std::sqrt(n);
+            }
+        }
+    for (size_t i = 0; i < npx; ++i) {
+        const double I = detector[i], Q = detector[npx + i], U = detector[2 * npx + i];
+        if (Q * Q + U * U > 0.0 && I > 0.0) {
+            const double pol = std::sqrt(Q * Q + U * U);
+            const double dpol = std::sqrt((std::pow(Q * error[npx + i], 2) + std::pow(U * error[2 * npx + i], 2)) / (2.0 * (Q * Q + U * U)));
+            error[4 * npx + i] = (pol / I) * std::sqrt(std::pow(dpol / pol, 2) + std::pow(error[i] / I, 2));
+        }
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc <= 2) {
+        std::printf("How to run ARTES:\n./bin/ARTES [inputDirectory] [photons] -o [outputDirectory] -k [keyWord]=[value]\n");
         return 0;
     }
+    Run R;
+    Config& c = R.c;
+    const bool dryrun = std::getenv("ARTES_DRYRUN") != nullptr;
+    std::string atmosphere_directory;
+    read_inputs(argc, argv, R, dryrun, atmosphere_directory);
+
+    // ---- get_atmosphere
+    get_atmosphere(atmosphere_directory + "/atmosphere.fits", R.a);
+    const Atmosphere& a = R.a;
+    const double phase_observer = derive_detector(R);
+    if (dryrun) { print_dryrun(R); return 0; }
 
     { std::ofstream f(R.outdir + "/error.log"); }
     if (c.log_file) R.log = std::fopen((R.outdir + "/output.log").c_str(), "w");
@@ -567,38 +611,7 @@ int main(int argc, char** argv) {
 
     // detector = thread sum x package energy (:959-975) and photometry (:977-1004); det layout (ix, iy, stokes, l)
     std::vector<double> detector(12 * npx), error(5 * npx);
-    auto finish_detector = [&](const std::vector<double>& sums, double energy) {
-        for (size_t i = 0; i < 4 * npx; ++i) {
-            detector[i] = sums[i] * energy; detector[4 * npx + i] = sums[4 * npx + i] * energy * energy; detector[8 * npx + i] = sums[8 * npx + i];
-        }
-        std::fill(photometry, photometry + 11, 0.0);
-        for (int s = 0; s < 4; ++s) {
-            double sum1 = 0, sum2 = 0, n = 0;
-            for (size_t i = 0; i < npx; ++i) { sum1 += detector[s * npx + i]; sum2 += detector[(4 + s) * npx + i]; n += detector[(8 + s) * npx + i]; }
-            photometry[2 * s] = sum1;
-            if (n > 0.0) { const double d = sum2 / n - (sum1 / n) * (sum1 / n); if (d > 0.0) photometry[2 * s + 1] = std::sqrt(d) * std::sqrt(n); }
-        }
-        photometry[8] = std::sqrt(photometry[2] * photometry[2] + photometry[4] * photometry[4]);
-        photometry[9] = photometry[0] != 0.0 ? photometry[8] / photometry[0] : 0.0;
-        // Stokes errors write_output :3481-3519
-        std::fill(error.begin(), error.end(), 0.0);
-        for (int s = 0; s < 4; ++s)
-            for (size_t i = 0; i < npx; ++i) {
-                const double n = detector[(8 + s) * npx + i];
-                if (n > 0.0) {
-                    const double d = detector[(4 + s) * npx + i] / n - std::pow(detector[s * npx + i] / n, 2);
-                    if (d > 0.0) error[s * npx + i] = std::sqrt(d) * std::sqrt(n);
-                }
-            }
-        for (size_t i = 0; i < npx; ++i) {
-            const double I = detector[i], Q = detector[npx + i], U = detector[2 * npx + i];
-            if (Q * Q + U * U > 0.0 && I > 0.0) {
-                const double pol = std::sqrt(Q * Q + U * U);
-                const double dpol = std::sqrt((std::pow(Q * error[npx + i], 2) + std::pow(U * error[2 * npx + i], 2)) / (2.0 * (Q * Q + U * U)));
-                error[4 * npx + i] = (pol / I) * std::sqrt(std::pow(dpol / pol, 2) + std::pow(error[i] / I, 2));
-            }
-        }
-    };
+    auto finish_detector = [&](const std::vector<double>& sums, double energy) { ::finish_detector(npx, sums, energy, detector, photometry, error); };
 
     // write_output :3472-3772
     auto write_output = [&](int l, double det_phi) {
