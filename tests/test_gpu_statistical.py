@@ -231,3 +231,27 @@ def test_rayleigh_semi_infinite_literature_anchor_on_gpu():
         assert abs(ag / 0.7975 - 1.0) < tol, (mode, ag)
         assert 0.315 < p90 < 0.335, (mode, p90)
         assert abs(u90) < 0.005
+
+
+def test_isotropic_semi_infinite_h_function_anchor_on_gpu():
+    """The exact-solution anchor of tests/test_oracle.py on the product (both engines): the conservative semi-infinite isotropically
+    scattering atmosphere reflects F H(mu)^2 / 8 at full phase (Chandrasekhar's H-function): geometric albedo 0.6897 and the
+    limb darkening in five rings of equal projected area.  With 1e6 packets the fast mode is held to 2 % per ring and 1 % in the
+    albedo (the finite depth, tau = 32 over a white surface, accounts for +0.4 % there)."""
+    from artes_b200.lib import GpuTransport
+    from test_oracle import isotropic_deep_observables
+
+    for mode, n, tol_ag, tol_ring in ((abi.MODE_FAST, 1000000, 0.010, 0.020), (abi.MODE_FAITHFUL, 100000, 0.015, 0.030)):
+        def runner(atm, L):
+            g = GpuTransport((0,))
+            g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+            g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)
+            L.mode = mode
+            r = g.run(L)
+            g.close()
+            return r
+        ag, ag_theory, ratios = isotropic_deep_observables(runner, n)
+        print("isotropic_deep", "fast" if mode == abi.MODE_FAST else "faithful", "A_g", ag, "theory", ag_theory, "rings", ratios)
+        assert abs(ag / ag_theory - 1.0) < tol_ag, (mode, ag)
+        for k, q in enumerate(ratios):
+            assert abs(q - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, k, q)

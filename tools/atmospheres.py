@@ -436,6 +436,19 @@ def rayleigh_deep(tau=32.0, nr=8, thickness=8e3):
     return atm
 
 
+def isotropic_deep(tau=32.0, nr=8, thickness=8e3):
+    """Analytic anchor for multiple scattering: a homogeneous, conservative, isotropically scattering atmosphere of radial optical
+    depth `tau` over a white Lambert surface -- for tau >~ 30 Chandrasekhar's conservative semi-infinite atmosphere, whose emergent
+    intensity at full phase is F H(mu)^2 / 8 (H = the H-function of isotropic scattering; geometric albedo 1/4 int H^2 mu dmu = 0.6897)."""
+    rfront = R_JUP + np.linspace(0.0, thickness, nr + 1)
+    b = _Builder(rfront, [0.0, 180.0], [0.0], [0.7])
+    b.add_region(isotropic([0.7]), 1.0, (0, nr), (0, 1), (0, 1))
+    atm = b.finish("isotropic_deep", artes_in=_artes_in(**{"planet:surface_albedo": "1"}))
+    atm.k_sca = atm.k_sca * (tau / atm.radial_tau())
+    atm.k_abs = atm.k_abs * 0.0
+    return atm
+
+
 CONFIGS = {"c1": c1_template_rayleigh, "c2": c2_hg_deck, "c3": c3_molecular, "c4": c4_mie_patches, "c5": c5_scale}
 
 
