@@ -239,7 +239,7 @@ def test_isotropic_semi_infinite_h_function_anchor_on_gpu():
     limb darkening in five rings of equal projected area.  With 1e6 packets the fast mode is held to 2 % per ring and 1 % in the
     albedo (the finite depth, tau = 32 over a white surface, accounts for +0.4 % there)."""
     from artes_b200.lib import GpuTransport
-    from test_oracle import isotropic_deep_observables
+    from test_oracle import isotropic_deep_observables, isotropic_deep_phase_points
 
     for mode, n, tol_ag, tol_ring in ((abi.MODE_FAST, 1000000, 0.010, 0.020), (abi.MODE_FAITHFUL, 100000, 0.015, 0.030)):
         def runner(atm, L):
@@ -250,8 +250,14 @@ def test_isotropic_semi_infinite_h_function_anchor_on_gpu():
             r = g.run(L)
             g.close()
             return r
-        ag, ag_theory, ratios = isotropic_deep_observables(runner, n)
-        print("isotropic_deep", "fast" if mode == abi.MODE_FAST else "faithful", "A_g", ag, "theory", ag_theory, "rings", ratios)
-        assert abs(ag / ag_theory - 1.0) < tol_ag, (mode, ag)
-        for k, q in enumerate(ratios):
-            assert abs(q - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, k, q)
+        for omega in (1.0, 0.8):      # conservative, and with absorption (the H-function of that albedo; survival weighting :791-813)
+            ag, ag_theory, ratios = isotropic_deep_observables(runner, n, omega=omega)
+            print("isotropic_deep", "fast" if mode == abi.MODE_FAST else "faithful", "omega", omega, "A_g", ag, "theory", ag_theory, "rings", ratios)
+            assert abs(ag / ag_theory - 1.0) < tol_ag, (mode, omega, ag)
+            for k, q in enumerate(ratios):
+                assert abs(q - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, omega, k, q)
+        if mode == abi.MODE_FAST:     # the disk-integrated phase law away from full phase (the crescent at 120 deg sits ~1 % low: sphericity at the limb)
+            qs = isotropic_deep_phase_points(runner, n)
+            print("isotropic_deep phase law, measured / theory at 60, 90, 120 deg:", qs)
+            for adeg, tol, q in zip((60.0, 90.0, 120.0), (0.01, 0.015, 0.025), qs):
+                assert abs(q - 1.0) < tol, (adeg, q)

@@ -127,14 +127,15 @@ def test_rayleigh_semi_infinite_literature_anchor():
     assert abs(u90) < 0.01
 
 
-def chandrasekhar_h(n=64):
-    """H-function of conservative isotropic scattering on a Gauss-Legendre grid of (0, 1): 1/H(mu) = 1/2 int mu' H(mu') / (mu + mu') dmu'
-    (Chandrasekhar 1960, ch. V).  Returns (mu, weights, H); checks: H(1) = 2.9078, int H = 2, int H mu = 2/sqrt(3)."""
+def chandrasekhar_h(omega=1.0, n=64):
+    """H-function of isotropic scattering with single-scattering albedo omega on a Gauss-Legendre grid of (0, 1):
+    1/H(mu) = sqrt(1 - omega) + omega/2 int mu' H(mu') / (mu + mu') dmu'  (Chandrasekhar 1960, ch. V).  Returns (mu, weights, H);
+    conservative case: H(1) = 2.9078, int H = 2, int H mu = 2/sqrt(3)."""
     x, w = np.polynomial.legendre.leggauss(n)
     mu, w = 0.5 * (x + 1.0), 0.5 * w
     H = np.ones_like(mu)
     for _ in range(4000):
-        Hn = 1.0 / (0.5 * np.sum(w * mu * H / (mu[:, None] + mu[None, :]), axis=1))
+        Hn = 1.0 / (math.sqrt(1.0 - omega) + 0.5 * omega * np.sum(w * mu * H / (mu[:, None] + mu[None, :]), axis=1))
         done = np.max(np.abs(Hn - H)) < 1e-13
         H = 0.5 * (H + Hn)
         if done:
@@ -142,26 +143,47 @@ def chandrasekhar_h(n=64):
     return mu, w, H
 
 
-def isotropic_deep_observables(runner, n, npix=31, seed=5):
+def h_at(m, omega, mu, w, H):
+    """H(m) for arbitrary m in [0, 1] from the grid solution (the integral equation itself is the interpolation formula)"""
+    m = np.asarray(m, dtype=np.float64)
+    return 1.0 / (math.sqrt(1.0 - omega) + 0.5 * omega * np.sum(w * mu * H / (m[..., None] + mu), axis=-1))
+
+
+def isotropic_phase_law(alpha, omega=1.0):
+    """pi x (reflected flux / incident flux on the disk) of the semi-infinite isotropic atmosphere at phase angle alpha, i.e. geometric
+    albedo x phase function: (1/pi) int int mu0 R(mu, mu0) mu cos(psi) dpsi dlambda over the lit and visible part of the sphere,
+    R = omega H(mu) H(mu0) / (4 (mu + mu0)), mu = cos(psi) cos(lambda), mu0 = cos(psi) cos(alpha - lambda)."""
+    mu_g, w_g, H = chandrasekhar_h(omega)
+    x, wq = np.polynomial.legendre.leggauss(96)
+    lam = 0.5 * (x + 1.0) * (math.pi - alpha) + (alpha - 0.5 * math.pi)       # lambda in [alpha - pi/2, pi/2]
+    wl = 0.5 * (math.pi - alpha) * wq
+    psi = 0.5 * math.pi * x                                                    # psi in [-pi/2, pi/2]
+    wp = 0.5 * math.pi * wq
+    cp = np.cos(psi)[:, None]
+    m, m0 = cp * np.cos(lam)[None, :], cp * np.cos(alpha - lam)[None, :]
+    R = 0.25 * omega * h_at(m, omega, mu_g, w_g, H) * h_at(m0, omega, mu_g, w_g, H) / (m + m0)
+    return float(np.sum(wp[:, None] * wl[None, :] * m0 * R * m * cp) / math.pi)
+
+
+def isotropic_deep_observables(runner, n, npix=31, seed=5, omega=1.0):
     """Full-phase image of A.isotropic_deep through `runner(atm, launch) -> result` against Chandrasekhar's semi-infinite atmosphere:
     returns (geometric albedo, its theoretical value, measured / expected intensity in five rings of equal projected area)."""
-    atm = A.isotropic_deep()
+    atm = A.isotropic_deep(omega=omega)
     xm = 1.3 * atm.rfront[-1]
     L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=seed, surface_albedo=1.0, det_phi=math.radians(0.0573), nx=npix, ny=npix, fstop=1e-7)
     r = runner(atm, L)
     assert int(r["err"].sum()) == 0
     img = r["det"][0, 0] / n                      # sum = A_g / pi; a pixel holds (1/pi) (I/F) dA / (pi R^2)
     assert r["det"][0, 1].sum() == 0.0 and r["det"][0, 2].sum() == 0.0      # F11 only: unpolarised
-    mu, w, H = chandrasekhar_h()
-    ag_theory = 0.25 * np.sum(w * H * H * mu)
-    # expected image: I/F = H(mu)^2 / 8 at mu = sqrt(1 - rho^2), integrated over every pixel on an 8 x 8 sub-grid
+    mu, w, H = chandrasekhar_h(omega)
+    ag_theory = 0.25 * omega * np.sum(w * H * H * mu)
+    # expected image: I/F = omega H(mu)^2 / 8 at mu = sqrt(1 - rho^2), integrated over every pixel on an 8 x 8 sub-grid
     sub = 8
     edges = np.linspace(-xm, xm, npix * sub + 1)
     c = 0.5 * (edges[1:] + edges[:-1]) / atm.rfront[-1]
     rho2 = c[None, :] ** 2 + c[:, None] ** 2
-    m = np.sqrt(np.clip(1.0 - rho2, 0.0, None))
-    Hm = 1.0 / (0.5 * np.sum(w * mu * H / (m[..., None] + mu), axis=-1))
-    fine = np.where(rho2 < 1.0, Hm * Hm / 8.0, 0.0) * (edges[1] - edges[0]) ** 2 / (math.pi * atm.rfront[-1] ** 2) / math.pi
+    Hm = h_at(np.sqrt(np.clip(1.0 - rho2, 0.0, None)), omega, mu, w, H)
+    fine = np.where(rho2 < 1.0, omega * Hm * Hm / 8.0, 0.0) * (edges[1] - edges[0]) ** 2 / (math.pi * atm.rfront[-1] ** 2) / math.pi
     expect = fine.reshape(npix, sub, npix, sub).sum(axis=(1, 3))
     pc = 0.5 * (np.linspace(-xm, xm, npix + 1)[1:] + np.linspace(-xm, xm, npix + 1)[:-1]) / atm.rfront[-1]
     ring = np.minimum((5.0 * (pc[None, :] ** 2 + pc[:, None] ** 2)).astype(int), 5)      # equal-area rings by the pixel centre; 5 = off the disk
@@ -169,26 +191,50 @@ def isotropic_deep_observables(runner, n, npix=31, seed=5):
     return math.pi * img.sum(), ag_theory, ratios
 
 
-def test_isotropic_semi_infinite_h_function_anchor():
-    """Multiple scattering against an exact solution: the conservative semi-infinite isotropically scattering atmosphere reflects
-    I(mu) = F H(mu)^2 / 8 at full phase (Chandrasekhar's H-function, computed here from its integral equation), i.e. a geometric
-    albedo of 0.6897 and a definite limb darkening.  The oracle's optical-depth sampling, survival / scattering loop, peel-off
-    weights, e^-tau walks and pixel mapping all enter the ring profile; none of the numbers comes from the code under test."""
-    from oracle_lib import Oracle
-    mu, w, H = chandrasekhar_h()
-    assert abs(1.0 / (0.5 * np.sum(w * mu * H / (1.0 + mu))) - 2.9078) < 2e-4 and abs(np.sum(w * H) - 2.0) < 1e-9
-    assert abs(np.sum(w * H * mu) - 2.0 / math.sqrt(3.0)) < 1e-9
+def isotropic_deep_phase_points(runner, n, alphas_deg=(60.0, 90.0, 120.0), omega=1.0, seed=6):
+    """measured / expected disk-integrated brightness of A.isotropic_deep at the given phase angles (1 x 1 detector)"""
+    atm = A.isotropic_deep(omega=omega)
+    xm = 1.3 * atm.rfront[-1]
+    out = []
+    for adeg in alphas_deg:
+        L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=seed, surface_albedo=1.0, det_phi=math.radians(adeg), nx=1, ny=1, fstop=1e-7)
+        r = runner(atm, L)
+        assert int(r["err"].sum()) == 0
+        out.append(math.pi * r["det"][0, 0].sum() / n / isotropic_phase_law(math.radians(adeg), omega))
+    return out
 
-    def runner(atm, L):
-        o = Oracle()
-        o.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
-        o.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)    # surface = the planet (no tau > 30 cut)
-        return o.run(L)
-    ag, ag_theory, ratios = isotropic_deep_observables(runner, 40000)
+
+def _oracle_runner(atm, L):
+    from oracle_lib import Oracle
+    o = Oracle()
+    o.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+    o.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)    # surface = the planet (no tau > 30 cut)
+    return o.run(L)
+
+
+def test_isotropic_semi_infinite_h_function_anchor():
+    """Multiple scattering against an exact solution: the semi-infinite isotropically scattering atmosphere reflects
+    I(mu, mu0) = F mu0 omega H(mu) H(mu0) / (4 (mu + mu0)) (Chandrasekhar's H-function, computed here from its integral equation):
+    conservative case, full phase: geometric albedo 0.6897 and a definite limb darkening; with absorption (omega = 0.8) the same
+    with the H-function of that albedo (survival weighting, :791-813); away from full phase the disk-integrated phase law.  The
+    oracle's optical-depth sampling, survival / scattering loop, peel-off weights, e^-tau walks and pixel mapping all enter; none
+    of the expected numbers comes from the code under test."""
+    mu, w, H = chandrasekhar_h()
+    assert abs(h_at(1.0, 1.0, mu, w, H) - 2.9078) < 2e-4 and abs(np.sum(w * H) - 2.0) < 1e-9
+    assert abs(np.sum(w * H * mu) - 2.0 / math.sqrt(3.0)) < 1e-9
+    assert abs(isotropic_phase_law(1e-9) - 0.25 * np.sum(w * H * H * mu)) < 2e-4      # the phase law ends in the geometric albedo
+    ag, ag_theory, ratios = isotropic_deep_observables(_oracle_runner, 40000)
     assert abs(ag_theory - 0.68967) < 1e-4
     assert abs(ag / ag_theory - 1.0) < 0.015, ag
     for k, q in enumerate(ratios):
         assert abs(q - 1.0) < (0.03 if k < 4 else 0.05), (k, q)      # the outermost ring holds the limb pixels (mu < 0.45)
+    ag, ag_theory, ratios = isotropic_deep_observables(_oracle_runner, 40000, omega=0.8)
+    assert abs(ag / ag_theory - 1.0) < 0.015, (ag, ag_theory)
+    for k, q in enumerate(ratios):
+        assert abs(q - 1.0) < (0.03 if k < 4 else 0.05), (k, q)
+    # (40 000 packets: sigma 0.4 / 0.7 / 1.6 % at 60 / 90 / 120 deg; the crescent at 120 deg also sits ~1 % low: sphericity at the limb)
+    for adeg, tol, q in zip((60.0, 90.0, 120.0), (0.02, 0.025, 0.045), isotropic_deep_phase_points(_oracle_runner, 40000)):
+        assert abs(q - 1.0) < tol, (adeg, q)
 
 
 def test_host_photometry_and_error_planes_match_oracle_restatement():
