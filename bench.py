@@ -382,7 +382,7 @@ def main():
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
             # as captured (the DRAM traffic of this kernel is mostly launch-constant: tables once, the L2-resident photon records
-            # as they are evicted, the image; 56 MB at 8e6 and 61 MB at 4e6 packets on C4), not scaled to this launch size
+            # as they are evicted, the image; 32 MB at 4e6 packets on C4 with the final kernel of round 2), not scaled to this launch size
             traffic = tr["dram_bytes_per_launch"] if tr else None
             traffic_at = tr["photons_per_launch"] if tr else None
         except Exception:
