@@ -256,6 +256,13 @@ def test_isotropic_semi_infinite_h_function_anchor_on_gpu():
             assert abs(ag / ag_theory - 1.0) < tol_ag, (mode, omega, ag)
             for k, q in enumerate(ratios):
                 assert abs(q - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, omega, k, q)
+        # the same medium cut into 6 polar x 8 azimuthal cells: the walks cross cones and half-planes as well (3-D marcher, RES events,
+        # polar / azimuthal re-solves inside the peel-off walk); the exact answer is the same
+        ag, ag_theory, ratios = isotropic_deep_observables(runner, n, ntheta=6, nphi=8)
+        print("isotropic_deep", "fast" if mode == abi.MODE_FAST else "faithful", "3-D grid A_g", ag, "theory", ag_theory, "rings", ratios)
+        assert abs(ag / ag_theory - 1.0) < tol_ag, (mode, "3-D", ag)
+        for k, q in enumerate(ratios):
+            assert abs(q - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, "3-D", k, q)
         if mode == abi.MODE_FAST:     # the disk-integrated phase law away from full phase (the crescent at 120 deg sits ~1 % low: sphericity at the limb)
             qs = isotropic_deep_phase_points(runner, n)
             print("isotropic_deep phase law, measured / theory at 60, 90, 120 deg:", qs)

@@ -165,10 +165,10 @@ def isotropic_phase_law(alpha, omega=1.0):
     return float(np.sum(wp[:, None] * wl[None, :] * m0 * R * m * cp) / math.pi)
 
 
-def isotropic_deep_observables(runner, n, npix=31, seed=5, omega=1.0):
+def isotropic_deep_observables(runner, n, npix=31, seed=5, omega=1.0, ntheta=1, nphi=1):
     """Full-phase image of A.isotropic_deep through `runner(atm, launch) -> result` against Chandrasekhar's semi-infinite atmosphere:
     returns (geometric albedo, its theoretical value, measured / expected intensity in five rings of equal projected area)."""
-    atm = A.isotropic_deep(omega=omega)
+    atm = A.isotropic_deep(omega=omega, ntheta=ntheta, nphi=nphi)
     xm = 1.3 * atm.rfront[-1]
     L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=seed, surface_albedo=1.0, det_phi=math.radians(0.0573), nx=npix, ny=npix, fstop=1e-7)
     r = runner(atm, L)
@@ -230,6 +230,11 @@ def test_isotropic_semi_infinite_h_function_anchor():
         assert abs(q - 1.0) < (0.03 if k < 4 else 0.05), (k, q)      # the outermost ring holds the limb pixels (mu < 0.45)
     ag, ag_theory, ratios = isotropic_deep_observables(_oracle_runner, 40000, omega=0.8)
     assert abs(ag / ag_theory - 1.0) < 0.015, (ag, ag_theory)
+    for k, q in enumerate(ratios):
+        assert abs(q - 1.0) < (0.03 if k < 4 else 0.05), (k, q)
+    # the same medium on a 3-D grid (6 polar x 8 azimuthal cells): cones and half-planes are crossed, the answer must not change
+    ag, ag_theory, ratios = isotropic_deep_observables(_oracle_runner, 40000, ntheta=6, nphi=8)
+    assert abs(ag / ag_theory - 1.0) < 0.015, ag
     for k, q in enumerate(ratios):
         assert abs(q - 1.0) < (0.03 if k < 4 else 0.05), (k, q)
     # (40 000 packets: sigma 0.4 / 0.7 / 1.6 % at 60 / 90 / 120 deg; the crescent at 120 deg also sits ~1 % low: sphericity at the limb)

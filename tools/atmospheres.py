@@ -436,14 +436,15 @@ def rayleigh_deep(tau=32.0, nr=8, thickness=8e3):
     return atm
 
 
-def isotropic_deep(tau=32.0, nr=8, thickness=8e3, omega=1.0):
+def isotropic_deep(tau=32.0, nr=8, thickness=8e3, omega=1.0, ntheta=1, nphi=1):
     """Analytic anchor for multiple scattering: a homogeneous, conservative, isotropically scattering atmosphere of radial optical
     depth `tau` over a white Lambert surface -- for tau >~ 30 Chandrasekhar's conservative semi-infinite atmosphere, whose emergent
     intensity at full phase is F H(mu)^2 / 8 (H = the H-function of isotropic scattering; geometric albedo 1/4 int H^2 mu dmu = 0.6897).
-    omega < 1: the same with absorption (single-scattering albedo omega): I = omega F H^2 / 8 with the H-function of that albedo."""
+    omega < 1: the same with absorption (single-scattering albedo omega): I = omega F H^2 / 8 with the H-function of that albedo.
+    ntheta, nphi > 1: the same homogeneous medium cut into polar / azimuthal cells (the walk then crosses cones and half-planes too)."""
     rfront = R_JUP + np.linspace(0.0, thickness, nr + 1)
-    b = _Builder(rfront, [0.0, 180.0], [0.0], [0.7])
-    b.add_region(isotropic([0.7]), 1.0, (0, nr), (0, 1), (0, 1))
+    b = _Builder(rfront, np.linspace(0.0, 180.0, ntheta + 1), np.arange(nphi) * (360.0 / nphi), [0.7])
+    b.add_region(isotropic([0.7]), 1.0, (0, nr), (0, ntheta), (0, nphi))
     atm = b.finish("isotropic_deep", artes_in=_artes_in(**{"planet:surface_albedo": "1"}))
     atm.k_abs = atm.k_abs * 0.0
     atm.k_sca = atm.k_sca * (tau / atm.radial_tau())          # radial optical depth `tau` in total,
