@@ -268,3 +268,27 @@ def test_isotropic_semi_infinite_h_function_anchor_on_gpu():
             print("isotropic_deep phase law, measured / theory at 60, 90, 120 deg:", qs)
             for adeg, tol, q in zip((60.0, 90.0, 120.0), (0.01, 0.015, 0.025), qs):
                 assert abs(q - 1.0) < tol, (adeg, q)
+
+
+def test_henyey_greenstein_semi_infinite_invariance_anchor_on_gpu():
+    """The anisotropic-scattering anchor of tests/test_oracle.py on the product: semi-infinite Henyey-Greenstein atmosphere (g = 0.5,
+    omega = 0.9, unpolarising) against the solution of Ambartsumian's invariance equation -- geometric albedo 0.18692 and the full-phase
+    brightness S(mu, mu, pi) / 4 mu in five rings.  This is the check that exercises what the interaction event of the fast mode does
+    differently from the reference: prefix-table CDFs inverted by bisection and the eight-element matrix table."""
+    from artes_b200.lib import GpuTransport
+    from test_oracle import hg_deep_observables
+
+    for mode, n, tol_ag, tol_ring in ((abi.MODE_FAST, 2000000, 0.008, 0.015), (abi.MODE_FAITHFUL, 150000, 0.015, 0.030)):
+        def runner(atm, L):
+            g = GpuTransport((0,))
+            g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+            g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)
+            L.mode = mode
+            r = g.run(L)
+            g.close()
+            return r
+        ag, ag_expected, ratios = hg_deep_observables(runner, n)
+        print("hg_deep", "fast" if mode == abi.MODE_FAST else "faithful", "A_g", ag, "expected", ag_expected, "rings", ratios)
+        assert abs(ag / ag_expected - 1.0) < tol_ag, (mode, ag)
+        for k, q in enumerate(ratios):
+            assert abs(q - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, k, q)
