@@ -292,3 +292,28 @@ def test_henyey_greenstein_semi_infinite_invariance_anchor_on_gpu():
         assert abs(ag / ag_expected - 1.0) < tol_ag, (mode, ag)
         for k, q in enumerate(ratios):
             assert abs(q - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, k, q)
+
+
+def test_rayleigh_vector_invariance_anchor_on_gpu():
+    """The polarised anchor of tests/test_oracle.py on the product: semi-infinite Rayleigh atmosphere with omega = 0.9 against the 3 x 3
+    invariance-equation solution -- geometric albedo 0.3999 (scalar theory: 0.3657), full-phase brightness in five rings, and the RADIAL
+    limb polarisation at full phase (a pure multiple-scattering effect, 0.6 % in the central ring to 6.9 % at the limb)."""
+    from artes_b200.lib import GpuTransport
+    from test_oracle import rayleigh_absorbing_observables
+
+    for mode, n, tol_ag, tol_ring, tol_pol in ((abi.MODE_FAST, 2000000, 0.005, 0.015, 0.003), (abi.MODE_FAITHFUL, 150000, 0.01, 0.03, 0.008)):
+        def runner(atm, L):
+            g = GpuTransport((0,))
+            g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+            g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)
+            L.mode = mode
+            r = g.run(L)
+            g.close()
+            return r
+        ag, ag_vector, ag_scalar, rI, pol, pol_expected = rayleigh_absorbing_observables(runner, n)
+        print("rayleigh omega 0.9", "fast" if mode == abi.MODE_FAST else "faithful", "A_g", ag, "vector theory", ag_vector, "scalar theory", ag_scalar,
+              "rings", rI, "Q_r/I", pol, "expected", pol_expected)
+        assert abs(ag / ag_vector - 1.0) < tol_ag, (mode, ag)
+        for k in range(5):
+            assert abs(rI[k] - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, k, rI[k])
+            assert abs(pol[k] - pol_expected[k]) < tol_pol, (mode, k, pol[k], pol_expected[k])

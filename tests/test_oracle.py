@@ -329,6 +329,121 @@ def test_henyey_greenstein_semi_infinite_invariance_anchor():
         assert abs(q - 1.0) < (0.03 if k < 4 else 0.05), (k, q)
 
 
+def rayleigh_phase_blocks(mu, phi, s_out, s_in, unpolarising=None):
+    """3 x 3 phase-matrix blocks P[a, b] in Chandrasekhar's (I_l, I_r, U) representation for the propagation directions
+    out_a = (s_out mu[a], phi[a]) and in_b = (s_in mu[b], phi[b]).  Rayleigh scattering projects the incident field on the plane transverse
+    to the new direction: E_l' = (l'.l) E_l + (l'.r) E_r, E_r' = (r'.l) E_l + (r'.r) E_r with the unit vectors l = d/dtheta, r = d/dphi of
+    each direction (the meridian-plane frame); I_l = |E_l|^2, I_r = |E_r|^2, U = 2 Re E_l E_r*; the factor 3/2 normalises
+    (1/4pi) int P dOmega to 1 for unpolarised light.  unpolarising: a test scatterer with that phase function and unpolarised output."""
+    def frame(sgn):
+        ct, st = sgn * mu, np.sqrt(1.0 - mu * mu)
+        l = np.stack([ct * np.cos(phi), ct * np.sin(phi), -st], axis=-1)
+        r = np.stack([-np.sin(phi), np.cos(phi), np.zeros_like(phi)], axis=-1)
+        k = np.stack([st * np.cos(phi), st * np.sin(phi), ct], axis=-1)
+        return l, r, k
+    lo, ro, ko = frame(s_out)
+    li, ri, ki = frame(s_in)
+    ll, lr, rl, rr = lo @ li.T, lo @ ri.T, ro @ li.T, ro @ ri.T
+    P = np.zeros(ll.shape + (3, 3))
+    if unpolarising is not None:
+        P[..., 0, 0] = P[..., 0, 1] = P[..., 1, 0] = P[..., 1, 1] = 0.5 * unpolarising(np.clip(ko @ ki.T, -1.0, 1.0))
+        return P
+    P[..., 0, 0], P[..., 0, 1], P[..., 0, 2] = ll * ll, lr * lr, ll * lr
+    P[..., 1, 0], P[..., 1, 1], P[..., 1, 2] = rl * rl, rr * rr, rl * rr
+    P[..., 2, 0], P[..., 2, 1], P[..., 2, 2] = 2.0 * ll * rl, 2.0 * lr * rr, ll * rr + lr * rl
+    return 1.5 * P
+
+
+def vector_reflection_semi_infinite(omega, n_mu=24, n_phi=8, tol=1e-11, unpolarising=None):
+    """The invariance equation of reflection_semi_infinite for POLARISED light, Rayleigh scattering: S and P are 3 x 3 matrices per pair of
+    directions ((1/mu + 1/mu0) S = P_ud + 1/4pi int S P_dd dOmega''/mu'' + 1/4pi int P_uu S dOmega'/mu' + 1/16pi^2 int int S P_du S ...;
+    the rightmost factor acts first), discretised on n_mu Gauss points x n_phi azimuths (Rayleigh scattering has azimuthal orders <= 2, so 8
+    equidistant azimuths integrate every product exactly).  Returns (mu, weights, S[a, k, b, k'], n_phi) with direction index a = i n_phi + j."""
+    x, w = np.polynomial.legendre.leggauss(n_mu)
+    mu, w = 0.5 * (x + 1.0), 0.5 * w
+    MU, PH = np.repeat(mu, n_phi), np.tile(2.0 * math.pi * np.arange(n_phi) / n_phi, n_mu)
+    nd = n_mu * n_phi
+
+    def big(s_out, s_in):
+        return (omega * rayleigh_phase_blocks(MU, PH, s_out, s_in, unpolarising)).transpose(0, 2, 1, 3).reshape(3 * nd, 3 * nd)
+    P_ud, P_dd, P_uu, P_du = big(+1, -1), big(-1, -1), big(+1, +1), big(-1, +1)
+    W3 = np.repeat(np.repeat(w / mu, n_phi) * (2.0 * math.pi / n_phi), 3)      # dOmega / mu per (direction, Stokes) column
+    inv = np.repeat(np.repeat(1.0 / (1.0 / MU[:, None] + 1.0 / MU[None, :]), 3, axis=0), 3, axis=1)
+    c1, c2 = 1.0 / (4.0 * math.pi), 1.0 / (16.0 * math.pi ** 2)
+    S = P_ud * inv
+    for _ in range(20000):
+        SW = S * W3[None, :]
+        new = (P_ud + c1 * SW @ P_dd + c1 * (P_uu * W3[None, :]) @ S + c2 * SW @ (P_du * W3[None, :]) @ S) * inv
+        done = np.max(np.abs(new - S)) < tol
+        S = new
+        if done:
+            break
+    return mu, w, S.reshape(nd, 3, nd, 3), n_phi
+
+
+def vector_backscatter(mu, S, n_phi):
+    """(I_l, I_r, U) / F of the light reflected straight back (mu = mu0, phi = phi0 + pi) for unpolarised incident light"""
+    out = np.zeros((len(mu), 3))
+    for i in range(len(mu)):
+        out[i] = S[i * n_phi + n_phi // 2, :, i * n_phi, :] @ np.array([0.5, 0.5, 0.0]) / (4.0 * mu[i])
+    return out
+
+
+def rayleigh_absorbing_observables(runner, n, omega=0.9, npix=31, seed=5):
+    """Full-phase image of A.rayleigh_deep(omega) against the vector invariance-equation solution: returns (geometric albedo, its expected
+    value, the scalar-theory value, measured / expected intensity in five rings, measured and expected radial polarisation Q_r / I per ring)."""
+    atm = A.rayleigh_deep(omega=omega)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=seed, surface_albedo=1.0, det_phi=math.radians(0.0573), nx=npix, ny=npix, fstop=1e-7)
+    r = runner(atm, L)
+    assert int(r["err"].sum()) == 0
+    I, Q, U = (r["det"][0, k] / n for k in range(3))
+    mu, w, S, n_phi = vector_reflection_semi_infinite(omega)
+    f = vector_backscatter(mu, S, n_phi)
+    fI, fQ = f[:, 0] + f[:, 1], f[:, 0] - f[:, 1]              # Q > 0: along the meridian plane, i.e. radial on the disk
+    assert np.max(np.abs(f[:, 2])) < 1e-9                        # no U in the meridian frame at exact backscattering (symmetry)
+    mus, ws, Ss = reflection_semi_infinite(lambda c: 0.75 * (1.0 + c * c), omega, n_mu=24, m_max=4)
+    ag_scalar = float(np.sum(ws * backscatter_brightness(mus, Ss) * 2.0 * mus))
+    sub = 8
+    edges = np.linspace(-xm, xm, npix * sub + 1)
+    c = 0.5 * (edges[1:] + edges[:-1]) / atm.rfront[-1]
+    rho2 = c[None, :] ** 2 + c[:, None] ** 2
+    m = np.sqrt(np.clip(1.0 - rho2, 0.0, None))
+    area = (edges[1] - edges[0]) ** 2 / (math.pi * atm.rfront[-1] ** 2) / math.pi
+    eI = (np.where(rho2 < 1.0, np.interp(m, mu, fI), 0.0) * area).reshape(npix, sub, npix, sub).sum(axis=(1, 3))
+    eQ = (np.where(rho2 < 1.0, np.interp(m, mu, fQ), 0.0) * area).reshape(npix, sub, npix, sub).sum(axis=(1, 3))
+    pc = 0.5 * (np.linspace(-xm, xm, npix + 1)[1:] + np.linspace(-xm, xm, npix + 1)[:-1]) / atm.rfront[-1]
+    X, Y = np.meshgrid(pc, pc)                                   # det[.., iy, ix]
+    ring = np.minimum((5.0 * (X ** 2 + Y ** 2)).astype(int), 5)
+    chi = np.arctan2(Y, X)
+    Qr = Q * np.cos(2.0 * chi) + U * np.sin(2.0 * chi)           # radial Stokes parameter from the detector-frame Q, U as the reference stores them
+    rI = [I[ring == k].sum() / eI[ring == k].sum() for k in range(5)]
+    pol = [Qr[ring == k].sum() / I[ring == k].sum() for k in range(5)]
+    pol_expected = [eQ[ring == k].sum() / eI[ring == k].sum() for k in range(5)]
+    return math.pi * I.sum(), float(np.sum(w * fI * 2.0 * mu)), ag_scalar, rI, pol, pol_expected
+
+
+def test_rayleigh_vector_invariance_anchor():
+    """POLARISED multiple scattering against an independent numerical solution: the 3 x 3 reflection matrix of the semi-infinite Rayleigh
+    atmosphere (omega = 0.9) from the invariance equation in Chandrasekhar's (I_l, I_r, U) representation.  The matrix machinery is checked
+    first with an unpolarising scatterer (it must reproduce the scalar solver).  Polarisation raises the geometric albedo from 0.3657
+    (scalar theory) to 0.3999 and polarises the limb RADIALLY at full phase (up to 7 % -- single scattering gives exactly zero there): the
+    oracle must show both.  A wrong sign in polarization_rotation (:1663-2052) or in the Mueller product lands on the scalar value or
+    beyond and flips or kills the limb polarisation."""
+    ray = lambda c: 0.75 * (1.0 + c * c)
+    mu, w, S, n_phi = vector_reflection_semi_infinite(0.9, n_mu=12, unpolarising=ray)
+    f = vector_backscatter(mu, S, n_phi)
+    mus, ws, Ss = reflection_semi_infinite(ray, 0.9, n_mu=12, m_max=4)
+    assert np.max(np.abs((f[:, 0] + f[:, 1]) / backscatter_brightness(mus, Ss) - 1.0)) < 1e-9
+    ag, ag_vector, ag_scalar, rI, pol, pol_expected = rayleigh_absorbing_observables(_oracle_runner, 150000)
+    assert abs(ag_vector - 0.39990) < 2e-5 and abs(ag_scalar - 0.36571) < 2e-5
+    assert abs(ag / ag_vector - 1.0) < 0.01, (ag, ag_vector)
+    for k in range(5):
+        assert abs(rI[k] - 1.0) < (0.03 if k < 4 else 0.05), (k, rI[k])
+        assert abs(pol[k] - pol_expected[k]) < 0.008, (k, pol[k], pol_expected[k])
+    assert pol_expected[4] > 0.06 and pol[4] > 0.05                # radial, and strongest in the limb ring
+
+
 def test_host_photometry_and_error_planes_match_oracle_restatement():
     """The tail of radiative_transfer (:957-1004) and the error planes of write_output (:3481-3519): the Python host
     mirror (artes_b200/host.py, which the driver tests compare bin/ARTES with) against the oracle's restatement, on

@@ -422,7 +422,7 @@ def lambert_sphere():
     return b.finish("lambert_sphere", artes_in=_artes_in(**{"planet:surface_albedo": "1"}))
 
 
-def rayleigh_deep(tau=32.0, nr=8, thickness=8e3):
+def rayleigh_deep(tau=32.0, nr=8, thickness=8e3, omega=1.0):
     """Literature anchor: a homogeneous, conservative Rayleigh atmosphere of radial optical depth `tau` over a white
     Lambert surface (planet:surface_albedo=1, cell_depth 0) -- for tau >~ 30 the conservative semi-infinite Rayleigh
     planet of Prather (1974) / Buenzli & Schmid (2009): geometric albedo 0.7975 with polarisation (0.75 without),
@@ -433,6 +433,9 @@ def rayleigh_deep(tau=32.0, nr=8, thickness=8e3):
     atm = b.finish("rayleigh_deep", artes_in=_artes_in(**{"planet:surface_albedo": "1"}))
     atm.k_sca = atm.k_sca * (tau / atm.radial_tau())
     atm.k_abs = atm.k_abs * 0.0
+    if omega < 1.0:      # the same with absorption: single-scattering albedo omega at the same total optical depth
+        atm.k_abs = atm.k_sca * (1.0 - omega)
+        atm.k_sca = atm.k_sca * omega
     return atm
 
 
