@@ -444,6 +444,20 @@ def test_rayleigh_vector_invariance_anchor():
     assert pol_expected[4] > 0.06 and pol[4] > 0.05                # radial, and strongest in the limb ring
 
 
+def test_vector_invariance_solver_reaches_the_literature_value():
+    """The reference solution itself against the literature: towards the conservative limit the geometric albedo of the semi-infinite
+    Rayleigh atmosphere behaves as A(1) - b sqrt(1 - omega) + c (1 - omega); the 3 x 3 solver at omega = 0.99, 0.999, 0.9999 extrapolates to
+    0.7976 -- Prather (1974) / Buenzli & Schmid (2009): 0.7975 (scalar theory: 0.7506)."""
+    s, a = [], []
+    for om in (0.99, 0.999, 0.9999):
+        mu, w, S, n_phi = vector_reflection_semi_infinite(om, n_mu=12, tol=1e-10)
+        f = vector_backscatter(mu, S, n_phi)
+        s.append(math.sqrt(1.0 - om))
+        a.append(float(np.sum(w * (f[:, 0] + f[:, 1]) * 2.0 * mu)))
+    a1 = np.linalg.solve(np.array([[1.0, -x, x * x] for x in s]), np.array(a))[0]
+    assert abs(a1 - 0.7975) < 1e-3, a1
+
+
 def test_host_photometry_and_error_planes_match_oracle_restatement():
     """The tail of radiative_transfer (:957-1004) and the error planes of write_output (:3481-3519): the Python host
     mirror (artes_b200/host.py, which the driver tests compare bin/ARTES with) against the oracle's restatement, on
