@@ -317,3 +317,26 @@ def test_rayleigh_vector_invariance_anchor_on_gpu():
         for k in range(5):
             assert abs(rI[k] - 1.0) < tol_ring * (1.0 if k < 4 else 1.6), (mode, k, rI[k])
             assert abs(pol[k] - pol_expected[k]) < tol_pol, (mode, k, pol[k], pol_expected[k])
+
+
+def test_rayleigh_polarised_phase_curve_anchor_on_gpu():
+    """The polarised phase-curve anchor of tests/test_oracle.py on the product (fast mode, 2e6 packets per angle): disk-integrated brightness
+    and degree of polarisation of the semi-infinite Rayleigh planet (omega = 0.9) at 60 / 90 / 120 deg against the invariance-equation solution."""
+    from artes_b200.lib import GpuTransport
+    from test_oracle import rayleigh_disk_theory, rayleigh_phase_points
+
+    def runner(atm, L):
+        g = GpuTransport((0,))
+        g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+        g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)
+        L.mode = abi.MODE_FAST
+        r = g.run(L)
+        g.close()
+        return r
+    th = rayleigh_disk_theory([math.radians(a) for a in (60.0, 90.0, 120.0)], 0.9)
+    got = rayleigh_phase_points(runner, 2000000)
+    print("rayleigh omega 0.9 phase points (pi I / n, P, U / I):", got, "theory (.., Q / I, U / I):", th)
+    for (i, p, u), (ti, tq, _) in zip(got, th):
+        assert abs(i / ti - 1.0) < 0.006, (i, ti)
+        assert abs(p - (-tq)) < 0.004, (p, -tq)
+        assert abs(u) < 0.003

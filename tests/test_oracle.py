@@ -444,6 +444,78 @@ def test_rayleigh_vector_invariance_anchor():
     assert pol_expected[4] > 0.06 and pol[4] > 0.05                # radial, and strongest in the limb ring
 
 
+def rayleigh_disk_theory(alphas, omega, n_mu=24, nq=64):
+    """Disk-integrated (geometric albedo x phase function, Q / I, U / I) of the semi-infinite Rayleigh planet at the phase angles `alphas` [rad]
+    from the 3 x 3 invariance-equation solution: at every point of the lit and visible crescent the reflected (I_l, I_r, U) for unpolarised
+    sunlight (the azimuth dependence of S is a trigonometric polynomial of order 2: exact from the 8 solved azimuths; cubic splines in mu, mu0),
+    rotated from the local meridian frame to the frame of the planet's scattering plane (l' = c l + s r with c = l.l', s = r.l':
+    Q' = (c^2 - s^2) Q + 2 c s U), integrated with the projected area.  Q < 0: polarised perpendicular to the scattering plane."""
+    from scipy.interpolate import RectBivariateSpline
+    mu, w, S, M = vector_reflection_semi_infinite(omega, n_mu=n_mu)
+    n = len(mu)
+    v = np.einsum('ijkab,b->iajk', S.reshape(n, M, 3, n, M, 3)[:, :, :, :, 0, :], np.array([0.5, 0.5, 0.0]))     # [i, i0, j, k]: incident azimuth 0
+    v = v * (1.0 / mu[:, None, None, None] + 1.0 / mu[None, :, None, None])                                          # smooth in (mu, mu0)
+    F = np.fft.rfft(v, axis=2) / M
+    spl = {(m, k, c): RectBivariateSpline(mu, mu, (F[:, :, m, k].real, F[:, :, m, k].imag)[c]) for m in range(3) for k in range(3) for c in (0, 1)}
+    x, wq = np.polynomial.legendre.leggauss(nq)
+    out = []
+    for alpha in alphas:
+        o = np.array([1.0, 0.0, 0.0])                                  # towards the observer
+        st_ = np.array([math.cos(alpha), math.sin(alpha), 0.0])        # towards the star
+        lam = 0.5 * (x + 1.0) * (math.pi - alpha) + (alpha - 0.5 * math.pi)
+        LAM, PSI = np.meshgrid(lam, 0.5 * math.pi * x)
+        WW = (0.5 * math.pi * wq)[:, None] * (0.5 * (math.pi - alpha) * wq)[None, :]
+        nrm = np.stack([np.cos(PSI) * np.cos(LAM), np.cos(PSI) * np.sin(LAM), np.sin(PSI)], axis=-1)
+        m_, m0 = nrm @ o, nrm @ st_
+        e1 = o[None, None, :] - m_[..., None] * nrm
+        e1 /= np.linalg.norm(e1, axis=-1, keepdims=True)               # local azimuth 0 = the outgoing direction
+        e2 = np.cross(nrm, e1)
+        dphi = -np.arctan2(e2 @ (-st_), e1 @ (-st_))                   # phi_out - phi_in of the propagation directions
+        vec = np.zeros(m_.shape + (3,))
+        for k in range(3):
+            acc = spl[(0, k, 0)].ev(m_, m0)
+            for m in (1, 2):
+                acc = acc + 2.0 * (spl[(m, k, 0)].ev(m_, m0) * np.cos(m * dphi) - spl[(m, k, 1)].ev(m_, m0) * np.sin(m * dphi))
+            vec[..., k] = acc / (1.0 / m_ + 1.0 / m0) / (4.0 * m_)
+        l = m_[..., None] * e1 - np.sqrt(np.clip(1.0 - m_ * m_, 0.0, None))[..., None] * nrm      # d/dtheta at o, theta from the local normal
+        lp = st_ - (st_ @ o) * o
+        lp /= np.linalg.norm(lp)                                       # l' in the scattering plane, perpendicular to o
+        c, sn = l @ lp, e2 @ lp
+        I, Q, U = vec[..., 0] + vec[..., 1], vec[..., 0] - vec[..., 1], vec[..., 2]
+        area = m_ * np.cos(PSI) * WW / math.pi
+        tot = float(np.sum(I * area))
+        out.append((tot, float(np.sum(((c * c - sn * sn) * Q + 2.0 * c * sn * U) * area)) / tot,
+                    float(np.sum((-2.0 * c * sn * Q + (c * c - sn * sn) * U) * area)) / tot))
+    return out
+
+
+def rayleigh_phase_points(runner, n, alphas_deg=(60.0, 90.0, 120.0), omega=0.9, seed=3):
+    """[(pi I / n, -Q / I, U / I)] of A.rayleigh_deep(omega) at the given phase angles (1 x 1 detector; the reference stores -Q, :4956)"""
+    atm = A.rayleigh_deep(omega=omega)
+    xm = 1.3 * atm.rfront[-1]
+    out = []
+    for adeg in alphas_deg:
+        L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=seed, surface_albedo=1.0, det_phi=math.radians(adeg), nx=1, ny=1, fstop=1e-7)
+        r = runner(atm, L)
+        assert int(r["err"].sum()) == 0
+        i, q, u = (r["det"][0, k].sum() / n for k in range(3))
+        out.append((math.pi * i, -q / i, u / i))
+    return out
+
+
+def test_rayleigh_polarised_phase_curve_anchor():
+    """The disk-integrated brightness and degree of polarisation of the semi-infinite Rayleigh planet (omega = 0.9) at 60 / 90 / 120 deg phase
+    angle against the 3 x 3 invariance-equation solution integrated over the crescent: 0.1772 / 0.0876 / 0.0414 and P = 37.2 / 57.3 / 37.4 %,
+    perpendicular to the scattering plane, U = 0.  (At alpha -> 0 the same integral returns the geometric albedo 0.3999 and P = 0.)"""
+    th = rayleigh_disk_theory([1e-6] + [math.radians(a) for a in (60.0, 90.0, 120.0)], 0.9)
+    assert abs(th[0][0] - 0.39990) < 1e-4 and abs(th[0][1]) < 1e-6
+    assert abs(-th[2][1] - 0.5732) < 5e-4 and all(abs(t[2]) < 1e-9 for t in th)
+    for (i, p, u), (ti, tq, _) in zip(rayleigh_phase_points(_oracle_runner, 100000), th[1:]):
+        assert abs(i / ti - 1.0) < 0.02, (i, ti)
+        assert abs(p - (-tq)) < 0.012, (p, -tq)
+        assert abs(u) < 0.01
+
+
 def test_vector_invariance_solver_reaches_the_literature_value():
     """The reference solution itself against the literature: towards the conservative limit the geometric albedo of the semi-infinite
     Rayleigh atmosphere behaves as A(1) - b sqrt(1 - omega) + c (1 - omega); the 3 x 3 solver at omega = 0.99, 0.999, 0.9999 extrapolates to
