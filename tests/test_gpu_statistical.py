@@ -340,3 +340,26 @@ def test_rayleigh_polarised_phase_curve_anchor_on_gpu():
         assert abs(i / ti - 1.0) < 0.006, (i, ti)
         assert abs(p - (-tq)) < 0.004, (p, -tq)
         assert abs(u) < 0.003
+
+
+def test_polarising_henyey_greenstein_invariance_anchor_on_gpu():
+    """The polarised, anisotropic anchor of tests/test_oracle.py on the product (fast mode, 2e6 packets): the cloud species of C2 (g = 0.5,
+    p_linear = 0.5, omega = 0.9) against the 4 x 4 invariance-equation solution for its tabulated matrix: geometric albedo 0.1932, ring
+    brightness, radial limb polarisation 0.5 .. 7.5 % at full phase."""
+    from artes_b200.lib import GpuTransport
+    from test_oracle import polarising_hg_observables
+
+    def runner(atm, L):
+        g = GpuTransport((0,))
+        g.set_grid(atm.rfront, atm.thetafront(), atm.thetaplane(), atm.phifront())
+        g.set_wavelength(atm.k_sca[0], atm.k_abs[0], atm.uniq[0], atm.cell_to_uniq[0], 0)
+        L.mode = abi.MODE_FAST
+        r = g.run(L)
+        g.close()
+        return r
+    ag, ag_expected, rI, pol, pol_expected = polarising_hg_observables(runner, 2000000)
+    print("polarising hg", "A_g", ag, "expected", ag_expected, "rings", rI, "Q_r/I", pol, "expected", pol_expected)
+    assert abs(ag / ag_expected - 1.0) < 0.006, ag
+    for k in range(5):
+        assert abs(rI[k] - 1.0) < 0.015 * (1.0 if k < 4 else 1.6), (k, rI[k])
+        assert abs(pol[k] - pol_expected[k]) < (0.003 if k < 4 else 0.005), (k, pol[k], pol_expected[k])

@@ -516,6 +516,152 @@ def test_rayleigh_polarised_phase_curve_anchor():
         assert abs(u) < 0.01
 
 
+def general_phase_blocks(mu_o, phi_o, s_out, mu_i, phi_i, s_in, Fmat):
+    """4 x 4 phase-matrix blocks Z[a, b] in the (I, Q, U, V) representation w.r.t. the meridian frames (l = d/dtheta, r = d/dphi, l x r = k) for
+    the propagation directions out_a = (s_out mu_o[a], phi_o[a]), in_b = (s_in mu_i[b], phi_i[b]): rotation of the incident Stokes vector into the
+    scattering plane (r_s = k_in x k_out / |..|, l_s = r_s x k), the scattering matrix F(cos Theta) of a macroscopically isotropic, mirror-symmetric
+    medium [[F11 F12 0 0] [F12 F22 0 0] [0 0 F33 F34] [0 0 -F34 F44]], rotation into the meridian frame of the new direction.  Every rotation
+    angle comes from dot products of unit vectors (for l' = c l + s r: Q' = (c^2 - s^2) Q + 2 c s U, U' = -2 c s Q + (c^2 - s^2) U)."""
+    def frame(mu, phi, sgn):
+        ct, st = sgn * mu, np.sqrt(1.0 - mu * mu)
+        return (np.stack([ct * np.cos(phi), ct * np.sin(phi), -st], axis=-1), np.stack([-np.sin(phi), np.cos(phi), np.zeros_like(phi)], axis=-1),
+                np.stack([st * np.cos(phi), st * np.sin(phi), ct], axis=-1))
+    lo, ro, ko = frame(mu_o, phi_o, s_out)
+    li, ri, ki = frame(mu_i, phi_i, s_in)
+    shape = (len(mu_o), len(mu_i), 3)
+    KI, LI, RI = (np.broadcast_to(v[None, :, :], shape) for v in (ki, li, ri))
+    KO, LO = (np.broadcast_to(v[:, None, :], shape) for v in (ko, lo))
+    ct = np.clip(np.sum(KI * KO, axis=-1), -1.0, 1.0)
+    rs = np.cross(KI, KO)
+    nrm = np.linalg.norm(rs, axis=-1)
+    deg = nrm < 1e-12                                                                # forward / backward: any plane through k_in will do
+    rs = np.where(deg[..., None], RI, rs / np.where(deg, 1.0, nrm)[..., None])
+    ls_i = np.cross(rs, KI)
+    ls_o = np.where(deg[..., None], np.where((ct < 0.0)[..., None], -ls_i, ls_i), np.cross(rs, KO))
+    c1, s1 = np.sum(ls_i * LI, axis=-1), np.sum(ls_i * RI, axis=-1)                   # l_s = c1 l + s1 r at k_in
+    c2, s2 = np.sum(LO * ls_o, axis=-1), np.sum(LO * rs, axis=-1)                    # l_out = c2 l_s + s2 r_s at k_out
+
+    def rot(c, s_):
+        R = np.zeros(c.shape + (4, 4))
+        R[..., 0, 0] = R[..., 3, 3] = 1.0
+        R[..., 1, 1] = R[..., 2, 2] = c * c - s_ * s_
+        R[..., 1, 2] = 2.0 * c * s_
+        R[..., 2, 1] = -2.0 * c * s_
+        return R
+    return rot(c2, s2) @ Fmat(ct) @ rot(c1, s1)
+
+
+def fourier_reflection(Fmat, omega, n_mu=24, n_phi=64, m_max=24, tol=1e-11):
+    """Reflection matrix of the semi-infinite atmosphere for a general scattering matrix: the invariance equation of
+    vector_reflection_semi_infinite per complex azimuthal Fourier component, S(mu, mu0, dphi) = sum_m S^m e^{i m dphi} (S^-m = conj S^m).
+    Returns (mu, weights, S^m[m, i, k, i0, k'] for m = 0 .. m_max)."""
+    x, w = np.polynomial.legendre.leggauss(n_mu)
+    mu, w = 0.5 * (x + 1.0), 0.5 * w
+    dphi = 2.0 * math.pi * np.arange(n_phi) / n_phi
+
+    def pm(s_out, s_in):          # (1/2pi) int Z(mu_a, dphi; mu_b, 0) e^{-i m dphi} ddphi
+        Z = omega * general_phase_blocks(np.repeat(mu, n_phi), np.tile(dphi, n_mu), s_out, mu, np.zeros(n_mu), s_in, Fmat)
+        Zm = np.fft.fft(Z.reshape(n_mu, n_phi, n_mu, 4, 4), axis=1) / n_phi
+        return np.stack([Zm[:, m].transpose(0, 2, 1, 3).reshape(4 * n_mu, 4 * n_mu) for m in range(m_max + 1)])
+    P_ud, P_dd, P_uu, P_du = pm(+1, -1), pm(-1, -1), pm(+1, +1), pm(-1, +1)
+    W4 = np.repeat(w / mu, 4)
+    inv = np.repeat(np.repeat(1.0 / (1.0 / mu[:, None] + 1.0 / mu[None, :]), 4, axis=0), 4, axis=1)
+    out = np.zeros((m_max + 1, n_mu, 4, n_mu, 4), dtype=complex)
+    for m in range(m_max + 1):
+        S = P_ud[m] * inv
+        for _ in range(20000):
+            SW = S * W4[None, :]
+            new = (P_ud[m] + 0.5 * SW @ P_dd[m] + 0.5 * (P_uu[m] * W4[None, :]) @ S + 0.25 * SW @ (P_du[m] * W4[None, :]) @ S) * inv
+            done = np.max(np.abs(new - S)) < tol
+            S = new
+            if done:
+                break
+        out[m] = S.reshape(n_mu, 4, n_mu, 4)
+    return mu, w, out
+
+
+def backscatter_stokes(mu, Sm):
+    """(I, Q, U, V) / F of the light reflected straight back (mu = mu0, dphi = pi) for unpolarised incident light; Q > 0: radial on the disk"""
+    res = np.zeros((len(mu), 4))
+    for i in range(len(mu)):
+        acc = Sm[0, i, :, i, 0].real.copy()
+        for m in range(1, Sm.shape[0]):
+            acc += 2.0 * (Sm[m, i, :, i, 0] * np.exp(1j * m * math.pi)).real
+        res[i] = acc / (4.0 * mu[i])
+    return res
+
+
+def tabulated_matrix(atm):
+    """F(cos Theta) of a homogeneous test atmosphere as the transport code sees it: the 180 one-degree bins of its matrix table, interpolated
+    linearly between the bin centres (matrix_at_deg, :4763-4810), normalised to (1/4pi) int F11 dOmega = 1"""
+    tab = np.asarray(atm.uniq[0]).reshape(-1, 180, 16)[np.asarray(atm.cell_to_uniq[0])[0]] * 4.0 * math.pi
+    centres = np.arange(180) + 0.5
+
+    def F(ct):
+        deg = np.degrees(np.arccos(np.clip(ct, -1.0, 1.0)))
+        out = np.zeros(ct.shape + (4, 4))
+        for (r, c), e in {(0, 0): 0, (0, 1): 1, (1, 0): 4, (1, 1): 5, (2, 2): 10, (2, 3): 11, (3, 2): 14, (3, 3): 15}.items():
+            out[..., r, c] = np.interp(deg, centres, tab[:, e])
+        return out
+    return F
+
+
+def polarising_hg_observables(runner, n, g=0.5, omega=0.9, p_linear=0.5, npix=31, seed=5):
+    """Full-phase image of A.hg_deep with the polarising Henyey-Greenstein matrix against the 4 x 4 invariance-equation solution for the
+    tabulated matrix: (geometric albedo, expected, measured / expected intensity in five rings, measured and expected radial polarisation)."""
+    atm = A.hg_deep(g=g, omega=omega, p_linear=p_linear)
+    xm = 1.3 * atm.rfront[-1]
+    L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=seed, surface_albedo=1.0, det_phi=math.radians(0.0573), nx=npix, ny=npix, fstop=1e-7)
+    r = runner(atm, L)
+    assert int(r["err"].sum()) == 0
+    I, Q, U = (r["det"][0, k] / n for k in range(3))
+    mu, w, Sm = fourier_reflection(tabulated_matrix(atm), omega)
+    bs = backscatter_stokes(mu, Sm)
+    assert np.max(np.abs(bs[:, 2:])) < 1e-9
+    sub = 8
+    edges = np.linspace(-xm, xm, npix * sub + 1)
+    c = 0.5 * (edges[1:] + edges[:-1]) / atm.rfront[-1]
+    rho2 = c[None, :] ** 2 + c[:, None] ** 2
+    m = np.sqrt(np.clip(1.0 - rho2, 0.0, None))
+    area = (edges[1] - edges[0]) ** 2 / (math.pi * atm.rfront[-1] ** 2) / math.pi
+    eI = (np.where(rho2 < 1.0, np.interp(m, mu, bs[:, 0]), 0.0) * area).reshape(npix, sub, npix, sub).sum(axis=(1, 3))
+    eQ = (np.where(rho2 < 1.0, np.interp(m, mu, bs[:, 1]), 0.0) * area).reshape(npix, sub, npix, sub).sum(axis=(1, 3))
+    pc = 0.5 * (np.linspace(-xm, xm, npix + 1)[1:] + np.linspace(-xm, xm, npix + 1)[:-1]) / atm.rfront[-1]
+    X, Y = np.meshgrid(pc, pc)
+    ring = np.minimum((5.0 * (X ** 2 + Y ** 2)).astype(int), 5)
+    chi = np.arctan2(Y, X)
+    Qr = Q * np.cos(2.0 * chi) + U * np.sin(2.0 * chi)
+    return (math.pi * I.sum(), float(np.sum(w * bs[:, 0] * 2.0 * mu)), [I[ring == k].sum() / eI[ring == k].sum() for k in range(5)],
+            [Qr[ring == k].sum() / I[ring == k].sum() for k in range(5)], [eQ[ring == k].sum() / eI[ring == k].sum() for k in range(5)])
+
+
+def test_polarising_henyey_greenstein_invariance_anchor():
+    """Polarised AND anisotropic: the cloud species of C2 (Henyey-Greenstein F11 with F12 = -p_linear F11 sin^2 / (1 + cos^2), F33 = F11 2 cos /
+    (1 + cos^2); g = 0.5, omega = 0.9) against the 4 x 4 invariance-equation solution for a general scattering matrix -- the Stokes vector is
+    rotated into the scattering plane, multiplied with F, rotated into the new meridian frame, all angles from dot products of unit vectors.
+    That machinery is checked first with the Rayleigh matrix against the field-projection solver (two formulations of the same physics:
+    1e-10).  Expected: geometric albedo 0.1932, radial limb polarisation 0.5 % (centre) to 7.5 % (limb) at full phase."""
+    def rayleigh_f(ct):
+        F = np.zeros(ct.shape + (4, 4))
+        F[..., 0, 0] = F[..., 1, 1] = 0.75 * (1.0 + ct * ct)
+        F[..., 0, 1] = F[..., 1, 0] = 0.75 * (ct * ct - 1.0)
+        F[..., 2, 2] = F[..., 3, 3] = 1.5 * ct
+        return F
+    mu, w, Sm = fourier_reflection(rayleigh_f, 0.9, n_mu=12, n_phi=16, m_max=4)
+    b = backscatter_stokes(mu, Sm)
+    mu2, _, S2, n_phi = vector_reflection_semi_infinite(0.9, n_mu=12)
+    f2 = vector_backscatter(mu2, S2, n_phi)
+    assert np.max(np.abs(b[:, 0] / (f2[:, 0] + f2[:, 1]) - 1.0)) < 1e-9 and np.max(np.abs(b[:, 1] - (f2[:, 0] - f2[:, 1]))) < 1e-10
+    assert np.max(np.abs(Sm[3:])) < 1e-12                            # Rayleigh scattering has azimuthal orders 0, 1, 2 only
+    ag, ag_expected, rI, pol, pol_expected = polarising_hg_observables(_oracle_runner, 150000)
+    assert abs(ag_expected - 0.19319) < 5e-5
+    assert abs(ag / ag_expected - 1.0) < 0.012, (ag, ag_expected)
+    for k in range(5):
+        assert abs(rI[k] - 1.0) < (0.03 if k < 4 else 0.05), (k, rI[k])
+        assert abs(pol[k] - pol_expected[k]) < (0.008 if k < 4 else 0.012), (k, pol[k], pol_expected[k])
+    assert pol_expected[4] > 0.07 and pol[4] > 0.06
+
+
 def test_vector_invariance_solver_reaches_the_literature_value():
     """The reference solution itself against the literature: towards the conservative limit the geometric albedo of the semi-infinite
     Rayleigh atmosphere behaves as A(1) - b sqrt(1 - omega) + c (1 - omega); the 3 x 3 solver at omega = 0.99, 0.999, 0.9999 extrapolates to

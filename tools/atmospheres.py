@@ -456,14 +456,15 @@ def isotropic_deep(tau=32.0, nr=8, thickness=8e3, omega=1.0, ntheta=1, nphi=1):
     return atm
 
 
-def hg_deep(g=0.5, omega=0.9, tau=32.0, nr=8, thickness=8e3):
+def hg_deep(g=0.5, omega=0.9, tau=32.0, nr=8, thickness=8e3, p_linear=0.0):
     """Numerical-solution anchor for ANISOTROPIC multiple scattering: a homogeneous atmosphere of radial optical depth `tau` with an
     unpolarising Henyey-Greenstein phase function (p_linear = 0: F12 = 0, so unpolarised light stays unpolarised and scalar transfer
     theory is exact) and single-scattering albedo `omega`; semi-infinite for tau >~ 30 (tests/test_oracle.py solves Ambartsumian's
-    invariance equation for its reflection function)."""
+    invariance equation for its reflection function).  p_linear > 0: the polarising Henyey-Greenstein matrix of
+    python/opacityHenyeyGreenstein.py:75-93 (the cloud species of C2): the 4 x 4 solver of tests/test_oracle.py applies."""
     rfront = R_JUP + np.linspace(0.0, thickness, nr + 1)
     b = _Builder(rfront, [0.0, 180.0], [0.0], [0.7])
-    b.add_region(henyey_greenstein([0.7], g=g, p_linear=0.0), 1.0, (0, nr), (0, 1), (0, 1))
+    b.add_region(henyey_greenstein([0.7], g=g, p_linear=p_linear), 1.0, (0, nr), (0, 1), (0, 1))
     atm = b.finish("hg_deep", artes_in=_artes_in(**{"planet:surface_albedo": "1"}))
     atm.k_abs = atm.k_abs * 0.0
     atm.k_sca = atm.k_sca * (tau / atm.radial_tau())
