@@ -1,7 +1,10 @@
 // artes_oracle.cc -- CPU restatement of the ARTES photon-packet transport loop.
 //
 // TEST INFRASTRUCTURE ONLY (see artes_oracle.h).  PARITY UNPINNED: no golden vectors exist in
-// the reference and it cannot be compiled here (no Fortran compiler).
+// the reference and it cannot be compiled here (no Fortran compiler).  What stands in for the pin (tests/test_oracle.py, DESIGN.md
+// section 2): Chandrasekhar's exact solution of the semi-infinite isotropic atmosphere, and numerical solutions of the invariance
+// equation for anisotropic (Henyey-Greenstein), polarised (Rayleigh) and polarised anisotropic scattering -- geometric albedo, limb
+// darkening, radial limb polarisation, the polarised phase curve -- which this restatement reproduces to its Monte Carlo noise.
 //
 // Every function cites the src/ARTES.f90 range it follows.  Arithmetic is IEEE double in the
 // reference's operation order; build with -ffp-contract=off (gfortran -O3 on generic x86-64
