@@ -662,6 +662,24 @@ def test_polarising_henyey_greenstein_invariance_anchor():
     assert pol_expected[4] > 0.07 and pol[4] > 0.06
 
 
+def test_limb_biased_emission_against_the_crescent_solution():
+    """Phase angles >= 170 deg are run with limb-biased emission (packets start on the outer 19 % of the disk only, :1041-1055) and a package
+    energy scaled by that area fraction (:2526-2530).  At 172.5 deg the thin crescent of the semi-infinite Rayleigh planet (omega = 0.9) has, from
+    the invariance-equation solution, a brightness of 5.77e-4 and a NEGATIVE polarisation (parallel to the scattering plane: multiple scattering
+    wins over the vanishing single-scattering polarisation near forward scattering), P = -1.7 %."""
+    adeg = 172.5
+    (ti, tq, _), = rayleigh_disk_theory([math.radians(adeg)], 0.9)
+    assert abs(ti - 5.7708e-4) < 2e-7 and abs(-tq - (-0.0171)) < 3e-4
+    atm = A.rayleigh_deep(omega=0.9)
+    xm = 1.3 * atm.rfront[-1]
+    n = 200000
+    L = make_launch(n_photons=n, x_max=xm, y_max=xm, seed=3, surface_albedo=1.0, det_phi=math.radians(adeg), nx=1, ny=1, fstop=1e-7, limb_emission=1)
+    r = _oracle_runner(atm, L)
+    i, q, u = (r["det"][0, k].sum() / n for k in range(3))
+    assert abs(0.19 * math.pi * i / ti - 1.0) < 0.04, (0.19 * math.pi * i, ti)        # sigma ~ 1.5 % at 2e5 packets
+    assert -0.035 < -q / i < -0.005 and abs(u / i) < 0.015, (-q / i, u / i)
+
+
 def test_vector_invariance_solver_reaches_the_literature_value():
     """The reference solution itself against the literature: towards the conservative limit the geometric albedo of the semi-infinite
     Rayleigh atmosphere behaves as A(1) - b sqrt(1 - omega) + c (1 - omega); the 3 x 3 solver at omega = 0.99, 0.999, 0.9999 extrapolates to
